@@ -1,0 +1,200 @@
+"""Generates the committed golden vectors under tests/golden/ by running the
+UNMODIFIED reference (`/root/reference`, imported through
+`oracle/reference_shim.py`) on CPU, torch 2.11.0, in the build container.
+
+    python tests/golden/make_golden.py
+
+The GPU box has no reference tree, so these files are what pins the oracle
+(`oracle/restated.py`) and, through it, the CUDA path.  Inputs are stored in
+the fixtures next to the outputs, so they do not depend on the generator.
+"""
+import hashlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "unsupervised-pseuso-lidar_b200"))
+
+from plb200 import synth  # noqa: E402
+from oracle import reference_shim  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _flatten_inputs(inp):
+    d = {"tgt": _np(inp["tgt"]), "poses": _np(inp["poses"]), "K": _np(inp["intrinsics"])}
+    for i, r in enumerate(inp["ref_imgs"]):
+        d["ref%d" % i] = _np(r)
+    for f, frame in enumerate(inp["disparity"]):
+        for s, t in enumerate(frame):
+            d["disp_f%d_s%d" % (f, s)] = _np(t)
+    return d
+
+
+def live_case(ref, name, B, H, W, n_scales, seed, regime):
+    """`Losses.forward` + `sum(loss).backward()` exactly as `trainer.py:312,264`."""
+    inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=n_scales, seed=seed, regime=regime)
+    disp = [[t.clone().requires_grad_(True) for t in frame] for frame in inp["disparity"]]
+    poses = inp["poses"].clone().requires_grad_(True)
+    tgt = inp["tgt"].clone().requires_grad_(True)
+    refs = [r.clone().requires_grad_(True) for r in inp["ref_imgs"]]
+    L = ref.Losses()
+    with reference_shim.quiet():
+        loss = L.forward(tgt, refs, disp, poses, inp["intrinsics"], None)
+    sum(loss).backward()
+    out = _flatten_inputs(inp)
+    out["loss_mam"] = _np(loss[0])
+    out["loss_smooth"] = _np(loss[1])
+    out["g_poses"] = _np(poses.grad)
+    out["g_tgt"] = _np(tgt.grad)
+    for i, r in enumerate(refs):
+        out["g_ref%d" % i] = _np(r.grad)
+    for f, frame in enumerate(disp):
+        for s, t in enumerate(frame):
+            out["g_disp_f%d_s%d" % (f, s)] = _np(t.grad)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, float(loss[0]), float(loss[1]))
+
+
+def warp_case(ref, name, B, H, W, seed):
+    """`inverse_warp` forward and vjp against a fixed cotangent, both pose_inv."""
+    inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=1, seed=seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    cot = torch.randn(B, 3, H, W, generator=gen)
+    out = {"K": _np(inp["intrinsics"]), "cot": _np(cot)}
+    depth0 = 1.0 / (10 * inp["disparity"][0][0] + 0.01)
+    out["img"] = _np(inp["ref_imgs"][0])
+    out["depth"] = _np(depth0)
+    out["pose"] = _np(inp["poses"][:, 0])
+    for inv in (False, True):
+        img = inp["ref_imgs"][0].clone().requires_grad_(True)
+        depth = depth0.clone().requires_grad_(True)
+        pose = inp["poses"][:, 0].clone().requires_grad_(True)
+        proj = ref.inverse_warp(img, depth, pose, inp["intrinsics"], inv)
+        (proj * cot).sum().backward()
+        tag = "inv" if inv else "fwd"
+        out["proj_" + tag] = _np(proj)
+        out["g_img_" + tag] = _np(img.grad)
+        out["g_depth_" + tag] = _np(depth.grad)
+        out["g_pose_" + tag] = _np(pose.grad)
+    # pose helper functions
+    rot, trans = inp["poses"][:, 0, :3].unsqueeze(1), inp["poses"][:, 0, 3:].unsqueeze(1)
+    M = ref.transformation_from_parameters(rot, trans)
+    out["M_axisangle"] = _np(M)
+    out["M_inverted"] = _np(ref.invert_pose(M))
+    out["M_euler"] = _np(ref.pose_vec2mat(inp["poses"][:, 0], "euler"))
+    # Transform.reconstruct / project
+    t = ref.Transform()
+    Xc = t.reconstruct(depth0[:, 0], inp["intrinsics"])
+    out["Xc"] = _np(Xc)
+    out["grid"] = _np(t.project(Xc, inp["intrinsics"], M))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok")
+
+
+def dormant_case(ref, name, B, H, W, n_scales, seed):
+    """SSIM, photometric mix (+clip), and the min-reprojection/automask
+    composition assembled from the reference's own functions the way
+    `notes/toy_problem/losses.py:107-129` composes them."""
+    inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=n_scales, seed=seed)
+    L = ref.Losses()
+    L.SSIM = ref.SSIM()
+    tgt, refs, K = inp["tgt"], inp["ref_imgs"], inp["intrinsics"]
+    out = _flatten_inputs(inp)
+    out["ssim_ref0_tgt"] = _np(L.SSIM.standard_loss(refs[0], tgt))
+    out["photo_clip_ref0_tgt"] = _np(L.compute_photometric_loss(refs[0], tgt))
+    out["photo_clip_nossim_ref0_tgt"] = _np(L.compute_photometric_loss(refs[0], tgt, no_ssim=True))
+
+    def photo_noclip(pred, target, no_ssim=False):
+        l1 = torch.abs(target - pred)
+        return l1 if no_ssim else 0.85 * L.SSIM.standard_loss(pred, target) + 0.15 * l1
+
+    import torch.nn.functional as F
+    for variant, photo in (("clip", L.compute_photometric_loss), ("noclip", photo_noclip)):
+        for automask in (True, False):
+            disp = [t.clone().requires_grad_(True) for t in inp["disparity"][0]]
+            poses = inp["poses"].clone().requires_grad_(True)
+            srcs = [r.clone().requires_grad_(True) for r in refs]
+            depths = ref.disp_to_depth([disp])[0]
+            total = 0
+            auto = [photo(r, tgt) for r in srcs]
+            for D in depths:
+                if D.shape[-1] != W:
+                    D = F.interpolate(D, [H, W], mode="bilinear", align_corners=False)
+                D = D.squeeze(1)
+                rp = [photo(ref.inverse_warp(r, D, poses[:, i, :], K, False), tgt)
+                      for i, r in enumerate(srcs)]
+                min_rpl = torch.minimum(rp[0], rp[1])
+                if automask:
+                    min_auto = torch.minimum(auto[0], auto[1])
+                    mu = torch.where(min_rpl < min_auto, torch.tensor([1.]), torch.tensor([0.]))
+                    min_rpl = mu * min_rpl
+                m, _ = torch.max(min_rpl, dim=1)
+                total = total + m.mean(1).mean(-1).mean()
+            total = total / len(depths)
+            total.backward()
+            tag = "%s_%s" % (variant, "auto" if automask else "noauto")
+            out["loss_" + tag] = _np(total)
+            out["g_poses_" + tag] = _np(poses.grad)
+            for s, t in enumerate(disp):
+                out["g_disp_s%d_%s" % (s, tag)] = _np(t.grad)
+            for i, r in enumerate(srcs):
+                out["g_ref%d_%s" % (i, tag)] = _np(r.grad)
+            print(name, tag, float(total))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
+def cloud_case(ref, name):
+    """`PseudoLiDAR.project_PL` on a small depth image (full cloud stored) and on
+    one full-resolution KITTI frame (count, checksums and a strided sample)."""
+    with tempfile.TemporaryDirectory() as d:
+        calib = synth.write_kitti_calib(d)
+        out = {}
+        small = synth.make_depth_images(1, 37, 124, seed=77, lo=0.5, hi=60.0)[0].numpy()
+        small[5, 7] = 0.0
+        small[6, 9] = -2.0
+        for sp in (0, 3):
+            pl = ref.PseudoLiDAR(calib, sp)
+            cloud = pl.project_PL(small)
+            out["small_cloud_sp%d" % sp] = cloud
+        out["small_depth"] = small
+        out["T"], out["P"] = pl.T, pl.P
+        full = synth.make_depth_images(1, 375, 1242, seed=78)[0].numpy()
+        pl = ref.PseudoLiDAR(calib, 0)
+        cloud = pl.project_PL(full)
+        out["full_seed"] = np.array(78)
+        out["full_count"] = np.array(cloud.shape[0])
+        out["full_colsum"] = cloud.sum(axis=0)
+        out["full_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(cloud).tobytes()).digest(), dtype=np.uint8)
+        out["full_sample"] = cloud[::997].copy()
+        cloud10 = ref.PseudoLiDAR(calib, 10).project_PL(full)
+        out["full_count_sp10"] = np.array(cloud10.shape[0])
+        print(name, cloud.shape, cloud10.shape, cloud.dtype)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(1)  # fixed reduction order for the committed vectors
+    ref = reference_shim.load(patch_batch=False)
+    live_case(ref, "live_b4_s1_32x48", 4, 32, 48, 1, seed=11, regime="trained")
+    live_case(ref, "live_b4_s4_32x64", 4, 32, 64, 4, seed=12, regime="trained")
+    live_case(ref, "live_b4_s1_init_24x40", 4, 24, 40, 1, seed=13, regime="init")
+    warp_case(ref, "warp_b4_24x40", 4, 24, 40, seed=21)
+    dormant_case(ref, "dormant_b4_s2_32x48", 4, 32, 48, 2, seed=31)
+    cloud_case(ref, "cloud_kitti")
+    ref = reference_shim.load(patch_batch=True)
+    live_case(ref, "live_b2_s2_32x48_patched", 2, 32, 48, 2, seed=14, regime="trained")
+    live_case(ref, "live_b3_s1_24x40_patched", 3, 24, 40, 1, seed=15, regime="trained")
+
+
+if __name__ == "__main__":
+    main()
