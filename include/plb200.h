@@ -1,0 +1,220 @@
+/*
+ * plb200.h - C ABI of libplb200.so: the B200 (sm_100a) implementation of the
+ * view-synthesis hot path of unsupervised-pseuso-LiDAR.
+ *
+ * The reference is pure Python over stock torch ops and has no FFI of its own
+ * (SURVEY.md section 0.1); the "interface each entry point replaces" is
+ * therefore the Python function named beside it (paths relative to the
+ * reference tree).  Every function
+ *   - takes plain device pointers, sizes and a cudaStream_t (passed as void*),
+ *   - never allocates, never synchronises, and is CUDA-graph capturable,
+ *   - returns 0 on success, a negative PLB_E* code for a bad argument, or a
+ *     positive cudaError_t if the launch failed.
+ * All image tensors are contiguous NCHW fp32 as `trainer.py:291-299` produces
+ * them; intrinsics may be fp64 (`dataloaders.py:98`) or fp32.
+ */
+#ifndef PLB200_H
+#define PLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLB_MAX_SRC 4
+#define PLB_MAX_SCALES 4
+#define PLB_MAX_JOBS 2
+
+#define PLB_OK 0
+#define PLB_EINVAL (-1)     /* bad shape / count / flag                     */
+#define PLB_ENULL (-2)      /* a required pointer is NULL                    */
+#define PLB_EWORKSPACE (-3) /* workspace missing or too small                */
+
+/* rotation_mode */
+#define PLB_ROT_AXISANGLE 0 /* live: transformation_from_parameters, geometry/pose_geometry.py:124-199 */
+#define PLB_ROT_EULER 1     /* dormant: pose_vec2mat / euler2mat, geometry/pose_geometry.py:38-108 */
+
+/* plb_photo_job.mode */
+#define PLB_PHOTO_L1_MEAN 0 /* live: nn.L1Loss per (scale, source), mean over sources: losses.py:223-228 */
+#define PLB_PHOTO_MIN_REPROJ 1 /* dormant: 0.85*SSIM+0.15*L1, per-pixel min over sources, automask,
+                                  max over channel: losses.py:12-84,94-96,154-162,
+                                  notes/toy_problem/losses.py:107-129 */
+/* plb_photo_job.flags (MIN_REPROJ mode) */
+#define PLB_PHOTO_NO_SSIM 1u
+#define PLB_PHOTO_NO_AUTOMASK 2u
+
+/*
+ * One "direction" of Losses.reprojection_loss (losses.py:190-228): a target
+ * frame, n_src source frames warped into it with one depth pyramid.
+ */
+typedef struct plb_photo_job {
+    const float* tgt;                   /* [B,3,H,W] target frame                                  */
+    const float* src[PLB_MAX_SRC];      /* [B,3,H,W] source frames                                 */
+    int32_t pose_index[PLB_MAX_SRC];    /* column of `poses` [B,n_pose,6] used for source i        */
+    int32_t pose_inv[PLB_MAX_SRC];      /* 1: invert_pose() the matrix (losses.py:202)             */
+    const float* disp[PLB_MAX_SCALES];  /* [B,1,dh,dw] disparity (or depth) pyramid of the target  */
+    int32_t dh[PLB_MAX_SCALES];
+    int32_t dw[PLB_MAX_SCALES];
+    float* g_disp[PLB_MAX_SCALES];      /* out (written): d loss / d disp[s]; NULL = not wanted    */
+    float* g_src[PLB_MAX_SRC];          /* out (ACCUMULATED, caller zeroes): d loss / d src[i]     */
+    float* g_tgt;                       /* out (ACCUMULATED, caller zeroes): d loss / d tgt        */
+    int32_t n_src;
+    int32_t n_scales;
+    float term_weight;                  /* weight of each (scale, source) mean in the final loss   */
+    int32_t mode;                       /* PLB_PHOTO_*                                             */
+    uint32_t flags;
+    int32_t reserved;
+} plb_photo_job;
+
+/*
+ * Fused photometric reprojection loss, forward (+ gradients in the same pass).
+ * Replaces Losses.reprojection_loss (losses.py:183-240) together with everything
+ * it calls: disp_to_depth (geometry/pose_geometry.py:70-95), F.interpolate of
+ * the low scales (losses.py:214-215), inverse_warp (geometry/pose_geometry.py:
+ * 201-228), Transform.reconstruct/project (geometry/transform.py:74-150),
+ * transformation_from_parameters / invert_pose (geometry/pose_geometry.py:
+ * 110-199), F.grid_sample and nn.L1Loss - and their autograd backward.
+ */
+typedef struct plb_photo_args {
+    int32_t B, H, W;
+    int32_t n_jobs;
+    int32_t n_pose;            /* poses is [B,n_pose,6] (rot3 | trans3)                           */
+    int32_t rotation_mode;     /* PLB_ROT_*                                                        */
+    int32_t k_is_f64;          /* intrinsics dtype                                                 */
+    int32_t input_is_depth;    /* 0: depth = 1/(disp_a*disp+disp_b); 1: `disp` already holds depth */
+    float disp_a, disp_b;      /* 10, 0.01 in the reference                                        */
+    int32_t want_grad;         /* 0: loss only (no_grad / eval)                                    */
+    int32_t deterministic;     /* 1: image gradients accumulate in 64-bit fixed point (see g_fix)  */
+    const float* poses;        /* [B,n_pose,6]                                                     */
+    const void* K;             /* [B,3,3] f64 or f32                                               */
+    float* g_poses;            /* out (written) [B,n_pose,6]; NULL = not wanted                    */
+    float* loss;               /* out (written) [1]                                                */
+    float* entry_loss;         /* out (written) [n_jobs*PLB_MAX_SCALES] per-(job,scale) means or NULL */
+    const float* upstream;     /* device scalar d L / d loss; NULL = 1                             */
+    const float* skip_if_unit; /* device ptr to skip_n floats or NULL: the launch returns at once
+                                  when all of them equal 1 (the gradients written by the forward
+                                  pass with unit upstream are then already exact) - see DESIGN.md  */
+    int32_t skip_n;
+    int32_t reserved;
+    void* workspace;           /* plb_photo_workspace_bytes() bytes, zero-filled ONCE by the caller */
+    size_t workspace_bytes;
+    plb_photo_job jobs[PLB_MAX_JOBS];
+} plb_photo_args;
+
+size_t plb_photo_workspace_bytes(const plb_photo_args* args);
+int plb_photo_loss(const plb_photo_args* args, void* stream);
+
+/*
+ * Second-order depth smoothness, forward + gradient in one pass.
+ * Replaces Losses.smooth_loss (losses.py:242-260) on the target-frame depth
+ * pyramid, with disp_to_depth folded in.
+ */
+typedef struct plb_smooth_args {
+    int32_t B;
+    int32_t n_scales;
+    const float* disp[PLB_MAX_SCALES];  /* [B,1,dh,dw]                                            */
+    int32_t dh[PLB_MAX_SCALES];
+    int32_t dw[PLB_MAX_SCALES];
+    float* g_disp[PLB_MAX_SCALES];      /* out; NULL = not wanted                                  */
+    int32_t accumulate;                 /* 1: g_disp += grad, 0: g_disp = grad                      */
+    int32_t input_is_depth;
+    float disp_a, disp_b;
+    float scale_decay;                  /* 2.3 in the reference (losses.py:259)                     */
+    int32_t want_grad;
+    float* loss;                        /* out (written) [1]                                        */
+    const float* upstream;              /* device scalar or NULL (=1)                               */
+    const float* skip_if_unit;          /* as in plb_photo_args                                     */
+    int32_t skip_n;
+    int32_t reserved;
+    void* workspace;                    /* plb_smooth_workspace_bytes() bytes, zero-filled once     */
+    size_t workspace_bytes;
+} plb_smooth_args;
+
+size_t plb_smooth_workspace_bytes(const plb_smooth_args* args);
+int plb_smooth_loss(const plb_smooth_args* args, void* stream);
+
+/*
+ * Stand-alone inverse warp (image out) and its vjp.
+ * Replaces inverse_warp (geometry/pose_geometry.py:201-228) incl. F.grid_sample
+ * (bilinear, zeros padding, align_corners=True).
+ */
+typedef struct plb_warp_args {
+    int32_t B, H, W;
+    int32_t rotation_mode;
+    int32_t pose_inv;
+    int32_t k_is_f64;
+    const float* img;          /* [B,3,H,W] source                                                */
+    const float* depth;        /* [B,H,W] depth of the target view                                */
+    const float* pose;         /* [B,6] (contiguous rows; row stride pose_stride floats)          */
+    int32_t pose_stride;
+    int32_t reserved;
+    const void* K;             /* [B,3,3]                                                          */
+    float* out;                /* fwd: [B,3,H,W] warped image                                      */
+    /* backward only */
+    const float* g_out;        /* [B,3,H,W] cotangent                                              */
+    float* g_img;              /* out (ACCUMULATED, caller zeroes) or NULL                         */
+    float* g_depth;            /* out (written) [B,H,W] or NULL                                    */
+    float* g_pose;             /* out (written) [B,6] or NULL                                      */
+    void* workspace;           /* plb_warp_workspace_bytes() bytes, zero-filled once (bwd only)    */
+    size_t workspace_bytes;
+} plb_warp_args;
+
+size_t plb_warp_workspace_bytes(const plb_warp_args* args);
+int plb_warp_forward(const plb_warp_args* args, void* stream);
+int plb_warp_backward(const plb_warp_args* args, void* stream);
+
+/* Transform.reconstruct (geometry/transform.py:74-105): Xc[B,3,H,W] = (K^-1 . pixel) * depth. */
+int plb_reconstruct(const float* depth, const void* K, int32_t k_is_f64, int32_t B, int32_t H,
+                    int32_t W, float* Xc, void* stream);
+/* Transform.project (geometry/transform.py:114-150): X[B,3,H,W], Tcw[B,4,4] -> grid[B,H,W,2] in [-1,1]. */
+int plb_project(const float* X, const void* K, int32_t k_is_f64, const float* Tcw, int32_t B,
+                int32_t H, int32_t W, float* grid, void* stream);
+/* pose [B,6] -> [B,4,4] (axis-angle: transformation_from_parameters, geometry/pose_geometry.py:124-136;
+ * euler: pose_vec2mat :97-108 padded with [0 0 0 1]); invert!=0 applies invert_pose (:110-115). */
+int plb_pose_matrix(const float* pose, int32_t pose_stride, int32_t B, int32_t rotation_mode,
+                    int32_t invert, float* M44, void* stream);
+/* vjp of plb_pose_matrix: g_M44 [B,4,4] -> g_pose [B,6]. */
+int plb_pose_matrix_backward(const float* pose, int32_t pose_stride, int32_t B, int32_t rotation_mode,
+                             int32_t invert, const float* g_M44, float* g_pose, void* stream);
+/* disp_to_depth (geometry/pose_geometry.py:70-95), elementwise; g != NULL also writes d depth/d disp. */
+int plb_disp_to_depth(const float* disp, int64_t n, float a, float b, float* depth, void* stream);
+int plb_disp_to_depth_backward(const float* disp, const float* g_depth, int64_t n, float a, float b,
+                               float* g_disp, void* stream);
+
+/*
+ * Depth image -> pseudo-LiDAR point cloud in the velodyne frame.
+ * Replaces PseudoLiDAR.project_PL (pseudo-lidar/utils/PseudoLiDAR.py:69-110),
+ * fp64 arithmetic in the reference's operation order, order-preserving
+ * compaction of the valid points, optional [0::sparsity] decimation.
+ */
+typedef struct plb_cloud_args {
+    int32_t B, H, W;           /* B independent depth images                                       */
+    int32_t sparsity;          /* 0 = keep all valid points, n = keep every n-th valid point       */
+    const float* depth;        /* [B,H,W] f32                                                      */
+    double P[12];              /* P_rect_02 3x4 row-major (PseudoLiDAR.py:60)                      */
+    double Tinv[16];           /* camera->velodyne 4x4 row-major exactly as inverse_rigid_trans builds
+                                  it (PseudoLiDAR.py:39-46): [R^T | -R^T t] with an ALL-ZERO last row  */
+    double* cloud_f64;         /* out [B, H*W, 4] f64 (parity layout) or NULL                      */
+    float* cloud_f32;          /* out [B, H*W, 4] f32 x,y,z,i (PointCloud2 layout,
+                                  PseudoLidarPipeline.py:51-54) or NULL                            */
+    int32_t* index;            /* out [B, H*W] row-major pixel index of each kept point, or NULL   */
+    uint8_t* valid;            /* out [B, H*W] mask (cloud_x>=0 & cloud_z<1) before decimation, or NULL */
+    int32_t* count;            /* out [B] number of points written per image                       */
+    void* workspace;           /* plb_cloud_workspace_bytes() bytes, zero-filled once              */
+    size_t workspace_bytes;
+} plb_cloud_args;
+
+size_t plb_cloud_workspace_bytes(const plb_cloud_args* args);
+int plb_cloud_project(const plb_cloud_args* args, void* stream);
+
+/* Library identification: "plb200 <version> sm_100a". */
+const char* plb_version(void);
+/* Number of kernel launches issued by this library since load (all entry points). */
+uint64_t plb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLB200_H */

@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads and exports every symbol include/plb200.h declares;
+argument validation returns error codes without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    import sys
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    from plb200 import _lib
+    return _lib
+
+
+def test_every_declared_symbol_is_exported(L):
+    header = open(os.path.join(ROOT, "include", "plb200.h")).read()
+    declared = set(re.findall(r"\b(plb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    for name in declared:
+        assert getattr(L.lib, name) is not None
+    assert "sm_100a" in L.version()
+
+
+def test_struct_sizes_match_header(L):
+    # compile a tiny C program against the header and compare sizeof()
+    import subprocess, tempfile
+    src = r'''
+    #include <stdio.h>
+    #include "plb200.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(plb_photo_job), sizeof(plb_photo_args),
+        sizeof(plb_smooth_args), sizeof(plb_warp_args), sizeof(plb_cloud_args)); return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    got = [ctypes.sizeof(t) for t in (L.PhotoJob, L.PhotoArgs, L.SmoothArgs, L.WarpArgs, L.CloudArgs)]
+    assert got == sizes, (got, sizes)
+
+
+def test_argument_validation_without_gpu(L):
+    a = L.PhotoArgs()
+    assert L.lib.plb_photo_loss(None, None) == -2
+    assert L.lib.plb_photo_loss(a, None) == -1          # B = 0
+    a.B, a.H, a.W, a.n_jobs, a.n_pose = 1, 8, 8, 1, 1
+    assert L.lib.plb_photo_loss(a, None) == -2          # poses NULL
+    s = L.SmoothArgs()
+    assert L.lib.plb_smooth_loss(s, None) == -1
+    c = L.CloudArgs()
+    assert L.lib.plb_cloud_project(c, None) == -1
+    c.B, c.H, c.W = 1, 4, 4
+    assert L.lib.plb_cloud_project(c, None) == -2
+    w = L.WarpArgs()
+    assert L.lib.plb_warp_forward(w, None) == -1
+    with pytest.raises(L.PlbError):
+        L.check(-3, "x")
+
+
+def test_ops_refuse_cpu_tensors(L):
+    import torch
+    from plb200 import ops, synth
+    inp = synth.make_photo_inputs(1, 8, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.fused_losses(inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"])
+    from geometry.pose_geometry import inverse_warp
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        inverse_warp(inp["tgt"], inp["disparity"][0][0], inp["poses"][:, 0], inp["intrinsics"], False)

@@ -1,0 +1,397 @@
+"""torch-facing host layer over the C ABI: autograd Functions and workspaces.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every
+computation is a libplb200.so kernel.  All ops require CUDA tensors and raise
+otherwise - there is no CPU path in the product.
+
+Gradient strategy (DESIGN.md "single-pass forward+backward"): the loss is a
+scalar whose gradients are linear in the upstream gradient g.  When gradients
+are needed the forward launch therefore also writes the gradients for g = 1
+(same memory pass: inputs are read once).  backward() relaunches the same
+kernels with the real upstream values and a device-side guard that makes the
+launch return at once when every upstream value is exactly 1 (the common
+`sum(loss).backward()`); any other upstream recomputes the gradients exactly.
+`fused_backward=False` (or image gradients being requested) selects the
+classic two-pass scheme: forward computes only the loss, backward recomputes.
+"""
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_ws_lock = threading.Lock()
+_ws_cache = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(tag, nbytes, device):
+    """Zero-filled once, then self-cleaning (kernels reset their tickets).
+    One buffer per (op, device, stream) so concurrent streams never share."""
+    key = (tag, device.index, _stream())
+    with _ws_lock:
+        buf = _ws_cache.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            _ws_cache[key] = buf
+    return buf
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("plb200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device.type)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _kc(K):
+    if K.dtype not in (torch.float64, torch.float32):
+        K = K.double()
+    return K.contiguous()
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class LossConfig:
+    """Static description of one fused-loss call (shapes, modes, weights)."""
+
+    def __init__(self, n_src, scales_per_frame, input_is_depth=False, do_photo=True, do_smooth=True,
+                 rotation_mode="axisangle", fused_backward=True, disp_a=10.0, disp_b=0.01, scale_decay=2.3,
+                 mode=_lib.PHOTO_L1_MEAN, flags=0):
+        self.n_src = n_src
+        self.scales_per_frame = list(scales_per_frame)  # e.g. [4, 4]: frames with a depth pyramid
+        self.input_is_depth = bool(input_is_depth)
+        self.do_photo, self.do_smooth = do_photo, do_smooth
+        self.rotation_mode = _lib.ROT_EULER if rotation_mode == "euler" else _lib.ROT_AXISANGLE
+        self.fused_backward = fused_backward
+        self.disp_a, self.disp_b, self.scale_decay = disp_a, disp_b, scale_decay
+        self.mode, self.flags = mode, flags
+
+
+def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt, g_refs, out, up2, skip):
+    """One photometric launch (all directions) + one smoothness launch.
+    out: float32[2] (loss_mam, loss_smooth).  up2: float32[2] upstream or None."""
+    dev = tgt.device
+    B, _, H, W = tgt.shape
+    st = _stream()
+    if cfg.do_photo:
+        a = _lib.PhotoArgs()
+        a.B, a.H, a.W = B, H, W
+        a.n_pose = poses.shape[1]
+        a.rotation_mode = cfg.rotation_mode
+        a.k_is_f64 = 1 if K.dtype == torch.float64 else 0
+        a.input_is_depth = int(cfg.input_is_depth)
+        a.disp_a, a.disp_b = cfg.disp_a, cfg.disp_b
+        a.want_grad = int(want_grad)
+        a.poses, a.K = poses.data_ptr(), K.data_ptr()
+        a.g_poses = _ptr(g_poses) if want_grad else 0
+        a.loss = out.data_ptr()
+        a.upstream = up2.data_ptr() if up2 is not None else 0
+        a.skip_if_unit = up2.data_ptr() if (up2 is not None and skip) else 0
+        a.skip_n = 2
+        n_jobs = len(pyr)
+        a.n_jobs = n_jobs
+        entries = sum(len(p) for p in pyr)
+        for j in range(n_jobs):
+            job = a.jobs[j]
+            if j == 0:
+                job.tgt = tgt.data_ptr()
+                job.n_src = len(refs)
+                for i, r in enumerate(refs):
+                    job.src[i] = r.data_ptr()
+                    job.pose_index[i] = i
+                    job.pose_inv[i] = 0
+                    job.g_src[i] = _ptr(g_refs[i]) if (want_grad and g_refs) else 0
+                job.g_tgt = _ptr(g_tgt) if want_grad else 0
+            else:
+                # losses.py:199-203: target = refs[indx], source = [tgt], pose = poses[indx-1] inverted
+                job.tgt = refs[j].data_ptr()
+                job.n_src = 1
+                job.src[0] = tgt.data_ptr()
+                job.pose_index[0] = j - 1
+                job.pose_inv[0] = 1
+                job.g_src[0] = _ptr(g_tgt) if want_grad else 0
+                job.g_tgt = _ptr(g_refs[j]) if (want_grad and g_refs) else 0
+            job.n_scales = len(pyr[j])
+            for s, d in enumerate(pyr[j]):
+                job.disp[s] = d.data_ptr()
+                job.dh[s], job.dw[s] = d.shape[-2], d.shape[-1]
+                job.g_disp[s] = _ptr(g_pyr[j][s]) if (want_grad and g_pyr is not None) else 0
+            job.term_weight = 1.0 / (entries * job.n_src)
+            job.mode, job.flags = cfg.mode, cfg.flags
+        nbytes = lib.plb_photo_workspace_bytes(a)
+        ws = _workspace("photo", nbytes, dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        check(lib.plb_photo_loss(a, st), "plb_photo_loss")
+    if cfg.do_smooth:
+        s_ = _lib.SmoothArgs()
+        s_.B = B
+        s_.n_scales = len(pyr[0])
+        for s, d in enumerate(pyr[0]):
+            s_.disp[s] = d.data_ptr()
+            s_.dh[s], s_.dw[s] = d.shape[-2], d.shape[-1]
+            s_.g_disp[s] = _ptr(g_pyr[0][s]) if (want_grad and g_pyr is not None) else 0
+        s_.accumulate = 1 if cfg.do_photo else 0
+        s_.input_is_depth = int(cfg.input_is_depth)
+        s_.disp_a, s_.disp_b, s_.scale_decay = cfg.disp_a, cfg.disp_b, cfg.scale_decay
+        s_.want_grad = int(want_grad)
+        s_.loss = out.data_ptr() + 4
+        s_.upstream = up2.data_ptr() + 4 if up2 is not None else 0
+        s_.skip_if_unit = up2.data_ptr() if (up2 is not None and skip) else 0
+        s_.skip_n = 2
+        nbytes = lib.plb_smooth_workspace_bytes(s_)
+        ws = _workspace("smooth", nbytes, dev)
+        s_.workspace, s_.workspace_bytes = ws.data_ptr(), ws.numel()
+        check(lib.plb_smooth_loss(s_, st), "plb_smooth_loss")
+
+
+class FusedLossFn(torch.autograd.Function):
+    """(cfg, tgt, poses, K, ref_0..ref_{n-1}, disp tensors frame-major) -> (loss_mam, loss_smooth)."""
+
+    @staticmethod
+    def forward(ctx, cfg, tgt, poses, K, *rest):
+        refs = list(rest[:cfg.n_src])
+        flat = list(rest[cfg.n_src:])
+        pyr, k = [], 0
+        for n in cfg.scales_per_frame:
+            pyr.append(flat[k:k + n])
+            k += n
+        _need_cuda(tgt, poses, K, *refs, *flat)
+        tgt, poses, K = _f32c(tgt), _f32c(poses), _kc(K)
+        refs = [_f32c(r) for r in refs]
+        pyr = [[_f32c(d) for d in p] for p in pyr]
+        need = ctx.needs_input_grad
+        img_grad = need[1] or any(need[4:4 + cfg.n_src])
+        any_grad = img_grad or need[2] or any(need[4 + cfg.n_src:])
+        fused = any_grad and cfg.fused_backward and not img_grad
+        out = torch.zeros(2, dtype=torch.float32, device=tgt.device)
+        g_pyr = g_poses = None
+        if fused:
+            g_pyr = [[torch.empty_like(d) for d in p] for p in pyr]
+            g_poses = torch.zeros_like(poses)
+            if not cfg.do_photo:
+                for j in range(1, len(g_pyr)):
+                    for g in g_pyr[j]:
+                        g.zero_()
+        _launch_loss(cfg, tgt, refs, poses, K, pyr, fused, g_pyr, g_poses, None, None, out, None, False)
+        ctx.cfg, ctx.fused, ctx.any_grad, ctx.img_grad = cfg, fused, any_grad, img_grad
+        ctx.tensors = (tgt, refs, poses, K, pyr, g_pyr, g_poses)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_mam, g_smooth):
+        cfg = ctx.cfg
+        tgt, refs, poses, K, pyr, g_pyr, g_poses = ctx.tensors
+        dev = tgt.device
+        parts = []
+        for g, active in ((g_mam, cfg.do_photo), (g_smooth, cfg.do_smooth)):
+            if not active:
+                parts.append(torch.ones((), dtype=torch.float32, device=dev))
+            elif g is None:
+                parts.append(torch.zeros((), dtype=torch.float32, device=dev))
+            else:
+                parts.append(g.detach().to(torch.float32).reshape(()))
+        up2 = torch.stack(parts).contiguous()
+        g_tgt = g_refs = None
+        if ctx.fused and not getattr(ctx, "used", False):
+            # first backward: the buffers written by the forward launch are handed to autograd
+            skip = True
+            ctx.used = True
+        else:
+            skip = False
+            g_pyr = [[torch.empty_like(d) for d in p] for p in pyr]
+            g_poses = torch.zeros_like(poses)
+            if not cfg.do_photo:
+                for j in range(1, len(g_pyr)):
+                    for g in g_pyr[j]:
+                        g.zero_()
+            if ctx.img_grad:
+                g_tgt = torch.zeros_like(tgt)
+                g_refs = [torch.zeros_like(r) for r in refs]
+        scratch = torch.empty(2, dtype=torch.float32, device=dev)
+        _launch_loss(cfg, tgt, refs, poses, K, pyr, True, g_pyr, g_poses, g_tgt, g_refs, scratch, up2, skip)
+        need = ctx.needs_input_grad
+        grads = [None, g_tgt if need[1] else None, g_poses if need[2] else None, None]
+        for i in range(cfg.n_src):
+            grads.append(g_refs[i] if (need[4 + i] and g_refs is not None) else None)
+        k = 4 + cfg.n_src
+        for j, p in enumerate(g_pyr):
+            for s, g in enumerate(p):
+                grads.append(g if need[k] else None)
+                k += 1
+        return tuple(grads)
+
+
+def fused_losses(tgt, refs, pyramids, poses, K, **cfg_kw):
+    """pyramids: list[frame] of list[scale] of [B,1,h,w].  Returns (loss_mam, loss_smooth)."""
+    cfg = LossConfig(len(refs), [len(p) for p in pyramids], **cfg_kw)
+    flat = [d for p in pyramids for d in p]
+    return FusedLossFn.apply(cfg, tgt, poses, K, *refs, *flat)
+
+
+# ---------------------------------------------------------------------------
+# inverse_warp and the small geometry ops
+# ---------------------------------------------------------------------------
+class InverseWarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, depth, pose, K, pose_inv, rotation_mode):
+        _need_cuda(img, depth, pose, K)
+        img, depth, pose, K = _f32c(img), _f32c(depth), _f32c(pose), _kc(K)
+        B, _, H, W = img.shape
+        out = torch.empty_like(img)
+        a = _lib.WarpArgs()
+        a.B, a.H, a.W = B, H, W
+        a.rotation_mode, a.pose_inv = rotation_mode, int(bool(pose_inv))
+        a.k_is_f64 = 1 if K.dtype == torch.float64 else 0
+        a.img, a.depth, a.pose, a.K, a.out = img.data_ptr(), depth.data_ptr(), pose.data_ptr(), K.data_ptr(), out.data_ptr()
+        a.pose_stride = 6
+        check(lib.plb_warp_forward(a, _stream()), "plb_warp_forward")
+        ctx.save_for_backward(img, depth, pose, K)
+        ctx.meta = (rotation_mode, int(bool(pose_inv)))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, depth, pose, K = ctx.saved_tensors
+        B, _, H, W = img.shape
+        g_out = _f32c(g_out)
+        need = ctx.needs_input_grad
+        g_img = torch.zeros_like(img) if need[0] else None
+        g_depth = torch.empty_like(depth) if need[1] else None
+        g_pose = torch.empty_like(pose) if need[2] else None
+        a = _lib.WarpArgs()
+        a.B, a.H, a.W = B, H, W
+        a.rotation_mode, a.pose_inv = ctx.meta
+        a.k_is_f64 = 1 if K.dtype == torch.float64 else 0
+        a.img, a.depth, a.pose, a.K = img.data_ptr(), depth.data_ptr(), pose.data_ptr(), K.data_ptr()
+        a.pose_stride = 6
+        a.g_out, a.g_img, a.g_depth, a.g_pose = g_out.data_ptr(), _ptr(g_img), _ptr(g_depth), _ptr(g_pose)
+        ws = _workspace("warp", lib.plb_warp_workspace_bytes(a), img.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        check(lib.plb_warp_backward(a, _stream()), "plb_warp_backward")
+        return g_img, g_depth, g_pose, None, None, None
+
+
+class PoseMatrixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, rotation_mode, invert):
+        _need_cuda(pose)
+        pose = _f32c(pose)
+        B = pose.shape[0]
+        M = torch.empty(B, 4, 4, dtype=torch.float32, device=pose.device)
+        check(lib.plb_pose_matrix(pose.data_ptr(), 6, B, rotation_mode, int(invert), M.data_ptr(), _stream()),
+              "plb_pose_matrix")
+        ctx.save_for_backward(pose)
+        ctx.meta = (rotation_mode, int(invert))
+        return M
+
+    @staticmethod
+    def backward(ctx, gM):
+        (pose,) = ctx.saved_tensors
+        gM = _f32c(gM)
+        g = torch.empty_like(pose)
+        check(lib.plb_pose_matrix_backward(pose.data_ptr(), 6, pose.shape[0], ctx.meta[0], ctx.meta[1],
+                                           gM.data_ptr(), g.data_ptr(), _stream()), "plb_pose_matrix_backward")
+        return g, None, None
+
+
+class DispToDepthFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, a, b):
+        _need_cuda(disp)
+        d = _f32c(disp)
+        out = torch.empty_like(d)
+        check(lib.plb_disp_to_depth(d.data_ptr(), d.numel(), a, b, out.data_ptr(), _stream()), "plb_disp_to_depth")
+        ctx.save_for_backward(d)
+        ctx.ab = (a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        g = _f32c(g)
+        out = torch.empty_like(d)
+        check(lib.plb_disp_to_depth_backward(d.data_ptr(), g.data_ptr(), d.numel(), ctx.ab[0], ctx.ab[1],
+                                             out.data_ptr(), _stream()), "plb_disp_to_depth_backward")
+        return out, None, None
+
+
+def reconstruct(depth, K):
+    """[B,H,W] depth, [B,3,3] K -> Xc [B,3,H,W] (forward only)."""
+    _need_cuda(depth, K)
+    depth, K = _f32c(depth), _kc(K)
+    B, H, W = depth.shape
+    out = torch.empty(B, 3, H, W, dtype=torch.float32, device=depth.device)
+    check(lib.plb_reconstruct(depth.data_ptr(), K.data_ptr(), int(K.dtype == torch.float64), B, H, W,
+                              out.data_ptr(), _stream()), "plb_reconstruct")
+    return out
+
+
+def project(X, K, Tcw):
+    """[B,3,H,W] points, [B,3,3] K, [B,4,4] Tcw -> grid [B,H,W,2] (forward only)."""
+    _need_cuda(X, K, Tcw)
+    X, K, Tcw = _f32c(X), _kc(K), _f32c(Tcw)
+    B, _, H, W = X.shape
+    out = torch.empty(B, H, W, 2, dtype=torch.float32, device=X.device)
+    check(lib.plb_project(X.data_ptr(), K.data_ptr(), int(K.dtype == torch.float64), Tcw.data_ptr(), B, H, W,
+                          out.data_ptr(), _stream()), "plb_project")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# pseudo-LiDAR
+# ---------------------------------------------------------------------------
+def cloud_project(depth, P, Tinv, sparsity=0, want_f64=True, want_f32=False, want_index=False, want_valid=False):
+    """depth [B,H,W] f32 CUDA -> dict(count[B] int32, cloud_f64 [B,HW,4], ...).  No sync."""
+    _need_cuda(depth)
+    depth = _f32c(depth)
+    B, H, W = depth.shape
+    dev = depth.device
+    a = _lib.CloudArgs()
+    a.B, a.H, a.W, a.sparsity = B, H, W, int(sparsity or 0)
+    a.depth = depth.data_ptr()
+    for i, v in enumerate([float(x) for x in P.reshape(-1)]):
+        a.P[i] = v
+    for i, v in enumerate([float(x) for x in Tinv.reshape(-1)]):
+        a.Tinv[i] = v
+    res = {"count": torch.empty(B, dtype=torch.int32, device=dev)}
+    a.count = res["count"].data_ptr()
+    if want_f64:
+        res["cloud_f64"] = torch.empty(B, H * W, 4, dtype=torch.float64, device=dev)
+        a.cloud_f64 = res["cloud_f64"].data_ptr()
+    if want_f32:
+        res["cloud_f32"] = torch.empty(B, H * W, 4, dtype=torch.float32, device=dev)
+        a.cloud_f32 = res["cloud_f32"].data_ptr()
+    if want_index:
+        res["index"] = torch.empty(B, H * W, dtype=torch.int32, device=dev)
+        a.index = res["index"].data_ptr()
+    if want_valid:
+        res["valid"] = torch.empty(B, H * W, dtype=torch.uint8, device=dev)
+        a.valid = res["valid"].data_ptr()
+    ws = _workspace("cloud", lib.plb_cloud_workspace_bytes(a), dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    check(lib.plb_cloud_project(a, _stream()), "plb_cloud_project")
+    return res
+
+
+def smooth_only(depth_maps, input_is_depth=True, fused_backward=True):
+    """Losses.smooth_loss on a list of [B,1,h,w] maps (no photometric launch)."""
+    d0 = depth_maps[0]
+    cfg = LossConfig(0, [len(depth_maps)], input_is_depth=input_is_depth, do_photo=False, do_smooth=True,
+                     fused_backward=fused_backward)
+    poses = torch.zeros(d0.shape[0], 1, 6, dtype=torch.float32, device=d0.device)
+    K = torch.zeros(d0.shape[0], 3, 3, dtype=torch.float32, device=d0.device)
+    # with do_photo=False the first tensor only supplies the batch size and device
+    _, smooth = FusedLossFn.apply(cfg, d0.detach(), poses, K, *depth_maps)
+    return smooth
