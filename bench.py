@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py - photometric loss fwd+bwd throughput (Mpix/s of target pixels).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+
+A "step" is one fwd+bwd of the loss (`Losses.forward` + `sum(loss).backward()`,
+trainer.py:312,264) over one batch of synthetic KITTI-shaped frames.  See
+DESIGN.md "Measurement" for the definition of every key of the JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "unsupervised-pseuso-lidar_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "photometric loss fwd+bwd Mpix/s at 192x640 x3 frames"
+UNIT = "Mpix/s"
+
+# name -> (B per GPU, H, W, n_src, n_scales, loss variant)
+WORKLOADS = {
+    "c1": dict(B=4, H=192, W=640, n_src=2, n_scales=1, variant="live"),
+    "c2": dict(B=12, H=192, W=640, n_src=2, n_scales=4, variant="live"),
+    "c3": dict(B=8, H=320, W=1024, n_src=3, n_scales=4, variant="live"),
+    "c5": dict(B=64, H=192, W=640, n_src=2, n_scales=4, variant="live"),
+    "headline": dict(B=12, H=192, W=640, n_src=2, n_scales=1, variant="dir0"),
+}
+
+
+def workload_name(wl, cfg):
+    return "%s: %dx%d batch %d/GPU, 1 target + %d source frames, %d-scale %s loss fwd+bwd" % (
+        wl, cfg["H"], cfg["W"], cfg["B"], cfg["n_src"], cfg["n_scales"],
+        {"live": "reference-live (2 directions, L1 mean + 2nd-order smoothness)",
+         "dir0": "single-direction L1"}[cfg["variant"]])
+
+
+def algorithmic_bytes_per_px(cfg):
+    """every input byte read once per pass (fwd, bwd), every
+    gradient byte written once; all scales of a direction fused into one pass."""
+    pyr = 4.0 * sum(0.25 ** s for s in range(cfg["n_scales"]))
+    def direction(n_src):
+        reads = 12.0 + 12.0 * n_src + pyr
+        return 2.0 * reads + pyr
+    total = direction(cfg["n_src"])
+    if cfg["variant"] == "live":
+        total += direction(1)
+    return total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's torch path, host cores
+# --------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, steps, warmup, budget_s=25.0):
+    """Times oracle/restated.py (`losses_forward` + backward: the same torch op
+    sequence as the reference's `Losses.forward`) on all host cores, on a bounded
+    sample of the workload (batch 4 - the only batch the reference itself runs at,
+    geometry/transform.py:110 - same H, W, sources, scales)."""
+    from oracle import restated as O
+    from plb200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(4, cfg["B"])
+    n_src = cfg["n_src"]
+    inp = synth.make_photo_inputs(Bs, cfg["H"], cfg["W"], n_src=n_src, n_scales=cfg["n_scales"], seed=1234)
+
+    def step():
+        disp = [[d.clone().requires_grad_(True) for d in fr] for fr in inp["disparity"]]
+        poses = inp["poses"].clone().requires_grad_(True)
+        if cfg["variant"] == "live":
+            loss = O.losses_forward(inp["tgt"], inp["ref_imgs"], disp, poses, inp["intrinsics"])
+            sum(loss).backward()
+        else:
+            depths = O.disp_to_depth(disp)
+            loss = O.reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[:1], poses, inp["intrinsics"])
+            loss.backward()
+        return float(sum(loss)) if isinstance(loss, list) else float(loss)
+
+    t_start = time.perf_counter()
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 3:
+            break
+    mean = sum(times) / len(times)
+    mpix = Bs * cfg["H"] * cfg["W"] / 1e6
+    return {"value": mpix / mean, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port of Losses.forward+backward (torch CPU, %d threads), batch %d of the workload's "
+                      "%dx%d / %d sources / %d scales, mean of %d steps" % (
+                          cores, Bs, cfg["H"], cfg["W"], n_src, cfg["n_scales"], len(times)),
+            "ms_per_step": mean * 1e3, "steps": len(times)}
+
+
+def run_reference_arm(args, cfg):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    r = cpu_reference_run(cfg, args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, cfg)},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def make_sets(cfg, n_sets, seed, dev):
+    from plb200 import synth
+    sets = []
+    for k in range(n_sets):
+        inp = synth.make_photo_inputs(cfg["B"], cfg["H"], cfg["W"], n_src=cfg["n_src"], n_scales=cfg["n_scales"],
+                                      seed=seed + 17 * k, n_depth_frames=2 if cfg["variant"] == "live" else 1)
+        sets.append(inp)
+    return sets
+
+
+def set_bytes(inp):
+    n = inp["tgt"].numel() * 4 + sum(r.numel() * 4 for r in inp["ref_imgs"]) + inp["poses"].numel() * 4
+    n += inp["intrinsics"].numel() * 8 + sum(d.numel() * 4 for fr in inp["disparity"] for d in fr)
+    return n
+
+
+def step_fn(criterion, g, cfg):
+    """One fwd+bwd through the public API; returns the loss tensors and the grads."""
+    disp = [[d.detach().requires_grad_(True) for d in fr] for fr in g["disparity"]]
+    poses = g["poses"].detach().requires_grad_(True)
+    if cfg["variant"] == "live":
+        loss = criterion.forward(g["tgt"], g["ref_imgs"], disp, poses, g["intrinsics"], None)
+        total = loss[0] + loss[1]
+    else:
+        from plb200 import ops
+        mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp[:1], poses, g["intrinsics"], do_smooth=False)
+        total = mam
+    total.backward()
+    return total.detach(), poses.grad, [d.grad for fr in disp for d in fr]
+
+
+def run_ours(args, cfg):
+    from plb200 import synth, _lib
+    from losses import Losses
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local if world > 1 else 0)
+    torch.cuda.set_device(dev)
+    criterion = Losses()
+    n_sets = args.sets
+    cpu_sets = make_sets(cfg, n_sets, 1234 + 1000 * rank, dev)
+    gpu_sets = [synth.to_device(s, dev) for s in cpu_sets]
+    pool_mb = sum(set_bytes(s) for s in cpu_sets) / 1e6
+    px_per_step = cfg["B"] * cfg["H"] * cfg["W"]
+
+    # ---- capture one CUDA graph per input set (same public-API calls, replayed) ----
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    graphs, outs = [], []
+    n_launch0 = _lib.launch_count()
+    with torch.cuda.stream(side):
+        for g in gpu_sets:
+            for _ in range(2):
+                step_fn(criterion, g, cfg)
+    launches_per_step = (_lib.launch_count() - n_launch0) // (2 * n_sets)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    use_graph = not args.no_graph
+    if use_graph:
+        for g in gpu_sets:
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg, stream=side):
+                outs.append(step_fn(criterion, g, cfg))
+            graphs.append(cg)
+
+    def device_step(i):
+        if use_graph:
+            graphs[i % n_sets].replay()
+        else:
+            outs_local = step_fn(criterion, gpu_sets[i % n_sets], cfg)
+            return outs_local
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        device_step(i)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- dominant kernel alone (photo_l1 fused fwd+grad), back-to-back launches -----
+    kern_ms = time_photo_kernel(criterion, gpu_sets, cfg, dev, max(20, min(args.steps, 200)))
+
+    # ---- e2e: host (pinned) inputs -> H2D -> public API fwd+bwd -> D2H loss ----------
+    e2e = time_e2e(criterion, cpu_sets, cfg, dev, max(5, min(args.steps, 50)), barrier)
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total, e2e["ms_per_step"], kern_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e["ms_per_step"], kern_ms = [float(x) for x in t]
+        # the path's only exchange: the two logged loss scalars
+        lt = (outs[0][0] if use_graph else torch.zeros((), device=dev)).clone().reshape(1)
+        dist.all_reduce(lt)
+    ms_step = ms_total / args.steps
+    value = world * px_per_step / 1e6 / (ms_step / 1e3)
+    e2e_value = world * px_per_step / 1e6 / (e2e["ms_per_step"] / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        abytes = algorithmic_bytes_per_px(cfg) * px_per_step
+        achieved = abytes / (kern_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+        if os.path.isfile(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except ValueError:
+                pass
+        cpu = cpu_reference_run(cfg, 6, 1) if (world == 1 and not args.no_cpu) else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, cfg), "global_batch": cfg["B"] * world,
+                       "parallelism": "batch-sharded x%d, no data-path collective" % world,
+                       "l2": "inputs rotate over %d distinct sets (%.0f MB per GPU) > 126 MB L2" % (n_sets, pool_mb),
+                       "step": "CUDA-graph replay of Losses.forward + backward" if use_graph else "eager public API"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "ms_per_step": e2e["ms_per_step"]},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "photo_l1_kernel<GRAD> (fused fwd+grad, all directions/scales)",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes,
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def time_photo_kernel(criterion, gpu_sets, cfg, dev, iters):
+    """Average duration of the dominant kernel, CUDA events on its own stream."""
+    from plb200 import ops
+    outs = []
+    st = torch.cuda.current_stream()
+    for g in gpu_sets:  # pre-build argument structs by running once
+        step_fn(criterion, g, cfg)
+    torch.cuda.synchronize()
+    # launch only the fused photometric kernel (forward + unit-upstream gradients)
+    calls = []
+    for g in gpu_sets:
+        pyr = g["disparity"] if cfg["variant"] == "live" else g["disparity"][:1]
+        lcfg = ops.LossConfig(cfg["n_src"], [len(p) for p in pyr], do_smooth=False)
+        g_pyr = [[torch.empty_like(d) for d in p] for p in pyr]
+        g_poses = torch.zeros_like(g["poses"])
+        out = torch.zeros(2, device=dev)
+        calls.append((lcfg, g, pyr, g_pyr, g_poses, out))
+
+    def launch(i):
+        lcfg, g, pyr, g_pyr, g_poses, out = calls[i % len(calls)]
+        ops._launch_loss(lcfg, g["tgt"], g["ref_imgs"], g["poses"], g["intrinsics"], pyr, True, g_pyr, g_poses,
+                         None, None, out, None, False)
+    for i in range(5):
+        launch(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(iters):
+        launch(i)
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier):
+    """Public API with HOST buffers: pinned inputs copied H2D every step, loss read D2H."""
+    from plb200 import synth
+    pinned = []
+    for s in cpu_sets:
+        p = {"tgt": s["tgt"].pin_memory(), "ref_imgs": [r.pin_memory() for r in s["ref_imgs"]],
+             "disparity": [[d.pin_memory() for d in fr] for fr in s["disparity"]], "poses": s["poses"].pin_memory(),
+             "intrinsics": s["intrinsics"].pin_memory()}
+        pinned.append(p)
+    h2d = set_bytes(cpu_sets[0])
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def one(i):
+        p = pinned[i % len(pinned)]
+        g = {"tgt": p["tgt"].to(dev, non_blocking=True), "ref_imgs": [r.to(dev, non_blocking=True) for r in p["ref_imgs"]],
+             "disparity": [[d.to(dev, non_blocking=True) for d in fr] for fr in p["disparity"]],
+             "poses": p["poses"].to(dev, non_blocking=True), "intrinsics": p["intrinsics"].to(dev, non_blocking=True)}
+        total, _, _ = step_fn(criterion, g, cfg)
+        host_loss.copy_(total, non_blocking=False)     # D2H of the step's result (synchronises)
+        return float(host_loss)
+    for i in range(3):
+        one(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        one(i)
+    e1.record()
+    barrier()
+    return {"ms_per_step": e0.elapsed_time(e1) / iters, "h2d": h2d, "d2h": 4}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated between steps (L2 defeat)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    import __graft_entry__ as ge
+    from plb200 import build as _b
+    if not os.path.isfile(_b.LIB):
+        ge.build()
+    run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,26 +57,42 @@ def test_golden_image_grads(name):
     assert rel_err(p.grad.cpu(), g["g_poses"]) < GRAD_TOL
 
 
-@pytest.mark.parametrize("B,H,W,S,regime", [(1, 33, 70, 1, "trained"), (5, 50, 131, 3, "trained"),
-                                            (2, 64, 128, 4, "init"), (3, 192, 640, 4, "trained")])
-def test_oracle_parity_odd_shapes(B, H, W, S, regime):
-    """Sizes the reference itself cannot run (B != 4, ragged tiles): oracle on CPU vs CUDA."""
-    from plb200 import synth
+def _oracle(inp, eps=0.0):
     from oracle import restated as O
-    inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=S, seed=100 + B, regime=regime)
-    if S > 1:  # pyramids of odd sizes: use ceil-halving like a conv stack would
-        pass
-    rd = [[d.clone().requires_grad_(True) for d in fr] for fr in inp["disparity"]]
+    rd = [[(d * (1.0 + eps)).detach().requires_grad_(True) for d in fr] for fr in inp["disparity"]]
     rp = inp["poses"].clone().requires_grad_(True)
     rl = O.losses_forward(inp["tgt"], inp["ref_imgs"], rd, rp, inp["intrinsics"])
     sum(rl).backward()
+    return rl, rp, rd
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.1])
+@pytest.mark.parametrize("B,H,W,S,regime", [(1, 33, 70, 1, "trained"), (5, 50, 131, 3, "trained"),
+                                            (2, 64, 128, 4, "init"), (3, 192, 640, 4, "trained")])
+def test_oracle_parity_odd_shapes(B, H, W, S, regime, noise):
+    """Sizes the reference itself cannot run (B != 4, ragged tiles): oracle on CPU vs CUDA.
+
+    Bilinear sampling has a gradient that jumps where a sample crosses a pixel
+    boundary, so on per-pixel-noise images (noise=0.1) the pose gradient of the
+    ORACLE ITSELF moves by ~3e-4 when the disparity is perturbed by one ulp
+    (relative 2e-7).  The 1e-4 bound is therefore enforced as written on smooth
+    frames (noise=0) and, on noisy frames, widened to 3x the oracle's own
+    one-ulp sensitivity when that is larger."""
+    from plb200 import synth
+    inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=S, seed=100 + B, regime=regime, noise=noise)
+    rl, rp, rd = _oracle(inp)
+    tol_pose, tol_disp = GRAD_TOL, GRAD_TOL
+    if noise > 0:
+        _, rp2, rd2 = _oracle(inp, eps=2e-7)
+        tol_pose = max(GRAD_TOL, 3 * rel_err(rp2.grad, rp.grad))
+        tol_disp = max(GRAD_TOL, 3 * max(rel_err(a.grad, b.grad) for fa, fb in zip(rd2, rd) for a, b in zip(fa, fb)))
     loss, disp, p, _, _ = _run_ours(inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"])
     assert abs(float(loss[0]) - float(rl[0])) <= LOSS_TOL * abs(float(rl[0]))
     assert abs(float(loss[1]) - float(rl[1])) <= LOSS_TOL * abs(float(rl[1]))
-    assert rel_err(p.grad.cpu(), rp.grad) < GRAD_TOL
+    assert rel_err(p.grad.cpu(), rp.grad) < tol_pose
     for f, fr in enumerate(disp):
         for s, t in enumerate(fr):
-            assert rel_err(t.grad.cpu(), rd[f][s].grad) < GRAD_TOL, (f, s)
+            assert rel_err(t.grad.cpu(), rd[f][s].grad) < tol_disp, (f, s)
 
 
 def test_non_unit_upstream_recomputes():

@@ -46,29 +46,28 @@ def kitti_intrinsics(B, H, W, dtype=torch.float64):
     return K.to(dtype).unsqueeze(0).repeat(B, 1, 1).contiguous()
 
 
-def _field(B, H, W, gen, shift=(0, 0)):
+def _field(B, H, W, gen, shift=(0, 0), noise=0.1):
     """Smooth colour field + noise, ImageNet-normalised; `shift` moves the
     smooth part so that source frames are shifted copies of the target."""
     v = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1) + shift[1]
     u = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W) + shift[0]
     phase = torch.tensor([0.0, 2.1, 4.2]).view(1, 3, 1, 1)
     smooth = 0.5 + 0.25 * torch.sin(2 * math.pi * u / 97.0 + phase) * torch.cos(2 * math.pi * v / 61.0)
-    noise = 0.1 * torch.randn(B, 3, H, W, generator=gen)
-    x = (smooth + noise).clamp_(0.0, 1.0)
+    x = (smooth + noise * torch.randn(B, 3, H, W, generator=gen)).clamp_(0.0, 1.0)
     mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
     return ((x - mean) / std).contiguous()
 
 
 def make_photo_inputs(B, H, W, n_src=2, n_scales=1, seed=1234, regime="trained",
-                      n_depth_frames=2, device="cpu"):
+                      n_depth_frames=2, device="cpu", noise=0.1):
     """One batch in the reference's sample layout.  `regime`: "trained" draws
     disparity U(0.002, 0.1) (depth 1..33 m), "init" draws sigmoid(N(0,1))
     (what a random-init DispNetS emits, `models/depth/disp_net.py:25-29`)."""
     gen = torch.Generator().manual_seed(seed)
     shifts = [(-3, -1), (3, 1), (-6, -2), (6, 2)]
-    tgt = _field(B, H, W, gen)
-    refs = [_field(B, H, W, gen, shifts[i % 4]) for i in range(n_src)]
+    tgt = _field(B, H, W, gen, noise=noise)
+    refs = [_field(B, H, W, gen, shifts[i % 4], noise=noise) for i in range(n_src)]
     disparity = []
     for _ in range(n_depth_frames):
         per_scale = []
