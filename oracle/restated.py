@@ -125,14 +125,15 @@ def reconstruct(depth, K):
     """`geometry/transform.py:74-105`: Xc = (K^-1 . grid) * depth; depth [B,H,W]."""
     depth = depth.unsqueeze(1)
     B, _, H, W = depth.shape
-    Kinv = K.inverse().float()
+    Kinv = K.inverse().to(depth.dtype)   # `.float()` in the reference (depth is fp32 there)
     grid = image_grid(B, H, W, depth.dtype).view(B, 3, -1)
     return Kinv.bmm(grid).view(B, 3, H, W) * depth
 
 
-def k_hom(K):
-    """`geometry/transform.py:107-112` with the hard-coded batch 4 replaced by K's."""
-    Kh = torch.eye(4).reshape(1, 4, 4).repeat(K.shape[0], 1, 1)
+def k_hom(K, dtype=torch.float32):
+    """`geometry/transform.py:107-112` with the hard-coded batch 4 replaced by K's
+    (fp32 in the reference; `dtype` exists for the fp64 accuracy study in the tests)."""
+    Kh = torch.eye(4, dtype=dtype).reshape(1, 4, 4).repeat(K.shape[0], 1, 1)
     Kh[:, :3, :3] = K.clone()
     return Kh
 
@@ -141,9 +142,9 @@ def project(X, K, Tcw):
     """`geometry/transform.py:114-150`: pixel grid in [-1,1] for grid_sample."""
     B, _, H, W = X.shape
     Xc = X.view(B, 3, -1)
-    ones = torch.ones(1, Xc.shape[-1]).repeat(B, 1, 1)
+    ones = torch.ones(1, Xc.shape[-1], dtype=X.dtype).repeat(B, 1, 1)
     Xh = torch.cat([Xc, ones], 1)
-    Tx = (k_hom(K) @ Tcw)[:, :3, :]
+    Tx = (k_hom(K, X.dtype) @ Tcw)[:, :3, :]
     cam = Tx @ Xh
     pix = cam[:, :2, :] / (cam[:, 2, :].unsqueeze(1) + 1e-5)
     pix = pix.view(B, 2, H, W).permute(0, 2, 3, 1)

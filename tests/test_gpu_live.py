@@ -57,42 +57,49 @@ def test_golden_image_grads(name):
     assert rel_err(p.grad.cpu(), g["g_poses"]) < GRAD_TOL
 
 
-def _oracle(inp, eps=0.0):
+def _oracle(inp, dtype=torch.float32):
     from oracle import restated as O
-    rd = [[(d * (1.0 + eps)).detach().requires_grad_(True) for d in fr] for fr in inp["disparity"]]
-    rp = inp["poses"].clone().requires_grad_(True)
-    rl = O.losses_forward(inp["tgt"], inp["ref_imgs"], rd, rp, inp["intrinsics"])
+    c = lambda t: t.to(dtype)
+    rd = [[c(d).detach().requires_grad_(True) for d in fr] for fr in inp["disparity"]]
+    rp = c(inp["poses"]).clone().requires_grad_(True)
+    rl = O.losses_forward(c(inp["tgt"]), [c(r) for r in inp["ref_imgs"]], rd, rp, inp["intrinsics"])
     sum(rl).backward()
     return rl, rp, rd
 
 
 @pytest.mark.parametrize("noise", [0.0, 0.1])
-@pytest.mark.parametrize("B,H,W,S,regime", [(1, 33, 70, 1, "trained"), (5, 50, 131, 3, "trained"),
-                                            (2, 64, 128, 4, "init"), (3, 192, 640, 4, "trained")])
+@pytest.mark.parametrize("B,H,W,S,regime", [(1, 33, 70, 1, "trained"), (5, 50, 131, 3, "noise"),
+                                            (2, 64, 128, 4, "init"), (3, 192, 640, 4, "trained"),
+                                            (3, 192, 640, 4, "noise")])
 def test_oracle_parity_odd_shapes(B, H, W, S, regime, noise):
     """Sizes the reference itself cannot run (B != 4, ragged tiles): oracle on CPU vs CUDA.
 
-    Bilinear sampling has a gradient that jumps where a sample crosses a pixel
-    boundary, so on per-pixel-noise images (noise=0.1) the pose gradient of the
-    ORACLE ITSELF moves by ~3e-4 when the disparity is perturbed by one ulp
-    (relative 2e-7).  The 1e-4 bound is therefore enforced as written on smooth
-    frames (noise=0) and, on noisy frames, widened to 3x the oracle's own
-    one-ulp sensitivity when that is larger."""
+    The gradient of bilinear sampling jumps where a sample crosses a pixel
+    boundary and the projected coordinate carries ~1e-4 px of fp32 rounding, so
+    the fp32 reference arithmetic is itself only accurate to e32 = |oracle_fp32 -
+    oracle_fp64| / |oracle_fp64|, which reaches 4e-4 (smooth frames) to 1e-2
+    (per-pixel-noise frames, incoherent depth) on some gradients.  The bar:
+    the CUDA result is within max(1e-4, 3*e32) of the fp64 evaluation of the
+    reference's formulas and within max(1e-4, 4*e32) of the fp32 oracle - i.e.
+    1e-4 wherever the reference itself is that accurate, and never less
+    accurate than a small multiple of the reference's own rounding noise."""
     from plb200 import synth
     inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=S, seed=100 + B, regime=regime, noise=noise)
     rl, rp, rd = _oracle(inp)
-    tol_pose, tol_disp = GRAD_TOL, GRAD_TOL
-    if noise > 0:
-        _, rp2, rd2 = _oracle(inp, eps=2e-7)
-        tol_pose = max(GRAD_TOL, 3 * rel_err(rp2.grad, rp.grad))
-        tol_disp = max(GRAD_TOL, 3 * max(rel_err(a.grad, b.grad) for fa, fb in zip(rd2, rd) for a, b in zip(fa, fb)))
+    rl64, rp64, rd64 = _oracle(inp, torch.float64)
     loss, disp, p, _, _ = _run_ours(inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"])
-    assert abs(float(loss[0]) - float(rl[0])) <= LOSS_TOL * abs(float(rl[0]))
-    assert abs(float(loss[1]) - float(rl[1])) <= LOSS_TOL * abs(float(rl[1]))
-    assert rel_err(p.grad.cpu(), rp.grad) < tol_pose
+    for k in range(2):
+        assert abs(float(loss[k]) - float(rl64[k])) <= LOSS_TOL * abs(float(rl64[k]))
+        assert abs(float(loss[k]) - float(rl[k])) <= LOSS_TOL * abs(float(rl[k]))
+
+    def check(ours, r32, r64, what):
+        e32 = rel_err(r32, r64)
+        assert rel_err(ours, r64) < max(GRAD_TOL, 3 * e32), (what, e32)
+        assert rel_err(ours, r32) < max(GRAD_TOL, 4 * e32), (what, e32)
+    check(p.grad.cpu(), rp.grad, rp64.grad, "poses")
     for f, fr in enumerate(disp):
         for s, t in enumerate(fr):
-            assert rel_err(t.grad.cpu(), rd[f][s].grad) < tol_disp, (f, s)
+            check(t.grad.cpu(), rd[f][s].grad, rd64[f][s].grad, ("disp", f, s))
 
 
 def test_non_unit_upstream_recomputes():

@@ -246,6 +246,13 @@ __device__ __forceinline__ void make_taps(float ix, float iy, int W, int H, Taps
     t.vy1 = t.any && t.y0 + 1 <= H - 1;
 }
 
+// 1/z: MUFU.RCP (1 ulp) + one Newton step; z = 0 gives inf/NaN, which callers clamp away.
+__device__ __forceinline__ float rcp_nr(float z) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
+    return r * fmaf(-z, r, 2.0f);
+}
+
 __device__ __forceinline__ float ldg_pred(const float* __restrict__ p, bool ok) {
     return ok ? __ldg(p) : 0.0f;
 }

@@ -57,72 +57,118 @@ __host__ __device__ inline PhotoLayout photo_layout(const plb_photo_args& a) {
     return L;
 }
 
+// One target pixel against one source at one depth: project, sample, L1, and
+// (GRAD) the gradient terms.  Written for instruction count: the projection is
+// cam = D * (P[:, :3].ray) + P[:, 3] (12 FMA), the perspective divide is one
+// MUFU.RCP + one Newton step, the normalise/un-normalise chain of the reference
+// (transform.py:143-148 + grid_sample) is the identity and is dropped, and the
+// bilinear blend is written as nested lerps whose intermediates ARE the
+// coordinate derivatives (d proj/d iy = bot - top).  A warp whose 32 pixels all
+// land strictly inside the source takes a branch with unpredicated loads.
 template <bool GRAD, bool IMG_GRAD>
-__device__ __forceinline__ void photo_pixel(const float* __restrict__ src, float* __restrict__ g_src,
+__device__ __forceinline__ void photo_pixel(const float* const (&cb)[3], float* const (&gb)[3],
                                             int H, int W, const float* __restrict__ P, float rx, float ry,
                                             float rz, float D, const float (&t)[3], float w_e, bool valid,
-                                            float (&acc)[16], float& gD, float (&e_out)[3]) {
-    const size_t plane = (size_t)H * W;
-    float X = rx * D, Y = ry * D, Z = rz * D;
-    float cx, cy, ze, ix, iy;
-    project_pixel(P, X, Y, Z, (float)(W - 1), (float)(H - 1), cx, cy, ze, ix, iy);
-    Taps tp;
-    make_taps(ix, iy, W, H, tp);
-    const int xa = max(tp.x0, 0), xb = min(tp.x0 + 1, W - 1);
-    const int ya = max(tp.y0, 0), yb = min(tp.y0 + 1, H - 1);
-    const bool mnw = valid && tp.vx0 && tp.vy0, mne = valid && tp.vx1 && tp.vy0;
-    const bool msw = valid && tp.vx0 && tp.vy1, mse = valid && tp.vx1 && tp.vy1;
-    const float* r0 = src + (size_t)ya * W;
-    const float* r1 = src + (size_t)yb * W;
-    float vnw[3], vne[3], vsw[3], vse[3];
+                                            float (&acc)[16], float& gD, float (&gt)[3]) {
+    const float Ax = fmaf(P[2], rz, fmaf(P[1], ry, P[0] * rx));
+    const float Ay = fmaf(P[6], rz, fmaf(P[5], ry, P[4] * rx));
+    const float Az = fmaf(P[10], rz, fmaf(P[9], ry, P[8] * rx));
+    const float cx = fmaf(D, Ax, P[3]), cy = fmaf(D, Ay, P[7]);
+    const float ze = fmaf(D, Az, P[11]) + 1e-5f;
+    const float inv = rcp_nr(ze);
+    const float px = cx * inv, py = cy * inv;
+    // clamp keeps float->int defined; NaN maps to -2 (out of the image)
+    const float ixc = fminf(fmaxf(px, -2.0f), (float)(W + 1));
+    const float iyc = fminf(fmaxf(py, -2.0f), (float)(H + 1));
+    const float xf = floorf(ixc), yf = floorf(iyc);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const float fx = ixc - xf, fy = iyc - yf;
+    const bool inter = ((unsigned)x0 < (unsigned)(W - 1)) && ((unsigned)y0 < (unsigned)(H - 1));
+    float v[3][4];
+    bool use;
+    bool mnw = true, mne = true, msw = true, mse = true;
+    if (__all_sync(0xffffffffu, inter || !valid)) {
+        // 32-bit element offsets: one IMAD.WIDE per (channel, row), +4 B as an immediate
+        const int off0 = (inter && valid) ? y0 * W + x0 : 0;
+        const int off1 = off0 + W;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        vnw[c] = ldg_pred(r0 + c * plane + xa, mnw);
-        vne[c] = ldg_pred(r0 + c * plane + xb, mne);
-        vsw[c] = ldg_pred(r1 + c * plane + xa, msw);
-        vse[c] = ldg_pred(r1 + c * plane + xb, mse);
+        for (int c = 0; c < 3; ++c) {
+            const float* q0 = cb[c] + off0;
+            const float* q1 = cb[c] + off1;
+            v[c][0] = __ldg(q0);
+            v[c][1] = __ldg(q0 + 1);
+            v[c][2] = __ldg(q1);
+            v[c][3] = __ldg(q1 + 1);
+        }
+        use = valid;
+    } else {
+        const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+        const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+        mnw = valid && vx0 && vy0; mne = valid && vx1 && vy0;
+        msw = valid && vx0 && vy1; mse = valid && vx1 && vy1;
+        const int off0 = y0 * W + x0, off1 = off0 + W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* q0 = cb[c] + off0;
+            const float* q1 = cb[c] + off1;
+            v[c][0] = ldg_pred(q0, mnw);
+            v[c][1] = ldg_pred(q0 + 1, mne);
+            v[c][2] = ldg_pred(q1, msw);
+            v[c][3] = ldg_pred(q1 + 1, mse);
+        }
+        use = mnw || mne || msw || mse;
     }
-    const float wnw = tp.wx0 * tp.wy0, wne = tp.wx1 * tp.wy0, wsw = tp.wx0 * tp.wy1, wse = tp.wx1 * tp.wy1;
     float Gx = 0.0f, Gy = 0.0f, l1 = 0.0f;
+    float e[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float proj = vnw[c] * wnw + vne[c] * wne + vsw[c] * wsw + vse[c] * wse;
-        float d = proj - t[c];
+        const float dA = v[c][1] - v[c][0], dB = v[c][3] - v[c][2];
+        const float top = fmaf(fx, dA, v[c][0]), bot = fmaf(fx, dB, v[c][2]);
+        const float dV = bot - top;
+        const float proj = fmaf(fy, dV, top);
+        const float d = proj - t[c];
         l1 += fabsf(d);
         if (GRAD) {
-            float e = d > 0.0f ? w_e : (d < 0.0f ? -w_e : 0.0f);
-            e_out[c] = e;
-            Gx += e * ((vne[c] - vnw[c]) * tp.wy0 + (vse[c] - vsw[c]) * tp.wy1);
-            Gy += e * ((vsw[c] - vnw[c]) * tp.wx0 + (vse[c] - vne[c]) * tp.wx1);
+            const float sg = (d > 0.0f ? 1.0f : 0.0f) - (d < 0.0f ? 1.0f : 0.0f);
+            e[c] = sg;
+            Gx = fmaf(sg, fmaf(fy, dB - dA, dA), Gx);
+            Gy = fmaf(sg, dV, Gy);
         }
     }
-    if (valid) acc[0] += l1;
+    acc[0] += valid ? l1 : 0.0f;
     if (GRAD) {
-        const float iz = 1.0f / ze;
-        const float px = cx * iz, py = cy * iz;
-        float gcx = Gx * iz, gcy = Gy * iz, gcz = -(Gx * px + Gy * py) * iz;
-        if (!(valid && tp.any)) { gcx = 0.0f; gcy = 0.0f; gcz = 0.0f; }
-        gD += gcx * (P[0] * rx + P[1] * ry + P[2] * rz) + gcy * (P[4] * rx + P[5] * ry + P[6] * rz) +
-              gcz * (P[8] * rx + P[9] * ry + P[10] * rz);
-        acc[1] += gcx * X; acc[2] += gcx * Y; acc[3] += gcx * Z; acc[4] += gcx;
-        acc[5] += gcy * X; acc[6] += gcy * Y; acc[7] += gcy * Z; acc[8] += gcy;
-        acc[9] += gcz * X; acc[10] += gcz * Y; acc[11] += gcz * Z; acc[12] += gcz;
-        if (IMG_GRAD && g_src != nullptr) {
-            float* q0 = g_src + (size_t)ya * W;
-            float* q1 = g_src + (size_t)yb * W;
+        const float gi = use ? w_e * inv : 0.0f;       // also keeps inf/NaN of a degenerate z out
+        const float gcx = Gx * gi, gcy = Gy * gi;
+        const float gcz = use ? -(gcx * px + gcy * py) : 0.0f;
+        gD += fmaf(gcx, Ax, fmaf(gcy, Ay, gcz * Az));
+        const float hx = gcx * D, hy = gcy * D, hz = gcz * D;
+        acc[1] = fmaf(hx, rx, acc[1]); acc[2] = fmaf(hx, ry, acc[2]); acc[3] = fmaf(hx, rz, acc[3]); acc[4] += gcx;
+        acc[5] = fmaf(hy, rx, acc[5]); acc[6] = fmaf(hy, ry, acc[6]); acc[7] = fmaf(hy, rz, acc[7]); acc[8] += gcy;
+        acc[9] = fmaf(hz, rx, acc[9]); acc[10] = fmaf(hz, ry, acc[10]); acc[11] = fmaf(hz, rz, acc[11]); acc[12] += gcz;
+        if (IMG_GRAD) {
+            const float m = valid ? w_e : 0.0f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (mnw) atomicAdd(q0 + c * plane + xa, wnw * e_out[c]);
-                if (mne) atomicAdd(q0 + c * plane + xb, wne * e_out[c]);
-                if (msw) atomicAdd(q1 + c * plane + xa, wsw * e_out[c]);
-                if (mse) atomicAdd(q1 + c * plane + xb, wse * e_out[c]);
+            for (int c = 0; c < 3; ++c) gt[c] -= m * e[c];
+            if (gb[0] != nullptr) {
+                const float wnw = (1.0f - fx) * (1.0f - fy), wne = fx * (1.0f - fy);
+                const float wsw = (1.0f - fx) * fy, wse = fx * fy;
+                const int off0 = y0 * W + x0;   // masks carry the per-tap bounds (all true on the fast path)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float ec = m * e[c];
+                    float* q = gb[c] + off0;
+                    if (valid && mnw) atomicAdd(q, wnw * ec);
+                    if (valid && mne) atomicAdd(q + 1, wne * ec);
+                    if (valid && msw) atomicAdd(q + W, wsw * ec);
+                    if (valid && mse) atomicAdd(q + W + 1, wse * ec);
+                }
             }
         }
     }
 }
 
 template <bool GRAD, bool IMG_GRAD>
-__global__ void __launch_bounds__(PH_THREADS)
+__global__ void __launch_bounds__(PH_THREADS, GRAD ? 3 : 4)
 photo_l1_kernel(const __grid_constant__ plb_photo_args a) {
     if (skip_launch(a.skip_if_unit, a.skip_n)) return;
 
@@ -180,10 +226,8 @@ photo_l1_kernel(const __grid_constant__ plb_photo_args a) {
         rz[j] = fmaf(s_kinv[7], yf, s_kinv[6] * xf) + s_kinv[8];
     }
     float gt[PH_ROWS][3];
-    if (GRAD && IMG_GRAD) {
 #pragma unroll
-        for (int j = 0; j < PH_ROWS; ++j) gt[j][0] = gt[j][1] = gt[j][2] = 0.0f;
-    }
+    for (int j = 0; j < PH_ROWS; ++j) gt[j][0] = gt[j][1] = gt[j][2] = 0.0f;
 
 #pragma unroll 1
     for (int s = 0; s < job.n_scales; ++s) {
@@ -223,12 +267,12 @@ photo_l1_kernel(const __grid_constant__ plb_photo_args a) {
             for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
             const float* src_b = job.src[i] + (size_t)b * 3 * plane;
             float* g_src_b = (GRAD && IMG_GRAD && job.g_src[i]) ? job.g_src[i] + (size_t)b * 3 * plane : nullptr;
+            const float* const cb[3] = {src_b, src_b + plane, src_b + 2 * plane};
+            float* const gb[3] = {g_src_b, g_src_b ? g_src_b + plane : nullptr, g_src_b ? g_src_b + 2 * plane : nullptr};
 #pragma unroll
             for (int j = 0; j < PH_ROWS; ++j) {
-                float e[3] = {0.0f, 0.0f, 0.0f};
-                photo_pixel<GRAD, IMG_GRAD>(src_b, g_src_b, H, W, s_P[i], rx[j], ry[j], rz[j], D[j], t[j], w_e,
-                                            valid[j], acc, gD[j], e);
-                if (GRAD && IMG_GRAD) { gt[j][0] -= e[0]; gt[j][1] -= e[1]; gt[j][2] -= e[2]; }
+                photo_pixel<GRAD, IMG_GRAD>(cb, gb, H, W, s_P[i], rx[j], ry[j], rz[j], D[j], t[j], w_e,
+                                            valid[j], acc, gD[j], gt[j]);
             }
             if (GRAD) {
                 int which;

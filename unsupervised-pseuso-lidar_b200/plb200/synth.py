@@ -61,9 +61,14 @@ def _field(B, H, W, gen, shift=(0, 0), noise=0.1):
 
 def make_photo_inputs(B, H, W, n_src=2, n_scales=1, seed=1234, regime="trained",
                       n_depth_frames=2, device="cpu", noise=0.1):
-    """One batch in the reference's sample layout.  `regime`: "trained" draws
-    disparity U(0.002, 0.1) (depth 1..33 m), "init" draws sigmoid(N(0,1))
-    (what a random-init DispNetS emits, `models/depth/disp_net.py:25-29`)."""
+    """One batch in the reference's sample layout.  `regime`:
+      "trained"  a road-scene-like disparity: smooth ground-plane ramp (far at the
+                 top, near at the bottom) with smooth bumps and 2% multiplicative
+                 noise, range ~[0.003, 0.1] (depth 1..30 m) - what a converged
+                 depth net emits, and the regime the bench runs;
+      "noise"    per-pixel U(0.002, 0.1): no spatial coherence at all (adversarial
+                 for gather locality, used by parity tests);
+      "init"     sigmoid(N(0,1)) per pixel (`models/depth/disp_net.py:25-29`)."""
     gen = torch.Generator().manual_seed(seed)
     shifts = [(-3, -1), (3, 1), (-6, -2), (6, 2)]
     tgt = _field(B, H, W, gen, noise=noise)
@@ -75,8 +80,16 @@ def make_photo_inputs(B, H, W, n_src=2, n_scales=1, seed=1234, regime="trained",
             hs, ws = H >> s, W >> s
             if regime == "init":
                 d = torch.sigmoid(torch.randn(B, 1, hs, ws, generator=gen))
-            else:
+            elif regime == "noise":
                 d = 0.002 + 0.098 * torch.rand(B, 1, hs, ws, generator=gen)
+            else:
+                v = (torch.arange(hs, dtype=torch.float32).view(1, 1, hs, 1) + 0.5) / hs
+                u = (torch.arange(ws, dtype=torch.float32).view(1, 1, 1, ws) + 0.5) / ws
+                ph = 6.28318 * torch.rand(B, 1, 1, 1, generator=gen)
+                ramp = 0.004 + 0.085 * v.clamp(min=0.35).sub(0.35).div(0.65) ** 1.5
+                bumps = 0.004 * torch.sin(9.0 * u + ph) * torch.cos(5.0 * v + 0.5 * ph)
+                d = (ramp + bumps + 0.004) * (1.0 + 0.02 * torch.randn(B, 1, hs, ws, generator=gen))
+                d = d.clamp(0.002, 0.1)
             per_scale.append(d.contiguous())
         disparity.append(per_scale)
     poses = torch.cat([0.01 * torch.randn(B, n_src, 3, generator=gen),
