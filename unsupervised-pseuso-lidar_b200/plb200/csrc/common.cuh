@@ -253,6 +253,8 @@ __device__ __forceinline__ float rcp_nr(float z) {
     return r * fmaf(-z, r, 2.0f);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float ldg_pred(const float* __restrict__ p, bool ok) {
     return ok ? __ldg(p) : 0.0f;
 }
