@@ -93,11 +93,10 @@ typedef struct plb_photo_args {
     float* loss;               /* out (written) [1]                                                */
     float* entry_loss;         /* out (written) [n_jobs*PLB_MAX_SCALES] per-(job,scale) means or NULL */
     const float* upstream;     /* device scalar d L / d loss; NULL = 1                             */
-    const float* skip_if_unit; /* device ptr to skip_n floats or NULL: the launch returns at once
-                                  when all of them equal 1 (the gradients written by the forward
-                                  pass with unit upstream are then already exact) - see DESIGN.md  */
-    int32_t skip_n;
-    int32_t reserved;
+    const float* skip_if_unit[2]; /* device scalars or NULL: when at least one is given and every
+                                  given one equals 1, the launch returns at once (the gradients
+                                  written by the forward pass with unit upstream are then already
+                                  exact) - see DESIGN.md                                          */
     void* workspace;           /* plb_photo_workspace_bytes() bytes, zero-filled ONCE by the caller */
     size_t workspace_bytes;
     plb_photo_job jobs[PLB_MAX_JOBS];
@@ -125,9 +124,7 @@ typedef struct plb_smooth_args {
     int32_t want_grad;
     float* loss;                        /* out (written) [1]                                        */
     const float* upstream;              /* device scalar or NULL (=1)                               */
-    const float* skip_if_unit;          /* as in plb_photo_args                                     */
-    int32_t skip_n;
-    int32_t reserved;
+    const float* skip_if_unit[2];       /* as in plb_photo_args                                     */
     void* workspace;                    /* plb_smooth_workspace_bytes() bytes, zero-filled once     */
     size_t workspace_bytes;
 } plb_smooth_args;

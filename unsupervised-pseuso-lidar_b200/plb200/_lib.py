@@ -56,9 +56,7 @@ class PhotoArgs(C.Structure):
         ("loss", _fp),
         ("entry_loss", _fp),
         ("upstream", _fp),
-        ("skip_if_unit", _fp),
-        ("skip_n", C.c_int32),
-        ("reserved", C.c_int32),
+        ("skip_if_unit", _fp * 2),
         ("workspace", _fp),
         ("workspace_bytes", C.c_size_t),
         ("jobs", PhotoJob * MAX_JOBS),
@@ -80,9 +78,7 @@ class SmoothArgs(C.Structure):
         ("want_grad", C.c_int32),
         ("loss", _fp),
         ("upstream", _fp),
-        ("skip_if_unit", _fp),
-        ("skip_n", C.c_int32),
-        ("reserved", C.c_int32),
+        ("skip_if_unit", _fp * 2),
         ("workspace", _fp),
         ("workspace_bytes", C.c_size_t),
     ]

@@ -272,10 +272,10 @@ __device__ __forceinline__ void up_coord(int dst, float scale, int in_size, int&
 
 // Backward relaunch guard: true when every upstream gradient equals 1, i.e. the
 // gradients the forward pass already wrote (unit upstream) are exact.
-__device__ __forceinline__ bool skip_launch(const float* flags, int n) {
-    if (flags == nullptr) return false;
-    for (int k = 0; k < n; ++k)
-        if (__ldg(flags + k) != 1.0f) return false;
+__device__ __forceinline__ bool skip_launch(const float* const (&flags)[2]) {
+    if (flags[0] == nullptr && flags[1] == nullptr) return false;
+    if (flags[0] != nullptr && __ldg(flags[0]) != 1.0f) return false;
+    if (flags[1] != nullptr && __ldg(flags[1]) != 1.0f) return false;
     return true;
 }
 

@@ -245,7 +245,7 @@ template <bool GRAD, bool IMG_GRAD, int MAXSRC>
 __global__ void __launch_bounds__(PH_THREADS, (MAXSRC <= 2) ? 3 : 2)
 photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
     const plb_photo_args& a = p.a;
-    if (skip_launch(a.skip_if_unit, a.skip_n)) return;
+    if (skip_launch(a.skip_if_unit)) return;
 
     char* ws = (char*)a.workspace;
     int32_t* tickets = (int32_t*)(ws + p.L.tickets);
@@ -534,51 +534,120 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
 }
 
 // Transposed bilinear upsample (gather form, deterministic) + disp->depth chain:
-// g_disp[s][b,j,i] = dD/dd * sum over the full-resolution pixels whose
-// align_corners=False footprint touches low-res pixel (j,i).
-__global__ void __launch_bounds__(256)
-photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p) {
+// g_disp[s][b,j,i] = dD/dd * sum over the full-resolution pixels whose align_corners=False
+// footprint touches low-res pixel (j,i).  Separable and streaming: one block owns UT_ROWS
+// consecutive low-res rows of one image and a chunk of UT_CHUNK full-res columns (+ halo).
+// Stage 1: every thread walks DOWN one full-res column of the scratch plane once (coalesced,
+// independent loads) and adds each value into the (at most two) low-res rows it feeds; stage 2:
+// every low-res pixel gathers its ~2f column sums from shared memory with the exact up_coord
+// weights.  The launch is a compact list of (job, scale, image, row group, chunk) work items.
+constexpr int UT_THREADS = 256;
+constexpr int UT_CHUNK = 192;   // full-res columns owned per block (a multiple of every factor <= 64)
+constexpr int UT_HALO = 32;     // >= 1.5 * factor + 2 for factor <= 16
+constexpr int UT_ROWS = 8;      // low-res rows per block
+
+struct UpTItem { int jb, s, first_block, groups, chunks; };
+struct UpTLaunch {
+    int n_items;
+    int total_blocks;
+    UpTItem items[PLB_MAX_JOBS * PLB_MAX_SCALES];
+};
+
+__global__ void __launch_bounds__(UT_THREADS)
+photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_constant__ UpTLaunch u) {
     const plb_photo_args& a = p.a;
-    if (skip_launch(a.skip_if_unit, a.skip_n)) return;
-    const float* gup = (const float*)((const char*)a.workspace + p.L.gup);
-    const int jb = blockIdx.z / PLB_MAX_SCALES, s = blockIdx.z % PLB_MAX_SCALES, b = blockIdx.y;
-    if (jb >= a.n_jobs) return;
+    if (skip_launch(a.skip_if_unit)) return;
+    int it = 0;
+    while (it + 1 < u.n_items && (int)blockIdx.x >= u.items[it + 1].first_block) ++it;
+    const UpTItem item = u.items[it];
+    const int local = blockIdx.x - item.first_block;
+    const int chunk = local % item.chunks;
+    const int grp_all = local / item.chunks;            // (image, row group)
+    const int b = grp_all / item.groups, grp = grp_all - b * item.groups;
+    const int jb = item.jb, s = item.s;
     const plb_photo_job& job = a.jobs[jb];
-    if (s >= job.n_scales || job.g_disp[s] == nullptr) return;
     const int dh = job.dh[s], dw = job.dw[s], H = a.H, W = a.W;
-    if (dh == H && dw == W) return;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= dh * dw) return;
-    const int i = idx % dw, j = idx / dw;
+    const int j0 = grp * UT_ROWS, j1 = min(j0 + UT_ROWS, dh);   // low-res rows [j0, j1)
+    const int xc0 = chunk * UT_CHUNK;
+    const int tid = threadIdx.x;
     const float sx = (float)dw / (float)W, sy = (float)dh / (float)H;
-    const float fx = (float)W / (float)dw, fy = (float)H / (float)dh;
-    const int xlo = max((int)floorf(((float)i - 1.0f + 0.5f) * fx - 0.5f) - 1, 0);
-    const int xhi = min((int)ceilf(((float)i + 1.0f + 0.5f) * fx - 0.5f) + 1, W - 1);
-    const int ylo = max((int)floorf(((float)j - 1.0f + 0.5f) * fy - 0.5f) - 1, 0);
-    const int yhi = min((int)ceilf(((float)j + 1.0f + 0.5f) * fy - 0.5f) + 1, H - 1);
+    const float fy = (float)H / (float)dh, fx = (float)W / (float)dw;
+
+    constexpr int CW = UT_CHUNK + 2 * UT_HALO;   // 256 columns staged per block
+    __shared__ float s_col[UT_ROWS][CW];
+    __shared__ float s_l0[CW], s_l1[CW];
+    __shared__ int s_x0[CW];
+    constexpr int UT_TAPS = 40;                  // >= 2*16 + 5 full-res rows feed one low-res row
+    __shared__ float s_wr[UT_ROWS][UT_TAPS];     // per local low-res row: weights of its full-res rows
+    __shared__ int s_ybeg[UT_ROWS], s_ycnt[UT_ROWS];
+
+    const float* gup = (const float*)((const char*)a.workspace + p.L.gup);
     const float* g = gup + ((size_t)(jb * PLB_MAX_SCALES + s) * a.B + b) * (size_t)H * W;
-    float acc = 0.0f;
-    for (int y = ylo; y <= yhi; ++y) {
-        int y0, y1; float ly0, ly1;
-        up_coord(y, sy, dh, y0, y1, ly0, ly1);
-        float wy = (y0 == j ? ly0 : 0.0f) + (y1 == j ? ly1 : 0.0f);
-        if (wy == 0.0f) continue;
-        float row = 0.0f;
-        for (int x = xlo; x <= xhi; ++x) {
-            int x0, x1; float lx0, lx1;
-            up_coord(x, sx, dw, x0, x1, lx0, lx1);
-            float wx = (x0 == i ? lx0 : 0.0f) + (x1 == i ? lx1 : 0.0f);
-            if (wx != 0.0f) row += wx * __ldcg(g + (size_t)y * W + x);
+    // per low-res row j: conservative full-res window, exact up_coord weights (zero outside the footprint)
+    for (int q = tid; q < UT_ROWS * UT_TAPS; q += UT_THREADS) {
+        const int r = q / UT_TAPS, k = q - r * UT_TAPS;
+        const int j = j0 + r;
+        const int ylo = max((int)floorf(((float)j - 0.5f) * fy - 0.5f) - 1, 0);
+        const int yhi = min((int)ceilf(((float)j + 1.5f) * fy - 0.5f) + 1, H - 1);
+        float wgt = 0.0f;
+        if (j < j1 && ylo + k <= yhi) {
+            int y0, y1; float ly0, ly1;
+            up_coord(ylo + k, sy, dh, y0, y1, ly0, ly1);
+            wgt = (y0 == j ? ly0 : 0.0f) + (y1 == j ? ly1 : 0.0f);
         }
-        acc += wy * row;
+        s_wr[r][k] = wgt;
+        if (k == 0) { s_ybeg[r] = ylo; s_ycnt[r] = (j < j1) ? min(yhi - ylo + 1, UT_TAPS) : 0; }
     }
-    float chain = 1.0f;
-    if (!a.input_is_depth) {
-        float d = __ldg(job.disp[s] + (size_t)b * dh * dw + idx);
-        float D = 1.0f / (a.disp_a * d + a.disp_b);
-        chain = -a.disp_a * D * D;
+    __syncthreads();
+    {
+        const int k = tid;             // CW == UT_THREADS: one staged column per thread
+        const int x = xc0 - UT_HALO + k;
+        float l0 = 0.0f, l1 = 0.0f;
+        int x0 = -1000000;
+        const bool xin = x >= 0 && x < W;
+        if (xin) {
+            int x1;
+            up_coord(x, sx, dw, x0, x1, l0, l1);
+            if (x1 == x0) { l0 += l1; l1 = 0.0f; }   // clamped at the right border: both taps are x0
+        }
+        s_x0[k] = x0; s_l0[k] = l0; s_l1[k] = l1;
+#pragma unroll 1
+        for (int r = 0; r < UT_ROWS; ++r) {
+            float acc = 0.0f;
+            if (xin) {
+                const float* gx = g + (s_ybeg[r] * W + x);
+                const int cnt = s_ycnt[r];
+#pragma unroll 4
+                for (int t = 0; t < cnt; ++t) acc = fmaf(s_wr[r][t], __ldg(gx + t * W), acc);
+            }
+            s_col[r][k] = acc;
+        }
     }
-    job.g_disp[s][(size_t)b * dh * dw + idx] = acc * chain;
+    __syncthreads();
+    // low-res columns whose centre of mass lies in the owned chunk: i in [i_lo, i_hi)
+    const int i_lo = (int)ceilf((float)xc0 * sx - 1e-4f);
+    const int i_hi = min((int)ceilf((float)min(xc0 + UT_CHUNK, W) * sx - 1e-4f), dw);
+    const int ni = i_hi - i_lo;
+    for (int q = tid; q < ni * (j1 - j0); q += UT_THREADS) {
+        const int r = q / ni, i = i_lo + (q - r * ni);
+        const int xlo = max((int)floorf(((float)i - 0.5f) * fx - 0.5f) - 1, 0);
+        const int xhi = min((int)ceilf(((float)i + 1.5f) * fx - 0.5f) + 1, W - 1);
+        float acc = 0.0f;
+        for (int x = xlo; x <= xhi; ++x) {
+            const int k = x - (xc0 - UT_HALO);
+            if (k < 0 || k >= CW) continue;   // cannot happen while factor <= 16
+            const int x0 = s_x0[k];
+            const float w = (x0 == i ? s_l0[k] : 0.0f) + (x0 + 1 == i ? s_l1[k] : 0.0f);
+            acc = fmaf(w, s_col[r][k], acc);
+        }
+        float chain = 1.0f;
+        const size_t o = (size_t)b * dh * dw + (size_t)(j0 + r) * dw + i;
+        if (!a.input_is_depth) {
+            const float D = 1.0f / (a.disp_a * __ldg(job.disp[s] + o) + a.disp_b);
+            chain = -a.disp_a * D * D;
+        }
+        job.g_disp[s][o] = acc * chain;
+    }
 }
 
 static int validate_photo(const plb_photo_args* a) {
@@ -601,6 +670,7 @@ static int validate_photo(const plb_photo_args* a) {
         for (int s = 0; s < job.n_scales; ++s) {
             if (job.disp[s] == nullptr) return PLB_ENULL;
             if (job.dh[s] < 1 || job.dw[s] < 1 || job.dh[s] > a->H || job.dw[s] > a->W) return PLB_EINVAL;
+            if (job.dw[s] * 16 < a->W || job.dh[s] * 16 < a->H) return PLB_EINVAL;  // upsampling factor <= 16
         }
     }
     if (a->workspace == nullptr) return PLB_EWORKSPACE;
@@ -702,13 +772,20 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     ++g_launches;
     PLB_CHECK_LAUNCH();
     if (lowres_grad) {
-        int maxpx = 0;
+        UpTLaunch u;
+        u.n_items = 0;
+        u.total_blocks = 0;
         for (int j = 0; j < a->n_jobs; ++j)
-            for (int s = 0; s < a->jobs[j].n_scales; ++s)
-                if (a->jobs[j].dh[s] != a->H || a->jobs[j].dw[s] != a->W)
-                    maxpx = max(maxpx, a->jobs[j].dh[s] * a->jobs[j].dw[s]);
-        dim3 g2((maxpx + 255) / 256, a->B, a->n_jobs * PLB_MAX_SCALES);
-        photo_upsample_T_kernel<<<g2, 256, 0, st>>>(p);
+            for (int s = 0; s < a->jobs[j].n_scales; ++s) {
+                const plb_photo_job& job = a->jobs[j];
+                if (!job.g_disp[s] || (job.dh[s] == a->H && job.dw[s] == a->W)) continue;
+                UpTItem& it = u.items[u.n_items++];
+                it.jb = j; it.s = s; it.first_block = u.total_blocks;
+                it.groups = (job.dh[s] + UT_ROWS - 1) / UT_ROWS;
+                it.chunks = (a->W + UT_CHUNK - 1) / UT_CHUNK;
+                u.total_blocks += it.groups * it.chunks * a->B;
+            }
+        photo_upsample_T_kernel<<<u.total_blocks, UT_THREADS, 0, st>>>(p, u);
         ++g_launches;
         PLB_CHECK_LAUNCH();
     }

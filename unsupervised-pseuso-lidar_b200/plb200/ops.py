@@ -79,9 +79,11 @@ class LossConfig:
         self.mode, self.flags = mode, flags
 
 
-def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt, g_refs, out, up2, skip):
+def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt, g_refs, out, up, skip):
     """One photometric launch (all directions) + one smoothness launch.
-    out: float32[2] (loss_mam, loss_smooth).  up2: float32[2] upstream or None."""
+    out: float32[2] (loss_mam, loss_smooth).  up: None or (g_mam, g_smooth) 0-d float32
+    CUDA tensors (either may be None = that part is inactive)."""
+    up_ptr = [0, 0] if up is None else [_ptr(up[0]), _ptr(up[1])]
     dev = tgt.device
     B, _, H, W = tgt.shape
     st = _stream()
@@ -97,9 +99,9 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
         a.poses, a.K = poses.data_ptr(), K.data_ptr()
         a.g_poses = _ptr(g_poses) if want_grad else 0
         a.loss = out.data_ptr()
-        a.upstream = up2.data_ptr() if up2 is not None else 0
-        a.skip_if_unit = up2.data_ptr() if (up2 is not None and skip) else 0
-        a.skip_n = 2
+        a.upstream = up_ptr[0]
+        if skip:
+            a.skip_if_unit[0], a.skip_if_unit[1] = up_ptr[0], up_ptr[1]
         n_jobs = len(pyr)
         a.n_jobs = n_jobs
         entries = sum(len(p) for p in pyr)
@@ -147,9 +149,9 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
         s_.disp_a, s_.disp_b, s_.scale_decay = cfg.disp_a, cfg.disp_b, cfg.scale_decay
         s_.want_grad = int(want_grad)
         s_.loss = out.data_ptr() + 4
-        s_.upstream = up2.data_ptr() + 4 if up2 is not None else 0
-        s_.skip_if_unit = up2.data_ptr() if (up2 is not None and skip) else 0
-        s_.skip_n = 2
+        s_.upstream = up_ptr[1]
+        if skip:
+            s_.skip_if_unit[0], s_.skip_if_unit[1] = up_ptr[0], up_ptr[1]
         nbytes = lib.plb_smooth_workspace_bytes(s_)
         ws = _workspace("smooth", nbytes, dev)
         s_.workspace, s_.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -175,11 +177,12 @@ class FusedLossFn(torch.autograd.Function):
         img_grad = need[1] or any(need[4:4 + cfg.n_src])
         any_grad = img_grad or need[2] or any(need[4 + cfg.n_src:])
         fused = any_grad and cfg.fused_backward and not img_grad
-        out = torch.zeros(2, dtype=torch.float32, device=tgt.device)
+        both = cfg.do_photo and cfg.do_smooth
+        out = (torch.empty if both else torch.zeros)(2, dtype=torch.float32, device=tgt.device)
         g_pyr = g_poses = None
         if fused:
             g_pyr = [[torch.empty_like(d) for d in p] for p in pyr]
-            g_poses = torch.zeros_like(poses)
+            g_poses = (torch.empty_like if cfg.do_photo else torch.zeros_like)(poses)
             if not cfg.do_photo:
                 for j in range(1, len(g_pyr)):
                     for g in g_pyr[j]:
@@ -194,15 +197,14 @@ class FusedLossFn(torch.autograd.Function):
         cfg = ctx.cfg
         tgt, refs, poses, K, pyr, g_pyr, g_poses = ctx.tensors
         dev = tgt.device
-        parts = []
+        up = []
         for g, active in ((g_mam, cfg.do_photo), (g_smooth, cfg.do_smooth)):
             if not active:
-                parts.append(torch.ones((), dtype=torch.float32, device=dev))
+                up.append(None)                      # inactive part: no launch reads it
             elif g is None:
-                parts.append(torch.zeros((), dtype=torch.float32, device=dev))
+                up.append(torch.zeros((), dtype=torch.float32, device=dev))
             else:
-                parts.append(g.detach().to(torch.float32).reshape(()))
-        up2 = torch.stack(parts).contiguous()
+                up.append(g.detach().to(torch.float32).reshape(()).contiguous())
         g_tgt = g_refs = None
         if ctx.fused and not getattr(ctx, "used", False):
             # first backward: the buffers written by the forward launch are handed to autograd
@@ -211,7 +213,7 @@ class FusedLossFn(torch.autograd.Function):
         else:
             skip = False
             g_pyr = [[torch.empty_like(d) for d in p] for p in pyr]
-            g_poses = torch.zeros_like(poses)
+            g_poses = (torch.empty_like if cfg.do_photo else torch.zeros_like)(poses)
             if not cfg.do_photo:
                 for j in range(1, len(g_pyr)):
                     for g in g_pyr[j]:
@@ -220,7 +222,7 @@ class FusedLossFn(torch.autograd.Function):
                 g_tgt = torch.zeros_like(tgt)
                 g_refs = [torch.zeros_like(r) for r in refs]
         scratch = torch.empty(2, dtype=torch.float32, device=dev)
-        _launch_loss(cfg, tgt, refs, poses, K, pyr, True, g_pyr, g_poses, g_tgt, g_refs, scratch, up2, skip)
+        _launch_loss(cfg, tgt, refs, poses, K, pyr, True, g_pyr, g_poses, g_tgt, g_refs, scratch, up, skip)
         need = ctx.needs_input_grad
         grads = [None, g_tgt if need[1] else None, g_poses if need[2] else None, None]
         for i in range(cfg.n_src):
