@@ -96,10 +96,26 @@ def test_oracle_parity_odd_shapes(B, H, W, S, regime, noise):
         e32 = rel_err(r32, r64)
         assert rel_err(ours, r64) < max(GRAD_TOL, 3 * e32), (what, e32)
         assert rel_err(ours, r32) < max(GRAD_TOL, 4 * e32), (what, e32)
+
+    def check_field(ours, r32, r64, what):
+        """Per-pixel gradient maps: one sample that lands on the other side of a pixel boundary
+        changes that pixel's gradient completely (and moves the norm-relative error of a 32k-pixel
+        map by 5e-3), which fp32 rounding of the coordinate decides.  So: all but a small fraction
+        of the elements agree to 1e-4 of the map's scale, and that fraction is bounded by a multiple
+        of the fp32 oracle's own."""
+        r64 = r64.double()
+        scale = float(r64.abs().max())
+        bad_ours = int(((ours.double() - r64).abs() > GRAD_TOL * scale).sum())
+        bad_ref = int(((r32.double() - r64).abs() > GRAD_TOL * scale).sum())
+        # one flipped sample touches up to 4 elements of a low-resolution map: allow 4 flips
+        assert bad_ours <= max(16, int(5e-4 * r64.numel())) + 4 * bad_ref, (what, bad_ours, bad_ref, r64.numel())
+        # the elements that agree must make the norm agree too
+        ok = (ours.double() - r64).abs() <= GRAD_TOL * scale
+        assert rel_err(ours.double()[ok], r64[ok]) < GRAD_TOL, what
     check(p.grad.cpu(), rp.grad, rp64.grad, "poses")
     for f, fr in enumerate(disp):
         for s, t in enumerate(fr):
-            check(t.grad.cpu(), rd[f][s].grad, rd64[f][s].grad, ("disp", f, s))
+            check_field(t.grad.cpu(), rd[f][s].grad, rd64[f][s].grad, ("disp", f, s))
 
 
 def test_non_unit_upstream_recomputes():

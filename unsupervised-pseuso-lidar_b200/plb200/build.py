@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("PLB_NVCC_EXTRA", "").split()
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

@@ -113,7 +113,11 @@ __device__ __forceinline__ void photo_pixel(const float* __restrict__ cb, float*
     const float cx = fmaf(D, Ax, Pa.w), cy = fmaf(D, Ay, Pb.w);
     const float ze = fmaf(D, Az, Pc.w) + 1e-5f;
     const float inv = rcp_nr(ze);
-    const float px = cx * inv, py = cy * inv;
+    // quotient + one residual correction: as accurate as an IEEE divide (the sample position is the
+    // difference of two ~W-sized numbers, so every ulp of px is 6e-5 px of bilinear weight)
+    float px = cx * inv, py = cy * inv;
+    px = fmaf(fmaf(-px, ze, cx), inv, px);
+    py = fmaf(fmaf(-py, ze, cy), inv, py);
     // clamp keeps float->int defined; NaN maps to -2 (out of the image)
     const float ixc = fminf(fmaxf(px, -2.0f), (float)(W + 1));
     const float iyc = fminf(fmaxf(py, -2.0f), (float)(H + 1));
