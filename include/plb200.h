@@ -86,12 +86,12 @@ typedef struct plb_photo_args {
     int32_t input_is_depth;    /* 0: depth = 1/(disp_a*disp+disp_b); 1: `disp` already holds depth */
     float disp_a, disp_b;      /* 10, 0.01 in the reference                                        */
     int32_t want_grad;         /* 0: loss only (no_grad / eval)                                    */
-    int32_t deterministic;     /* 1: image gradients accumulate in 64-bit fixed point (see g_fix)  */
+    int32_t deterministic;     /* reserved (loss, pose and disparity gradients are always
+                                  bitwise repeatable; image gradients use float atomics)            */
     const float* poses;        /* [B,n_pose,6]                                                     */
     const void* K;             /* [B,3,3] f64 or f32                                               */
     float* g_poses;            /* out (written) [B,n_pose,6]; NULL = not wanted                    */
     float* loss;               /* out (written) [1]                                                */
-    float* entry_loss;         /* out (written) [n_jobs*PLB_MAX_SCALES] per-(job,scale) means or NULL */
     const float* upstream;     /* device scalar d L / d loss; NULL = 1                             */
     const float* skip_if_unit[2]; /* device scalars or NULL: when at least one is given and every
                                   given one equals 1, the launch returns at once (the gradients

@@ -54,7 +54,6 @@ class PhotoArgs(C.Structure):
         ("K", _fp),
         ("g_poses", _fp),
         ("loss", _fp),
-        ("entry_loss", _fp),
         ("upstream", _fp),
         ("skip_if_unit", _fp * 2),
         ("workspace", _fp),
