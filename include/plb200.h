@@ -181,6 +181,36 @@ int plb_disp_to_depth_backward(const float* disp, const float* g_depth, int64_t 
                                float* g_disp, void* stream);
 
 /*
+ * Stand-alone photometric maps (the reference's dormant functions) and their vjp.
+ *   w_ssim=1,    w_l1=0,    clip<0 : SSIM.standard_loss (losses.py:12-54)
+ *   w_ssim=0.85, w_l1=0.15, clip=0.5: Losses.compute_photometric_loss (losses.py:66-84);
+ *   w_ssim=0,    w_l1=1             : its no_ssim=True branch (losses.py:73-74)
+ * out = w_ssim * clamp((1 - SSIM3x3(x, y)) / 2, 0, 1) + w_l1 * |y - x|, ReflectionPad2d(1) borders;
+ * clip >= 0 additionally clamps at mean + clip * std (unbiased) of the whole map, the threshold being a
+ * detached device scalar (`threshold`, written by the forward call, read by the backward call).
+ */
+typedef struct plb_photomap_args {
+    int32_t B, C, H, W;
+    const float* x;            /* [B,C,H,W] predicted image                                       */
+    const float* y;            /* [B,C,H,W] target image                                          */
+    float C1, C2;              /* 1e-4, 9e-4 in the reference                                      */
+    float w_ssim, w_l1;
+    float clip;                /* < 0: no clip                                                     */
+    int32_t reserved;
+    float* out;                /* fwd out [B,C,H,W]                                                */
+    float* threshold;          /* device scalar (clip >= 0)                                        */
+    const float* g_out;        /* bwd in  [B,C,H,W]                                                */
+    float* g_x;                /* bwd out (written) or NULL                                        */
+    float* g_y;                /* bwd out (written) or NULL                                        */
+    void* workspace;           /* plb_photometric_map_workspace_bytes() bytes, zero-filled once (clip >= 0) */
+    size_t workspace_bytes;
+} plb_photomap_args;
+
+size_t plb_photometric_map_workspace_bytes(const plb_photomap_args* args);
+int plb_photometric_map(const plb_photomap_args* args, void* stream);
+int plb_photometric_map_backward(const plb_photomap_args* args, void* stream);
+
+/*
  * Depth image -> pseudo-LiDAR point cloud in the velodyne frame.
  * Replaces PseudoLiDAR.project_PL (pseudo-lidar/utils/PseudoLiDAR.py:69-110),
  * fp64 arithmetic in the reference's operation order, order-preserving

@@ -105,6 +105,25 @@ class WarpArgs(C.Structure):
     ]
 
 
+class PhotomapArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("x", _fp),
+        ("y", _fp),
+        ("C1", C.c_float), ("C2", C.c_float),
+        ("w_ssim", C.c_float), ("w_l1", C.c_float),
+        ("clip", C.c_float),
+        ("reserved", C.c_int32),
+        ("out", _fp),
+        ("threshold", _fp),
+        ("g_out", _fp),
+        ("g_x", _fp),
+        ("g_y", _fp),
+        ("workspace", _fp),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class CloudArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
@@ -137,6 +156,9 @@ SYMBOLS = {
     "plb_pose_matrix_backward": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, C.c_void_p]),
     "plb_disp_to_depth": (C.c_int, [_fp, C.c_int64, C.c_float, C.c_float, _fp, C.c_void_p]),
     "plb_disp_to_depth_backward": (C.c_int, [_fp, _fp, C.c_int64, C.c_float, C.c_float, _fp, C.c_void_p]),
+    "plb_photometric_map_workspace_bytes": (C.c_size_t, [C.POINTER(PhotomapArgs)]),
+    "plb_photometric_map": (C.c_int, [C.POINTER(PhotomapArgs), C.c_void_p]),
+    "plb_photometric_map_backward": (C.c_int, [C.POINTER(PhotomapArgs), C.c_void_p]),
     "plb_cloud_workspace_bytes": (C.c_size_t, [C.POINTER(CloudArgs)]),
     "plb_cloud_project": (C.c_int, [C.POINTER(CloudArgs), C.c_void_p]),
     "plb_version": (C.c_char_p, []),

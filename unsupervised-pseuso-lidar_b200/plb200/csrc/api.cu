@@ -18,6 +18,9 @@ int pose_matrix_launch(const float*, int, int, int, int, float*, cudaStream_t);
 int pose_matrix_bwd_launch(const float*, int, int, int, int, const float*, float*, cudaStream_t);
 int disp_to_depth_launch(const float*, int64_t, float, float, float*, cudaStream_t);
 int disp_to_depth_bwd_launch(const float*, const float*, int64_t, float, float, float*, cudaStream_t);
+int photomap_launch(const plb_photomap_args*, cudaStream_t);
+int photomap_bwd_launch(const plb_photomap_args*, cudaStream_t);
+size_t photomap_workspace_bytes(const plb_photomap_args*);
 int cloud_launch(const plb_cloud_args*, cudaStream_t);
 size_t cloud_workspace_bytes(const plb_cloud_args*);
 }  // namespace plb
@@ -56,6 +59,12 @@ int plb_disp_to_depth(const float* disp, int64_t n, float a, float b, float* dep
 int plb_disp_to_depth_backward(const float* disp, const float* g_depth, int64_t n, float a, float b, float* g_disp,
                                void* stream) {
     return plb::disp_to_depth_bwd_launch(disp, g_depth, n, a, b, g_disp, (cudaStream_t)stream);
+}
+
+size_t plb_photometric_map_workspace_bytes(const plb_photomap_args* a) { return a ? plb::photomap_workspace_bytes(a) : 0; }
+int plb_photometric_map(const plb_photomap_args* a, void* stream) { return plb::photomap_launch(a, (cudaStream_t)stream); }
+int plb_photometric_map_backward(const plb_photomap_args* a, void* stream) {
+    return plb::photomap_bwd_launch(a, (cudaStream_t)stream);
 }
 
 size_t plb_cloud_workspace_bytes(const plb_cloud_args* a) { return a ? plb::cloud_workspace_bytes(a) : 0; }

@@ -19,79 +19,9 @@
 // registers across all of a warp's units, reduced warp -> block -> (job, image)
 // -> launch in a fixed order by "last block done" epilogues: one launch, no
 // atomics on the results, bitwise repeatable.
-#include "common.cuh"
+#include "photo_common.cuh"
 
 namespace plb {
-
-constexpr int PH_THREADS = 256;
-constexpr int PH_WARPS = PH_THREADS / 32;
-constexpr int PH_NREC = PLB_MAX_SRC * 12 + 1;  // per (job,image) record: dP[src][12], sum|diff|
-constexpr int PH_REC_STRIDE = 56;
-#ifndef PH_PREFETCH_ROWS
-#define PH_PREFETCH_ROWS 2
-#endif              // floats per (block, set) record: [0]=pair, [1..] values
-
-struct PhotoLayout {
-    size_t tickets;   // int32 [n_pairs + 1]
-    size_t records;   // float [grid][2][PH_REC_STRIDE]
-    size_t ws_pose;   // float [n_pairs][MAX_SRC][6]
-    size_t ws_loss;   // float [n_pairs]
-    size_t gup;       // float [n_jobs][MAX_SCALES][B*H*W]  (only when a low scale carries a gradient)
-    size_t total;
-};
-
-// Launch-time constants computed once on the host (kept out of the kernel's instruction stream).
-struct PhotoLaunch {
-    plb_photo_args a;
-    PhotoLayout L;
-    int grid;                            // number of blocks
-    int n_warps;                         // grid * PH_WARPS
-    int strips;                          // ceil(W / 32)
-    int units_per_pair;                  // strips * H
-    int n_pairs;                         // n_jobs * B
-    int unit_weight[PLB_MAX_JOBS];       // n_scales * n_src
-    long long weight_start[PLB_MAX_JOBS + 1];  // cumulative weight at the start of each job
-    int unit_start[PLB_MAX_JOBS + 1];    // cumulative unit index at the start of each job
-    float w_e[PLB_MAX_JOBS];             // term_weight / (3*B*H*W)
-    int lowres[PLB_MAX_JOBS];            // bit s set: scale s is not full resolution
-    int share, share_rem;                // warp w starts at weight w*share + min(w, share_rem)
-};
-
-__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-static bool photo_has_lowres_grad(const plb_photo_args& a) {
-    if (!a.want_grad) return false;
-    for (int j = 0; j < a.n_jobs; ++j)
-        for (int s = 0; s < a.jobs[j].n_scales; ++s)
-            if (a.jobs[j].g_disp[s] && (a.jobs[j].dh[s] != a.H || a.jobs[j].dw[s] != a.W)) return true;
-    return false;
-}
-
-static int photo_max_grid(const plb_photo_args& a) {
-    // upper bound used for sizing the workspace (the launch may use fewer blocks)
-    const long long strips = (a.W + 31) / 32;
-    const long long units = strips * a.H * (long long)a.B * a.n_jobs;
-    (void)units;
-    long long g = 148LL * 8;                         // 148 SMs x at most 8 resident blocks
-    const long long pairs_bound = 1LL * a.n_jobs * a.B * PLB_MAX_SCALES * PLB_MAX_SRC + 2;
-    if (g < pairs_bound) g = pairs_bound;
-    return (int)g;
-}
-
-static PhotoLayout photo_layout(const plb_photo_args& a) {
-    PhotoLayout L;
-    const size_t n_pairs = (size_t)a.n_jobs * a.B;
-    size_t off = 0;
-    L.tickets = off; off = align_up(off + sizeof(int32_t) * (n_pairs + 1), 256);
-    L.records = off; off = align_up(off + sizeof(float) * (size_t)photo_max_grid(a) * 2 * PH_REC_STRIDE, 256);
-    L.ws_pose = off; off = align_up(off + sizeof(float) * n_pairs * PLB_MAX_SRC * 6, 256);
-    L.ws_loss = off; off = align_up(off + sizeof(float) * n_pairs, 256);
-    L.gup = off;
-    if (photo_has_lowres_grad(a))
-        off = align_up(off + sizeof(float) * (size_t)a.n_jobs * PLB_MAX_SCALES * a.B * a.H * a.W, 256);
-    L.total = off;
-    return L;
-}
 
 // ---------------------------------------------------------------------------------------------
 // One target pixel against one source at one depth: project, sample, L1, and (GRAD) the
@@ -204,23 +134,6 @@ __device__ __forceinline__ void photo_pixel(const float* __restrict__ cb, float*
         }
     }
 }
-
-// shared-memory context of one (job, image) pair, built once per block: K^-1, P per source and
-// every base pointer already offset to image b, so the unit loop does no 64-bit address maths.
-struct __align__(16) PairConst {
-    float4 P[PLB_MAX_SRC][3];
-    float kinv[12];
-    const float* tgt;
-    float* g_tgt;
-    const float* src[PLB_MAX_SRC];
-    float* g_src[PLB_MAX_SRC];
-    const float* disp[PLB_MAX_SCALES];
-    float* g_disp[PLB_MAX_SCALES];   // full-res scales: the user's buffer; low-res scales: the gup scratch plane
-    int dh[PLB_MAX_SCALES], dw[PLB_MAX_SCALES];
-    float sx[PLB_MAX_SCALES], sy[PLB_MAX_SCALES];
-    int n_src, n_scales, lowres, pad;
-    float w_e, pad2[3];
-};
 
 template <int MAXSRC>
 __device__ __forceinline__ void flush_acc(float (&acc)[MAXSRC][12], float& l1acc, float* rec, int lane) {
@@ -654,7 +567,7 @@ photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_cons
     }
 }
 
-static int validate_photo(const plb_photo_args* a) {
+int validate_photo(const plb_photo_args* a) {
     if (a == nullptr) return PLB_ENULL;
     if (a->B < 1 || a->H < 2 || a->W < 2 || a->n_jobs < 1 || a->n_jobs > PLB_MAX_JOBS || a->n_pose < 1)
         return PLB_EINVAL;
@@ -711,7 +624,32 @@ static int sm_count() {
     return cached;
 }
 
+int photo_upsample_T_launch(const PhotoLaunch& p, cudaStream_t st) {
+    const plb_photo_args* a = &p.a;
+    {
+        UpTLaunch u;
+        u.n_items = 0;
+        u.total_blocks = 0;
+        for (int j = 0; j < a->n_jobs; ++j)
+            for (int s = 0; s < a->jobs[j].n_scales; ++s) {
+                const plb_photo_job& job = a->jobs[j];
+                if (!job.g_disp[s] || (job.dh[s] == a->H && job.dw[s] == a->W)) continue;
+                UpTItem& it = u.items[u.n_items++];
+                it.jb = j; it.s = s; it.first_block = u.total_blocks;
+                it.groups = (job.dh[s] + UT_ROWS - 1) / UT_ROWS;
+                it.chunks = (a->W + UT_CHUNK - 1) / UT_CHUNK;
+                u.total_blocks += it.groups * it.chunks * a->B;
+            }
+        photo_upsample_T_kernel<<<u.total_blocks, UT_THREADS, 0, st>>>(p, u);
+        ++g_launches;
+        PLB_CHECK_LAUNCH();
+    }
+    return PLB_OK;
+}
+
 int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
+    if (a != nullptr && a->n_jobs >= 1 && a->n_jobs <= PLB_MAX_JOBS && a->jobs[0].mode == PLB_PHOTO_MIN_REPROJ)
+        return photo_min_launch(a, st);
     int rc = validate_photo(a);
     if (rc != PLB_OK) return rc;
     PhotoLaunch p;
@@ -776,22 +714,8 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     ++g_launches;
     PLB_CHECK_LAUNCH();
     if (lowres_grad) {
-        UpTLaunch u;
-        u.n_items = 0;
-        u.total_blocks = 0;
-        for (int j = 0; j < a->n_jobs; ++j)
-            for (int s = 0; s < a->jobs[j].n_scales; ++s) {
-                const plb_photo_job& job = a->jobs[j];
-                if (!job.g_disp[s] || (job.dh[s] == a->H && job.dw[s] == a->W)) continue;
-                UpTItem& it = u.items[u.n_items++];
-                it.jb = j; it.s = s; it.first_block = u.total_blocks;
-                it.groups = (job.dh[s] + UT_ROWS - 1) / UT_ROWS;
-                it.chunks = (a->W + UT_CHUNK - 1) / UT_CHUNK;
-                u.total_blocks += it.groups * it.chunks * a->B;
-            }
-        photo_upsample_T_kernel<<<u.total_blocks, UT_THREADS, 0, st>>>(p, u);
-        ++g_launches;
-        PLB_CHECK_LAUNCH();
+        const int rc2 = photo_upsample_T_launch(p, st);
+        if (rc2 != PLB_OK) return rc2;
     }
     return PLB_OK;
 }

@@ -1,0 +1,496 @@
+// Fused SSIM + L1 photometric loss with per-pixel minimum reprojection and automasking
+// (the reference's dormant path: losses.py:12-84,94-96,154-162 and
+// notes/toy_problem/losses.py:107-129), forward and gradients in one launch.
+//
+//   rp_i  = 0.85 * clamp((1 - SSIM3x3(warp_i, tgt)) / 2, 0, 1) + 0.15 * |tgt - warp_i|     per channel
+//   m     = min_i rp_i ;  mu = [m < min_i photo(src_i, tgt)]  (automask) ;  loss = mean_px max_c (mu * m)
+//   scales are averaged (losses.py:181); low scales warp with the bilinearly upsampled depth.
+//
+// One block = one 32x8 tile of one target image, all scales and sources.  SSIM needs the warped
+// image on a 3x3 neighbourhood and its gradient needs the SSIM terms of the 3x3 neighbours, so
+// per scale the block (1) warps the tile + 2-pixel halo into shared memory (reflected
+// coordinates at the image border, exactly ReflectionPad2d(1)), (2) evaluates SSIM / the
+// photometric mix / min / mask / channel max on tile + 1 halo, keeping for every pixel the
+// selected (channel, source) and the three coefficients of d rp / d warped(q) = a + b*x_q + c*y_q,
+// (3) gathers d loss / d warped for the tile pixels from their 3x3 neighbours (with the
+// multiplicities reflection padding induces) and pushes it through the bilinear sampler and the
+// projection as the L1 kernel does.  Reductions are fixed-order (bitwise repeatable).
+#include "photo_common.cuh"
+
+namespace plb {
+
+int validate_photo(const plb_photo_args* a);  // photo.cu
+
+constexpr int PM_THREADS = 256;
+constexpr int PM_W2 = PM_TW + 4, PM_H2 = PM_TH + 4;   // tile + 2 halo: 36 x 12
+constexpr int PM_W1 = PM_TW + 2, PM_H1 = PM_TH + 2;   // tile + 1 halo: 34 x 10
+constexpr int PM_N2 = PM_W2 * PM_H2;                  // 432
+constexpr int PM_N1 = PM_W1 * PM_H1;                  // 340
+
+struct PminLaunch {
+    plb_photo_args a;
+    PhotoLayout L;
+    int tiles_x, tiles;
+    float w_e;   // term_weight / (B*H*W): weight of one pixel's max_c in the loss
+    float C1, C2;
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // ReflectionPad2d(1) index rule extended so that any tile position maps inside the image
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);
+}
+
+struct MinProj { float Ax, Ay, Az, inv, px, py, fx, fy; int o00; unsigned mask; };
+
+__device__ __forceinline__ void pm_project(const float4 Pa, const float4 Pb, const float4 Pc, float rx, float ry,
+                                           float rz, float D, int H, int W, MinProj& q) {
+    q.Ax = fmaf(Pa.z, rz, fmaf(Pa.y, ry, Pa.x * rx));
+    q.Ay = fmaf(Pb.z, rz, fmaf(Pb.y, ry, Pb.x * rx));
+    q.Az = fmaf(Pc.z, rz, fmaf(Pc.y, ry, Pc.x * rx));
+    const float cx = fmaf(D, q.Ax, Pa.w), cy = fmaf(D, q.Ay, Pb.w);
+    const float ze = fmaf(D, q.Az, Pc.w) + 1e-5f;
+    q.inv = rcp_nr(ze);
+    float px = cx * q.inv, py = cy * q.inv;
+    px = fmaf(fmaf(-px, ze, cx), q.inv, px);
+    py = fmaf(fmaf(-py, ze, cy), q.inv, py);
+    q.px = px; q.py = py;
+    const float ixc = fminf(fmaxf(px, -2.0f), (float)(W + 1));
+    const float iyc = fminf(fmaxf(py, -2.0f), (float)(H + 1));
+    const float xf = floorf(ixc), yf = floorf(iyc);
+    const int x0 = (int)xf, y0 = (int)yf;
+    q.fx = ixc - xf; q.fy = iyc - yf;
+    q.o00 = y0 * W + x0;
+    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+    q.mask = (vx0 && vy0 ? 1u : 0u) | (vx1 && vy0 ? 2u : 0u) | (vx0 && vy1 ? 4u : 0u) | (vx1 && vy1 ? 8u : 0u);
+}
+
+__device__ __forceinline__ void pm_taps(const float* __restrict__ cb, int plane, int W, const MinProj& q,
+                                        float (&v)[3][4]) {
+    const bool mnw = q.mask & 1u, mne = q.mask & 2u, msw = q.mask & 4u, mse = q.mask & 8u;
+    const int o00 = q.o00, o01 = o00 + W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        v[c][0] = ldg_pred(cb + (o00 + c * plane), mnw); v[c][1] = ldg_pred(cb + (o00 + c * plane) + 1, mne);
+        v[c][2] = ldg_pred(cb + (o01 + c * plane), msw); v[c][3] = ldg_pred(cb + (o01 + c * plane) + 1, mse);
+    }
+}
+
+// depth at full-resolution pixel (x, y) of scale s (direct, or align_corners=False upsample of depth)
+__device__ __forceinline__ float pm_depth(const plb_photo_args& a, const PairConst& pc, int s, bool full, int x, int y,
+                                          int W) {
+    if (full) {
+        const float d = __ldg(pc.disp[s] + (y * W + x));
+        return a.input_is_depth ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
+    }
+    const float* disp_b = pc.disp[s];
+    const int dh = pc.dh[s], dw = pc.dw[s];
+    int x0, x1, y0, y1; float lx0, lx1, ly0, ly1;
+    up_coord(x, pc.sx[s], dw, x0, x1, lx0, lx1);
+    up_coord(y, pc.sy[s], dh, y0, y1, ly0, ly1);
+    float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
+    float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
+    if (!a.input_is_depth) {
+        v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
+        v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
+    }
+    return ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+}
+
+// 3x3 window statistics of one channel at tile+1 position (px1, py1): x from sx (tile+2 layout), y from sy
+struct WinY { float sy, syy; };
+__device__ __forceinline__ WinY win_y(const float* __restrict__ sy_, int k2) {
+    WinY w; w.sy = 0.0f; w.syy = 0.0f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const float y = sy_[k2 + dy * PM_W2 + dx];
+            w.sy += y; w.syy = fmaf(y, y, w.syy);
+        }
+    return w;
+}
+
+// photometric value of one (pixel, channel) and the coefficients of its derivative w.r.t. the
+// predicted image at window position q:  d rp / d x_q = ca + cb * x_q + cc * y_q   (+ cl at the centre)
+struct Photo { float rp, ca, cb, cc, cl; };
+__device__ __forceinline__ Photo photo_term(const float* __restrict__ sx_, const float* __restrict__ sy_, int k2,
+                                            const WinY wy, float C1, float C2, bool no_ssim) {
+    const float xc = sx_[k2], yc = sy_[k2];
+    Photo r;
+    const float diff = xc - yc;
+    const float sg = (diff > 0.0f ? 1.0f : 0.0f) - (diff < 0.0f ? 1.0f : 0.0f);
+    if (no_ssim) {
+        r.rp = fabsf(diff); r.ca = r.cb = r.cc = 0.0f; r.cl = sg;
+        return r;
+    }
+    float sx = 0.0f, sxx = 0.0f, sxy = 0.0f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const float x = sx_[k2 + dy * PM_W2 + dx], y = sy_[k2 + dy * PM_W2 + dx];
+            sx += x; sxx = fmaf(x, x, sxx); sxy = fmaf(x, y, sxy);
+        }
+    const float i9 = 1.0f / 9.0f;
+    const float mux = sx * i9, muy = wy.sy * i9;
+    const float mxx = mux * mux, myy = muy * muy, mxy = mux * muy;
+    const float sigx = sxx * i9 - mxx, sigy = wy.syy * i9 - myy, sigxy = sxy * i9 - mxy;
+    const float N1 = 2.0f * mxy + C1, N2 = 2.0f * sigxy + C2;
+    const float D1 = mxx + myy + C1, D2 = sigx + sigy + C2;
+    const float iD1 = 1.0f / D1, iD2 = 1.0f / D2;
+    const float ssim = (N1 * N2) * (iD1 * iD2);
+    const float h = (1.0f - ssim) * 0.5f;
+    r.rp = 0.85f * fminf(fmaxf(h, 0.0f), 1.0f) + 0.15f * fabsf(diff);
+    // d ssim / d x_q = (2/9) { [mu_y (N2 - N1)]/(D1 D2) - ssim mu_x (1/D1 - 1/D2) }  +  x_q (-(2/9) ssim / D2)
+    //                  + y_q ((2/9) N1 / (D1 D2));   d rp / d x_q = -0.425 * (that) inside the clamp
+    const float k = (h > 0.0f && h < 1.0f) ? (-0.425f * 2.0f * i9) : 0.0f;
+    r.ca = k * (muy * (N2 - N1) * (iD1 * iD2) - ssim * mux * (iD1 - iD2));
+    r.cb = k * (-ssim * iD2);
+    r.cc = k * (N1 * (iD1 * iD2));
+    r.cl = 0.15f * sg;
+    return r;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(PM_THREADS)
+photo_min_kernel(const __grid_constant__ PminLaunch p) {
+    const plb_photo_args& a = p.a;
+    if (skip_launch(a.skip_if_unit)) return;
+    char* ws = (char*)a.workspace;
+    int32_t* tickets = (int32_t*)(ws + p.L.tickets);
+    float* records = (float*)(ws + p.L.records);
+    float* ws_pose = (float*)(ws + p.L.ws_pose);
+    float* ws_loss = (float*)(ws + p.L.ws_loss);
+    float* gup = (float*)(ws + p.L.gup);
+
+    const int H = a.H, W = a.W, plane = H * W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int tx0 = (tile % p.tiles_x) * PM_TW, ty0 = (tile / p.tiles_x) * PM_TH;
+    const plb_photo_job& job = a.jobs[0];
+    const bool no_ssim = job.flags & PLB_PHOTO_NO_SSIM, automask = !(job.flags & PLB_PHOTO_NO_AUTOMASK);
+
+    __shared__ PairConst pc;
+    __shared__ float sT[3][PM_N2];                     // target, tile + 2 (reflected at the border)
+    __shared__ float sX[PLB_MAX_SRC][3][PM_N2];        // warped (or, for the automask pass, raw) sources
+    __shared__ float sAuto[3][PM_N1];                  // min_i photo(src_i, tgt) per channel
+    __shared__ float sCa[PM_N1], sCb[PM_N1], sCc[PM_N1], sCl[PM_N1];
+    __shared__ signed char sSel[PM_N1];                // channel + 4 * source of the selected term, -1 = none
+    __shared__ float s_rec[PM_THREADS / 32][PH_NREC + 3];
+    __shared__ float s_red[PH_NREC + 3];
+    __shared__ float s_part4[4][64];
+    __shared__ int s_flag;
+
+    // ---- prologue: K^-1, P per source, base pointers of image b ------------------------------------
+    {
+        const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
+        const size_t img = (size_t)b * 3 * plane;
+        if (warp == 0) {
+            if (lane == 0) kinv_f32(Kb, a.k_is_f64, pc.kinv);
+            if (lane == 1) {
+                pc.tgt = job.tgt + img;
+                pc.n_src = job.n_src; pc.n_scales = job.n_scales;
+                pc.w_e = p.w_e * (a.upstream ? __ldg(a.upstream) : 1.0f);
+            }
+            if (lane >= 4 && lane < 4 + job.n_scales) {
+                const int sc = lane - 4;
+                const int dh = job.dh[sc], dw = job.dw[sc];
+                pc.dh[sc] = dh; pc.dw[sc] = dw;
+                pc.sx[sc] = (float)dw / (float)W; pc.sy[sc] = (float)dh / (float)H;
+                pc.disp[sc] = job.disp[sc] + (size_t)b * dh * dw;
+                float* g = nullptr;
+                if (GRAD && job.g_disp[sc] != nullptr)
+                    g = (dh != H || dw != W) ? gup + ((size_t)sc * a.B + b) * plane : job.g_disp[sc] + (size_t)b * plane;
+                pc.g_disp[sc] = g;
+            }
+        } else if (warp == 1 && lane < job.n_src) {
+            float M[12], P[12];
+            pose_to_M(a.poses + ((size_t)b * a.n_pose + job.pose_index[lane]) * 6, a.rotation_mode, job.pose_inv[lane], M);
+            k_times_M(Kb, a.k_is_f64, M, P);
+            pc.P[lane][0] = make_float4(P[0], P[1], P[2], P[3]);
+            pc.P[lane][1] = make_float4(P[4], P[5], P[6], P[7]);
+            pc.P[lane][2] = make_float4(P[8], P[9], P[10], P[11]);
+            pc.src[lane] = job.src[lane] + img;
+        }
+    }
+    for (int k = tid; k < (PM_THREADS / 32) * (PH_NREC + 3); k += PM_THREADS) (&s_rec[0][0])[k] = 0.0f;
+    __syncthreads();
+    const int n_src = pc.n_src, n_scales = pc.n_scales;
+    const float w_e = pc.w_e / (float)n_scales;        // scales are averaged
+
+    // ---- target tile (+2, reflected) and the automask reference min_i photo(src_i, tgt) -------------
+    for (int k = tid; k < PM_N2; k += PM_THREADS) {
+        const int ly = k / PM_W2, lx = k - ly * PM_W2;
+        const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
+        const int o = gy * W + gx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sT[c][k] = __ldg(pc.tgt + (o + c * plane));
+        if (automask)
+            for (int i = 0; i < n_src; ++i)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sX[i][c][k] = __ldg(pc.src[i] + (o + c * plane));
+    }
+    __syncthreads();
+    if (automask) {
+        for (int k1 = tid; k1 < PM_N1; k1 += PM_THREADS) {
+            const int ly = k1 / PM_W1, lx = k1 - ly * PM_W1;
+            const int k2 = (ly + 1) * PM_W2 + (lx + 1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const WinY wy = win_y(sT[c], k2);
+                float m = 3.0e38f;
+                for (int i = 0; i < n_src; ++i) m = fminf(m, photo_term(sX[i][c], sT[c], k2, wy, p.C1, p.C2, no_ssim).rp);
+                sAuto[c][k1] = m;
+            }
+        }
+    }
+    __syncthreads();
+
+    float acc[PLB_MAX_SRC][12];
+    float lsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PLB_MAX_SRC; ++i)
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[i][k] = 0.0f;
+
+    // this thread's tile pixel
+    const int qx = tx0 + lane, qy = ty0 + warp;
+    const bool qin = qx < W && qy < H;
+    const int qk1 = (warp + 1) * PM_W1 + (lane + 1), qk2 = (warp + 2) * PM_W2 + (lane + 2);
+
+#pragma unroll 1
+    for (int s = 0; s < n_scales; ++s) {
+        const bool full = pc.dh[s] == H && pc.dw[s] == W;
+        // ---- (1) warp tile + 2 halo of every source into shared memory ---------------------------
+        for (int k = tid; k < PM_N2; k += PM_THREADS) {
+            const int ly = k / PM_W2, lx = k - ly * PM_W2;
+            const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
+            const float D = pm_depth(a, pc, s, full, gx, gy, W);
+            const float xf = (float)gx, yf = (float)gy;
+            const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
+            const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
+            const float rz = fmaf(pc.kinv[7], yf, pc.kinv[6] * xf) + pc.kinv[8];
+            for (int i = 0; i < n_src; ++i) {
+                MinProj q;
+                pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
+                float v[3][4];
+                pm_taps(pc.src[i], plane, W, q, v);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float top = fmaf(q.fx, v[c][1] - v[c][0], v[c][0]), bot = fmaf(q.fx, v[c][3] - v[c][2], v[c][2]);
+                    sX[i][c][k] = fmaf(q.fy, bot - top, top);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- (2) photometric mix, min over sources, automask, max over channels on tile + 1 -------
+        for (int k1 = tid; k1 < PM_N1; k1 += PM_THREADS) {
+            const int ly = k1 / PM_W1, lx = k1 - ly * PM_W1;
+            const int gx = tx0 + lx - 1, gy = ty0 + ly - 1;
+            const int k2 = (ly + 1) * PM_W2 + (lx + 1);
+            float best = 0.0f, bca = 0.0f, bcb = 0.0f, bcc = 0.0f, bcl = 0.0f;
+            int bsel = -1;
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const WinY wy = win_y(sT[c], k2);
+                    Photo m; m.rp = 3.0e38f; m.ca = m.cb = m.cc = m.cl = 0.0f;
+                    int mi = 0;
+                    for (int i = 0; i < n_src; ++i) {
+                        const Photo r = photo_term(sX[i][c], sT[c], k2, wy, p.C1, p.C2, no_ssim);
+                        if (r.rp < m.rp) { m = r; mi = i; }
+                    }
+                    const bool keep = !automask || m.rp < sAuto[c][k1];
+                    const float val = keep ? m.rp : 0.0f;
+                    // torch.max over channels: first maximal channel wins; a masked channel carries no gradient
+                    if (bsel == -1 || val > best) {
+                        best = val;
+                        bsel = keep ? (c + 4 * mi) : -2;
+                        bca = m.ca; bcb = m.cb; bcc = m.cc; bcl = m.cl;
+                    }
+                }
+                const bool interior = lx >= 1 && lx <= PM_TW && ly >= 1 && ly <= PM_TH;
+                if (interior) lsum += best;
+            }
+            sSel[k1] = (signed char)(bsel >= 0 ? bsel : -1);
+            sCa[k1] = bca; sCb[k1] = bcb; sCc[k1] = bcc; sCl[k1] = bcl;
+        }
+        __syncthreads();
+        // ---- (3) gradient of the tile pixels ------------------------------------------------------
+        if (GRAD) {
+            float gD = 0.0f, D = 0.0f;
+            if (qin) {
+                D = pm_depth(a, pc, s, full, qx, qy, W);
+                const float xf = (float)qx, yf = (float)qy;
+                const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
+                const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
+                const float rz = fmaf(pc.kinv[7], yf, pc.kinv[6] * xf) + pc.kinv[8];
+#pragma unroll
+                for (int i = 0; i < PLB_MAX_SRC; ++i) {
+                    if (i < n_src) {
+                        // d loss / d warped_i(q, c): the selected terms of the 3x3 neighbours p that use source i
+                        float e[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+                        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const int pk1 = qk1 + dy * PM_W1 + dx;
+                                const int sel = sSel[pk1];
+                                if (sel >= 0 && (sel >> 2) == i) {
+                                    const int c = sel & 3;
+                                    const int pxg = qx + dx, pyg = qy + dy;
+                                    // multiplicity of q in p's reflection-padded window
+                                    const float mx = 1.0f + ((pxg == 0 && dx == -1) ? 1.0f : 0.0f) + ((pxg == W - 1 && dx == 1) ? 1.0f : 0.0f);
+                                    const float my = 1.0f + ((pyg == 0 && dy == -1) ? 1.0f : 0.0f) + ((pyg == H - 1 && dy == 1) ? 1.0f : 0.0f);
+                                    float g = mx * my * fmaf(sCb[pk1], sX[i][c][qk2], fmaf(sCc[pk1], sT[c][qk2], sCa[pk1]));
+                                    if (dx == 0 && dy == 0) g += sCl[pk1];
+                                    e[c] += g;
+                                }
+                            }
+                        if (e[0] != 0.0f || e[1] != 0.0f || e[2] != 0.0f) {
+                            MinProj q;
+                            pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
+                            float v[3][4];
+                            pm_taps(pc.src[i], plane, W, q, v);
+                            float Gx = 0.0f, Gy = 0.0f;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float dA = v[c][1] - v[c][0], dB = v[c][3] - v[c][2];
+                                const float top = fmaf(q.fx, dA, v[c][0]), bot = fmaf(q.fx, dB, v[c][2]);
+                                Gx = fmaf(e[c], fmaf(q.fy, dB - dA, dA), Gx);
+                                Gy = fmaf(e[c], bot - top, Gy);
+                            }
+                            const bool use = q.mask != 0u;
+                            const float gi = use ? w_e * q.inv : 0.0f;
+                            const float gcx = Gx * gi, gcy = Gy * gi;
+                            const float gcz = use ? -(gcx * q.px + gcy * q.py) : 0.0f;
+                            gD += fmaf(gcx, q.Ax, fmaf(gcy, q.Ay, gcz * q.Az));
+                            const float hx = gcx * D, hy = gcy * D, hz = gcz * D;
+                            acc[i][0] = fmaf(hx, rx, acc[i][0]); acc[i][1] = fmaf(hx, ry, acc[i][1]); acc[i][2] = fmaf(hx, rz, acc[i][2]); acc[i][3] += gcx;
+                            acc[i][4] = fmaf(hy, rx, acc[i][4]); acc[i][5] = fmaf(hy, ry, acc[i][5]); acc[i][6] = fmaf(hy, rz, acc[i][6]); acc[i][7] += gcy;
+                            acc[i][8] = fmaf(hz, rx, acc[i][8]); acc[i][9] = fmaf(hz, ry, acc[i][9]); acc[i][10] = fmaf(hz, rz, acc[i][10]); acc[i][11] += gcz;
+                        }
+                    }
+                }
+                float* g = pc.g_disp[s];
+                if (g != nullptr) {
+                    const float chain = (full && !a.input_is_depth) ? -a.disp_a * D * D : 1.0f;
+                    g[qy * W + qx] = gD * chain;
+                }
+            }
+        }
+        __syncthreads();   // sX / selection arrays are rewritten by the next scale
+    }
+
+    // ---- block record: warp butterflies, fixed-order sum over warps --------------------------------
+#pragma unroll
+    for (int i = 0; i < PLB_MAX_SRC; ++i) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v[k] = acc[i][k];
+        v[12] = (i == 0) ? lsum : 0.0f;
+        v[13] = v[14] = v[15] = 0.0f;
+        int which;
+        const float r = warp_reduce16(v, lane, which);
+        if ((lane & 1) == 0) {
+            if (which < 12) s_rec[warp][i * 12 + which] = r;
+            else if (which == 12 && i == 0) s_rec[warp][PLB_MAX_SRC * 12] = r;
+        }
+    }
+    __syncthreads();
+    float* my_rec = records + ((size_t)b * p.tiles + tile) * PH_REC_STRIDE;
+    if (tid < PH_NREC) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < PM_THREADS / 32; ++w) v += s_rec[w][tid];
+        __stcg(my_rec + tid, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag = (atomicAdd(&tickets[b], 1) == p.tiles - 1);
+    __syncthreads();
+    if (!s_flag) return;
+
+    // ---- last tile of image b: sum its records (4 groups x 64 lanes, fixed order), pose chain -------
+    __threadfence();
+    {
+        const int c = tid & 63, grp = tid >> 6;
+        float v = 0.0f;
+        if (c < PH_NREC) {
+#pragma unroll 4
+            for (int t = grp; t < p.tiles; t += 4) v += __ldcg(records + ((size_t)b * p.tiles + t) * PH_REC_STRIDE + c);
+        }
+        s_part4[grp][c] = v;
+        __syncthreads();
+        if (tid < PH_NREC) s_red[tid] = ((s_part4[0][tid] + s_part4[1][tid]) + s_part4[2][tid]) + s_part4[3][tid];
+    }
+    __syncthreads();
+    if (tid == 0) { ws_loss[b] = s_red[PLB_MAX_SRC * 12]; tickets[b] = 0; }
+    if (GRAD && tid < n_src) {
+        float dP[12], dM[12], g6[6];
+        for (int k = 0; k < 12; ++k) dP[k] = s_red[tid * 12 + k];
+        const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
+        kT_times_dP(Kb, a.k_is_f64, dP, dM);
+        pose_to_M_vjp(a.poses + ((size_t)b * a.n_pose + job.pose_index[tid]) * 6, a.rotation_mode, job.pose_inv[tid], dM, g6);
+        float* o = ws_pose + ((size_t)b * PLB_MAX_SRC + tid) * 6;
+        for (int k = 0; k < 6; ++k) o[k] = g6[k];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag = (atomicAdd(&tickets[a.B], 1) == a.B - 1);
+    __syncthreads();
+    if (!s_flag) return;
+
+    // ---- last image of the launch -----------------------------------------------------------------
+    __threadfence();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int q = 0; q < a.B; ++q) tot += (double)__ldcg(ws_loss + q);
+        if (a.loss != nullptr) *a.loss = (float)(tot * (double)p.w_e / (double)n_scales);
+        tickets[a.B] = 0;
+    }
+    if (GRAD && a.g_poses != nullptr) {
+        for (int k = tid; k < a.B * a.n_pose * 6; k += PM_THREADS) {
+            const int bb = k / (a.n_pose * 6), col = (k / 6) % a.n_pose, c = k % 6;
+            float v = 0.0f;
+            for (int i = 0; i < job.n_src; ++i)
+                if (job.pose_index[i] == col) v += __ldcg(ws_pose + ((size_t)bb * PLB_MAX_SRC + i) * 6 + c);
+            a.g_poses[k] = v;
+        }
+    }
+}
+
+int photo_min_launch(const plb_photo_args* a, cudaStream_t st) {
+    int rc = validate_photo(a);
+    if (rc != PLB_OK) return rc;
+    if (a->n_jobs != 1) return PLB_EINVAL;            // the dormant composition has one direction
+    const plb_photo_job& job = a->jobs[0];
+    if (job.g_tgt != nullptr) return PLB_EINVAL;      // image gradients: L1 mode only
+    for (int i = 0; i < job.n_src; ++i)
+        if (job.g_src[i] != nullptr) return PLB_EINVAL;
+    PminLaunch p;
+    p.a = *a;
+    p.L = photo_layout(*a);
+    p.tiles_x = (a->W + PM_TW - 1) / PM_TW;
+    p.tiles = photo_min_tiles(*a);
+    p.w_e = job.term_weight / ((float)a->B * (float)a->H * (float)a->W);
+    p.C1 = 1e-4f; p.C2 = 9e-4f;
+    dim3 grid(p.tiles, a->B);
+    if (a->want_grad) photo_min_kernel<true><<<grid, PM_THREADS, 0, st>>>(p);
+    else photo_min_kernel<false><<<grid, PM_THREADS, 0, st>>>(p);
+    ++g_launches;
+    PLB_CHECK_LAUNCH();
+    if (photo_has_lowres_grad(*a)) {
+        PhotoLaunch pl;
+        pl.a = *a;
+        pl.L = p.L;
+        rc = photo_upsample_T_launch(pl, st);
+        if (rc != PLB_OK) return rc;
+    }
+    return PLB_OK;
+}
+
+}  // namespace plb

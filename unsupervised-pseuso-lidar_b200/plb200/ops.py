@@ -130,7 +130,7 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
                 job.disp[s] = d.data_ptr()
                 job.dh[s], job.dw[s] = d.shape[-2], d.shape[-1]
                 job.g_disp[s] = _ptr(g_pyr[j][s]) if (want_grad and g_pyr is not None) else 0
-            job.term_weight = 1.0 / (entries * job.n_src)
+            job.term_weight = 1.0 if cfg.mode == _lib.PHOTO_MIN_REPROJ else 1.0 / (entries * job.n_src)
             job.mode, job.flags = cfg.mode, cfg.flags
         nbytes = lib.plb_photo_workspace_bytes(a)
         ws = _workspace("photo", nbytes, dev)
@@ -175,6 +175,8 @@ class FusedLossFn(torch.autograd.Function):
         pyr = [[_f32c(d) for d in p] for p in pyr]
         need = ctx.needs_input_grad
         img_grad = need[1] or any(need[4:4 + cfg.n_src])
+        if img_grad and cfg.mode == _lib.PHOTO_MIN_REPROJ:
+            raise NotImplementedError("image gradients are implemented for the live L1 loss only")
         any_grad = img_grad or need[2] or any(need[4 + cfg.n_src:])
         fused = any_grad and cfg.fused_backward and not img_grad
         both = cfg.do_photo and cfg.do_smooth
@@ -349,6 +351,65 @@ def project(X, K, Tcw):
     check(lib.plb_project(X.data_ptr(), K.data_ptr(), int(K.dtype == torch.float64), Tcw.data_ptr(), B, H, W,
                           out.data_ptr(), _stream()), "plb_project")
     return out
+
+
+# ---------------------------------------------------------------------------
+# stand-alone SSIM / photometric maps (the reference's dormant functions)
+# ---------------------------------------------------------------------------
+class PhotometricMapFn(torch.autograd.Function):
+    """out = w_ssim * clamp((1 - SSIM(x, y)) / 2, 0, 1) + w_l1 * |y - x|, optional clip at mean + clip * std."""
+
+    @staticmethod
+    def _args(x, y, C1, C2, w_ssim, w_l1, clip, thr):
+        a = _lib.PhotomapArgs()
+        a.B, a.C, a.H, a.W = x.shape
+        a.x, a.y = x.data_ptr(), y.data_ptr()
+        a.C1, a.C2, a.w_ssim, a.w_l1 = C1, C2, w_ssim, w_l1
+        a.clip = -1.0 if clip is None else float(clip)
+        a.threshold = _ptr(thr)
+        return a
+
+    @staticmethod
+    def forward(ctx, x, y, C1, C2, w_ssim, w_l1, clip):
+        _need_cuda(x, y)
+        x, y = _f32c(x), _f32c(y)
+        if x.dim() != 4 or x.shape != y.shape:
+            raise ValueError("expected two [B,C,H,W] images of the same shape")
+        out = torch.empty_like(x)
+        thr = torch.empty((), dtype=torch.float32, device=x.device) if clip is not None else None
+        a = PhotometricMapFn._args(x, y, C1, C2, w_ssim, w_l1, clip, thr)
+        a.out = out.data_ptr()
+        if clip is not None:
+            ws = _workspace("photomap", lib.plb_photometric_map_workspace_bytes(a), x.device)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        check(lib.plb_photometric_map(a, _stream()), "plb_photometric_map")
+        ctx.save_for_backward(x, y)
+        ctx.meta = (C1, C2, w_ssim, w_l1, clip, thr)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, y = ctx.saved_tensors
+        C1, C2, w_ssim, w_l1, clip, thr = ctx.meta
+        g_out = _f32c(g_out)
+        need = ctx.needs_input_grad
+        g_x = torch.empty_like(x) if need[0] else None
+        g_y = torch.empty_like(y) if need[1] else None
+        a = PhotometricMapFn._args(x, y, C1, C2, w_ssim, w_l1, clip, thr)
+        a.g_out, a.g_x, a.g_y = g_out.data_ptr(), _ptr(g_x), _ptr(g_y)
+        check(lib.plb_photometric_map_backward(a, _stream()), "plb_photometric_map_backward")
+        return g_x, g_y, None, None, None, None, None
+
+
+def ssim_map(x, y, C1=1e-4, C2=9e-4):
+    """`SSIM.standard_loss` (losses.py:12-54)."""
+    return PhotometricMapFn.apply(x, y, float(C1), float(C2), 1.0, 0.0, None)
+
+
+def photometric_map(pred, target, no_ssim=False, clip=0.5, C1=1e-4, C2=9e-4):
+    """`Losses.compute_photometric_loss` (losses.py:66-84); clip=None skips the clamp."""
+    w = (0.0, 1.0) if no_ssim else (0.85, 0.15)
+    return PhotometricMapFn.apply(pred, target, float(C1), float(C2), w[0], w[1], clip)
 
 
 # ---------------------------------------------------------------------------
