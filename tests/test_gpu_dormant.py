@@ -126,7 +126,7 @@ def test_min_reprojection_vs_oracle(B, H, W, S, automask, no_ssim):
         rl.backward()
         return rl, rp, rd
     rl, rp, rd = oracle(torch.float32)
-    _, rp64, _ = oracle(torch.float64)
+    _, rp64, rd64 = oracle(torch.float64)
     loss, disp, p = _run_min(tgt, refs, inp["disparity"][0], poses, K, automask, no_ssim)
     assert abs(float(loss) - float(rl)) <= 2 * LOSS_TOL * abs(float(rl))
     # pose gradients sum over every pixel, so each flipped selection moves them: the bar is a small
@@ -134,10 +134,15 @@ def test_min_reprojection_vs_oracle(B, H, W, S, automask, no_ssim):
     e32 = rel_err(rp.grad, rp64.grad)
     assert rel_err(p.grad.cpu(), rp64.grad) < max(GRAD_TOL, 3 * e32), e32
     assert rel_err(p.grad.cpu(), rp.grad) < max(GRAD_TOL, 4 * e32), e32
-    for s, (a, b) in enumerate(zip(disp, rd)):
-        scale = float(b.grad.abs().max())
-        bad = int(((a.grad.cpu() - b.grad).abs() > GRAD_TOL * scale).sum())
-        assert bad <= max(8, int(2e-3 * b.grad.numel())), (s, bad, b.grad.numel())
+    # per-pixel gradient maps: elements off by more than 1e-4 of the map's scale are counted against
+    # the fp64 evaluation; the budget is a multiple of the fp32 reference's own count (a flipped
+    # min / mask / max selection or bilinear cell moves the ~16 low-resolution elements it feeds)
+    for s, (a, b32, b64) in enumerate(zip(disp, rd, rd64)):
+        x = b64.grad
+        scale = float(x.abs().max())
+        bad = int(((a.grad.cpu().double() - x).abs() > GRAD_TOL * scale).sum())
+        bad_ref = int(((b32.grad.double() - x).abs() > GRAD_TOL * scale).sum())
+        assert bad <= max(16, int(5e-4 * x.numel())) + 4 * bad_ref, (s, bad, bad_ref, x.numel())
 
 
 def test_min_reprojection_repeatable_and_forward_only():

@@ -32,6 +32,30 @@ def _run_ours(tgt, refs, disparity, poses, K, fused_backward=True, image_grads=F
     return loss, disp, p, tgt, refs
 
 
+def _golden_fp64(g):
+    """fp64 evaluation of the reference's formulas on a golden case (CPU, small): how far the
+    reference's own fp32 result (the golden vector) is from exact arithmetic."""
+    from oracle import restated as O
+    tgt, refs, disparity, poses, K = golden_inputs(g)
+    rd = [[d.double().requires_grad_(True) for d in fr] for fr in disparity]
+    rp = poses.double().requires_grad_(True)
+    rt = tgt.double().requires_grad_(True)
+    rr = [r.double().requires_grad_(True) for r in refs]
+    rl = O.losses_forward(rt, rr, rd, rp, K)
+    sum(rl).backward()
+    return rp.grad, [[d.grad for d in fr] for fr in rd], rt.grad, [r.grad for r in rr]
+
+
+def _check_grad(ours, golden, exact, what):
+    """1e-4 relative against the golden vector - widened only where the golden vector (the
+    reference's own fp32 arithmetic) is itself further than that from the fp64 evaluation of the
+    same formulas: a bilinear sample that fp32 rounding puts on the other side of a pixel boundary
+    (measured: e32 = 1.3e-4 on the pose gradients of live_b4_s4_32x64, <= 1e-5 elsewhere)."""
+    e32 = rel_err(golden, exact)
+    assert rel_err(ours, exact) < max(GRAD_TOL, 2 * e32), (what, e32)
+    assert rel_err(ours, golden) < max(GRAD_TOL, 2 * e32), (what, e32)
+
+
 @pytest.mark.parametrize("name", LIVE)
 @pytest.mark.parametrize("fused", [True, False])
 def test_golden_loss_and_grads(name, fused):
@@ -40,10 +64,11 @@ def test_golden_loss_and_grads(name, fused):
     loss, disp, p, _, _ = _run_ours(tgt, refs, disparity, poses, K, fused_backward=fused)
     assert abs(float(loss[0]) - float(g["loss_mam"])) <= LOSS_TOL * abs(float(g["loss_mam"]))
     assert abs(float(loss[1]) - float(g["loss_smooth"])) <= LOSS_TOL * abs(float(g["loss_smooth"]))
-    assert rel_err(p.grad.cpu(), g["g_poses"]) < GRAD_TOL
+    xp, xd, _, _ = _golden_fp64(g)
+    _check_grad(p.grad.cpu(), g["g_poses"], xp, "poses")
     for f, fr in enumerate(disp):
         for s, t in enumerate(fr):
-            assert rel_err(t.grad.cpu(), g["g_disp_f%d_s%d" % (f, s)]) < GRAD_TOL, (f, s)
+            _check_grad(t.grad.cpu(), g["g_disp_f%d_s%d" % (f, s)], xd[f][s], ("disp", f, s))
 
 
 @pytest.mark.parametrize("name", ["live_b4_s1_32x48", "live_b4_s4_32x64"])
@@ -51,10 +76,11 @@ def test_golden_image_grads(name):
     g = load_golden(name)
     tgt, refs, disparity, poses, K = golden_inputs(g)
     loss, disp, p, t, r = _run_ours(tgt, refs, disparity, poses, K, image_grads=True)
-    assert rel_err(t.grad.cpu(), g["g_tgt"]) < GRAD_TOL
+    xp, _, xt, xr = _golden_fp64(g)
+    _check_grad(t.grad.cpu(), g["g_tgt"], xt, "tgt")
     for i in range(2):
-        assert rel_err(r[i].grad.cpu(), g["g_ref%d" % i]) < GRAD_TOL
-    assert rel_err(p.grad.cpu(), g["g_poses"]) < GRAD_TOL
+        _check_grad(r[i].grad.cpu(), g["g_ref%d" % i], xr[i], ("ref", i))
+    _check_grad(p.grad.cpu(), g["g_poses"], xp, "poses")
 
 
 def _oracle(inp, dtype=torch.float32):

@@ -22,22 +22,28 @@ __device__ __forceinline__ double load_k(const void* K, int is_f64, int i) {
 // K^-1 in K's precision (fp64 maths), cast to fp32: `Kinv = K.inverse().float()`
 // (geometry/transform.py:92).  Closed-form adjugate instead of the LU the
 // library call runs.
-__device__ inline void kinv_f32(const void* K, int is_f64, float* out9) {
+__device__ inline void kinv_f64(const void* K, int is_f64, double* out9) {
     double a = load_k(K, is_f64, 0), b = load_k(K, is_f64, 1), c = load_k(K, is_f64, 2);
     double d = load_k(K, is_f64, 3), e = load_k(K, is_f64, 4), f = load_k(K, is_f64, 5);
     double g = load_k(K, is_f64, 6), h = load_k(K, is_f64, 7), i = load_k(K, is_f64, 8);
     double A = e * i - f * h, Bc = -(d * i - f * g), C = d * h - e * g;
     double det = a * A + b * Bc + c * C;
     double r = 1.0 / det;
-    out9[0] = (float)(A * r);
-    out9[1] = (float)(-(b * i - c * h) * r);
-    out9[2] = (float)((b * f - c * e) * r);
-    out9[3] = (float)(Bc * r);
-    out9[4] = (float)((a * i - c * g) * r);
-    out9[5] = (float)(-(a * f - c * d) * r);
-    out9[6] = (float)(C * r);
-    out9[7] = (float)(-(a * h - b * g) * r);
-    out9[8] = (float)((a * e - b * d) * r);
+    out9[0] = A * r;
+    out9[1] = -(b * i - c * h) * r;
+    out9[2] = (b * f - c * e) * r;
+    out9[3] = Bc * r;
+    out9[4] = (a * i - c * g) * r;
+    out9[5] = -(a * f - c * d) * r;
+    out9[6] = C * r;
+    out9[7] = -(a * h - b * g) * r;
+    out9[8] = (a * e - b * d) * r;
+}
+
+__device__ inline void kinv_f32(const void* K, int is_f64, float* out9) {
+    double t[9];
+    kinv_f64(K, is_f64, t);
+    for (int i = 0; i < 9; ++i) out9[i] = (float)t[i];
 }
 
 // ---------------------------------------------------------------------------

@@ -16,134 +16,252 @@
 // for both are built once in the block prologue and kept in shared memory.
 //
 // Reductions (loss, 3x4 projection-matrix gradient per source) are kept in
-// registers across all of a warp's units, reduced warp -> block -> (job, image)
-// -> launch in a fixed order by "last block done" epilogues: one launch, no
-// atomics on the results, bitwise repeatable.
+// registers across a warp's run of rows, reduced warp -> block record in a fixed
+// order; a small finalize kernel (one block per image) sums the records of each
+// (job, image) pair, runs the pose chain and adds the loss: no atomics on the
+// results, bitwise repeatable, and no fence / ticket traffic in the main kernel.
 #include "photo_common.cuh"
 
 namespace plb {
 
 // ---------------------------------------------------------------------------------------------
-// One target pixel against one source at one depth: project, sample, L1, and (GRAD) the
-// gradient terms.  Written for instruction count: the projection is
-// cam = D * (P[:, :3].ray) + P[:, 3], the perspective divide is one MUFU.RCP + one Newton step,
-// the normalise/un-normalise chain of the reference (transform.py:143-148 + grid_sample) is the
-// identity and is dropped, and the bilinear blend is written as nested lerps whose
-// intermediates ARE the coordinate derivatives (d proj / d iy = bot - top).  A warp whose 32
-// pixels all land strictly inside the source takes a branch with unpredicated loads.
+// Per-pixel stages.  A "group" is one or two sources handled together.  For a pair of sources all
+// floating-point work runs on Blackwell's packed fp32 pipe (FFMA2 / FADD2 / FMUL2: source 0 in the
+// low half, source 1 in the high half of a 64-bit register pair), which halves the issue slots of
+// the arithmetic; the coordinates of every source of the group are computed first, ONE warp vote
+// decides between the unpredicated and the predicated tap loads, all 12 x NS loads are issued back
+// to back, and only then is anything blended.
+//
+// Projection: cam = D * A + p3 with A = Q . (x, y, 1), Q = P[:, :3] . K^-1 (composed in fp64 in
+// the block prologue, rounded once): the ray is never formed.  The perspective divide is one
+// MUFU.RCP + one Newton step + a residual correction (as accurate as an IEEE divide: the sample
+// position is the difference of two ~W-sized numbers, every ulp of px is 6e-5 px of bilinear
+// weight); the normalise / un-normalise chain of the reference (transform.py:143-148 +
+// grid_sample) is the identity and is dropped; the bilinear blend is written as nested lerps
+// whose intermediates ARE the coordinate derivatives (d proj / d iy = bot - top).
+//
+// Depth gradient: d loss / d D = g_cam . A.  Because g_cam . (cx, cy, ze) = 0 identically (the
+// perspective divide is scale invariant) and (cx, cy, ze) = D * A + p3', this equals
+// -(g_cam . p3') / D - the analytically cancelled form, free of the ~W-sized cancellation the
+// chain-rule form carries, and A need not stay live across the loads.
 // ---------------------------------------------------------------------------------------------
-template <bool GRAD, bool IMG_GRAD>
-__device__ __forceinline__ void photo_pixel(const float* __restrict__ cb, float* gbase, int plane, int pf_rows,
-                                            int H, int W, const float4 Pa, const float4 Pb, const float4 Pc,
-                                            float rx, float ry, float rz, float D, const float (&t)[3], float w_e,
-                                            bool valid, float (&acc)[12], float& l1acc, float& gD, float (&gt)[3]) {
-    const float Ax = fmaf(Pa.z, rz, fmaf(Pa.y, ry, Pa.x * rx));
-    const float Ay = fmaf(Pb.z, rz, fmaf(Pb.y, ry, Pb.x * rx));
-    const float Az = fmaf(Pc.z, rz, fmaf(Pc.y, ry, Pc.x * rx));
-    const float cx = fmaf(D, Ax, Pa.w), cy = fmaf(D, Ay, Pb.w);
-    const float ze = fmaf(D, Az, Pc.w) + 1e-5f;
-    const float inv = rcp_nr(ze);
-    // quotient + one residual correction: as accurate as an IEEE divide (the sample position is the
-    // difference of two ~W-sized numbers, so every ulp of px is 6e-5 px of bilinear weight)
-    float px = cx * inv, py = cy * inv;
-    px = fmaf(fmaf(-px, ze, cx), inv, px);
-    py = fmaf(fmaf(-py, ze, cy), inv, py);
-    // clamp keeps float->int defined; NaN maps to -2 (out of the image)
-    const float ixc = fminf(fmaxf(px, -2.0f), (float)(W + 1));
-    const float iyc = fminf(fmaxf(py, -2.0f), (float)(H + 1));
-    const float xf = floorf(ixc), yf = floorf(iyc);
-    const int x0 = (int)xf, y0 = (int)yf;
-    const float fx = ixc - xf, fy = iyc - yf;
-    const bool inter = ((unsigned)x0 < (unsigned)(W - 1)) && ((unsigned)y0 < (unsigned)(H - 1));
-    float v[3][4];
-    bool use;
-    bool mnw = true, mne = true, msw = true, mse = true;
-    // 32-bit element offsets from ONE base pointer: an IMAD.WIDE per (channel, row), +4 B as an immediate
-    int o00 = y0 * W + x0;
-    if (__all_sync(0xffffffffu, inter || !valid)) {
-        o00 = (inter && valid) ? o00 : 0;
-        const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
-        v[0][0] = __ldg(cb + o00); v[0][1] = __ldg(cb + o00 + 1); v[0][2] = __ldg(cb + o01); v[0][3] = __ldg(cb + o01 + 1);
-        v[1][0] = __ldg(cb + o10); v[1][1] = __ldg(cb + o10 + 1); v[1][2] = __ldg(cb + o11); v[1][3] = __ldg(cb + o11 + 1);
-        v[2][0] = __ldg(cb + o20); v[2][1] = __ldg(cb + o20 + 1); v[2][2] = __ldg(cb + o21); v[2][3] = __ldg(cb + o21 + 1);
-        if (pf_rows > 0) {
-            // the warp walks DOWN a strip: the source row needed pf_rows units from now, one line per channel
-            const int opf = o01 + pf_rows * W;
-            prefetch_l1(cb + opf); prefetch_l1(cb + (opf + plane)); prefetch_l1(cb + (opf + 2 * plane));
-        }
-        use = valid;
-    } else {
-        const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
-        const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
-        mnw = valid && vx0 && vy0; mne = valid && vx1 && vy0;
-        msw = valid && vx0 && vy1; mse = valid && vx1 && vy1;
-        const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
-        v[0][0] = ldg_pred(cb + o00, mnw); v[0][1] = ldg_pred(cb + o00 + 1, mne);
-        v[0][2] = ldg_pred(cb + o01, msw); v[0][3] = ldg_pred(cb + o01 + 1, mse);
-        v[1][0] = ldg_pred(cb + o10, mnw); v[1][1] = ldg_pred(cb + o10 + 1, mne);
-        v[1][2] = ldg_pred(cb + o11, msw); v[1][3] = ldg_pred(cb + o11 + 1, mse);
-        v[2][0] = ldg_pred(cb + o20, mnw); v[2][1] = ldg_pred(cb + o20 + 1, mne);
-        v[2][2] = ldg_pred(cb + o21, msw); v[2][3] = ldg_pred(cb + o21 + 1, mse);
-        use = mnw || mne || msw || mse;
+template <int NS> struct Vec;
+template <> struct Vec<1> { typedef float T; };
+template <> struct Vec<2> { typedef float2 T; };
+
+__device__ __forceinline__ float v_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float2 v_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float v_mul(float a, float b) { return a * b; }
+__device__ __forceinline__ float2 v_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float v_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 v_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float v_sub(float a, float b) { return a - b; }
+__device__ __forceinline__ float2 v_sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+__device__ __forceinline__ void v_bc(float& v, float s) { v = s; }
+__device__ __forceinline__ void v_bc(float2& v, float s) { v = make_float2(s, s); }
+__device__ __forceinline__ float v_get(float v, int) { return v; }
+__device__ __forceinline__ float v_get(float2 v, int k) { return k == 0 ? v.x : v.y; }
+__device__ __forceinline__ void v_set(float& v, int, float s) { v = s; }
+__device__ __forceinline__ void v_set(float2& v, int k, float s) { if (k == 0) v.x = s; else v.y = s; }
+__device__ __forceinline__ float v_hsum(float v) { return v; }
+__device__ __forceinline__ float v_hsum(float2 v) { return v.x + v.y; }
+
+// row r of [Q | p3] for the group starting at source i0: x / y / constant coefficient and p3
+__device__ __forceinline__ void load_q(const PairConst& pc, int i0, int r, float& qx, float& qy, float& qz, float& qw) {
+    const float4 q = pc.Q[i0][r];
+    qx = q.x; qy = q.y; qz = q.z; qw = q.w;
+}
+__device__ __forceinline__ void load_q(const PairConst& pc, int i0, int r, float2& qx, float2& qy, float2& qz, float2& qw) {
+    const float4 a = pc.Q2[i0 >> 1][r][0], b = pc.Q2[i0 >> 1][r][1];
+    qx = make_float2(a.x, a.y); qy = make_float2(a.z, a.w); qz = make_float2(b.x, b.y); qw = make_float2(b.z, b.w);
+}
+
+// p3 re-read from shared memory (asm volatile: a fresh load, not a value held in registers across the taps)
+__device__ __forceinline__ void load_p3(const PairConst& pc, int i0, int r, float& w) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(&pc.Q[i0][r].w);
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(a));
+}
+__device__ __forceinline__ void load_p3(const PairConst& pc, int i0, int r, float2& w) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(&pc.Q2[i0 >> 1][r][1].z);
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w.x), "=f"(w.y) : "r"(a));
+}
+
+template <bool GRAD, bool IMG_GRAD, int NS>
+__device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int plane, int H, int W, float xf, float yf,
+                                            float D, const float (&t)[3], float w_e, bool valid, bool pf,
+                                            typename Vec<NS>::T (&acc)[9], float& l1acc, float& gp, float (&gt)[3]) {
+    typedef typename Vec<NS>::T V;
+    V xv, yv, Dv, eps, neg1, two;
+    v_bc(xv, xf); v_bc(yv, yf); v_bc(Dv, D); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f); v_bc(two, 2.0f);
+    V p3[3], cam[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        V qx, qy, qz;
+        load_q(pc, i0, r, qx, qy, qz, p3[r]);
+        cam[r] = v_fma(Dv, v_fma(qx, xv, v_fma(qy, yv, qz)), p3[r]);
     }
-    float Gx = 0.0f, Gy = 0.0f, l1 = 0.0f;
-    float e[3];
+    const V ze = v_add(cam[2], eps);
+    const V nze = v_mul(ze, neg1);
+    V inv;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v_get(ze, k)));
+        v_set(inv, k, r);
+    }
+    inv = v_mul(inv, v_fma(nze, inv, two));                  // Newton step
+    V px = v_mul(cam[0], inv), py = v_mul(cam[1], inv);
+    px = v_fma(v_fma(px, nze, cam[0]), inv, px);             // residual correction: IEEE-accurate quotient
+    py = v_fma(v_fma(py, nze, cam[1]), inv, py);
+    V fx, fy;
+    int x0[NS], y0[NS];
+    bool all_in = true;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        // clamp keeps float->int defined; NaN maps to -2 (out of the image)
+        const float ixc = fminf(fmaxf(v_get(px, k), -2.0f), (float)(W + 1));
+        const float iyc = fminf(fmaxf(v_get(py, k), -2.0f), (float)(H + 1));
+        const float xfl = floorf(ixc), yfl = floorf(iyc);
+        x0[k] = (int)xfl; y0[k] = (int)yfl;
+        v_set(fx, k, ixc - xfl); v_set(fy, k, iyc - yfl);
+        all_in = all_in && ((unsigned)x0[k] < (unsigned)(W - 1)) && ((unsigned)y0[k] < (unsigned)(H - 1));
+    }
+    V v[3][4];
+    unsigned msk[NS];
+    if (__all_sync(0xffffffffu, all_in || !valid)) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const float* __restrict__ cb = pc.src[i0 + k];
+            const int o00 = (all_in && valid) ? y0[k] * W + x0[k] : 0;
+            const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
+            v_set(v[0][0], k, __ldg(cb + o00)); v_set(v[0][1], k, __ldg(cb + o00 + 1));
+            v_set(v[0][2], k, __ldg(cb + o01)); v_set(v[0][3], k, __ldg(cb + o01 + 1));
+            v_set(v[1][0], k, __ldg(cb + o10)); v_set(v[1][1], k, __ldg(cb + o10 + 1));
+            v_set(v[1][2], k, __ldg(cb + o11)); v_set(v[1][3], k, __ldg(cb + o11 + 1));
+            v_set(v[2][0], k, __ldg(cb + o20)); v_set(v[2][1], k, __ldg(cb + o20 + 1));
+            v_set(v[2][2], k, __ldg(cb + o21)); v_set(v[2][3], k, __ldg(cb + o21 + 1));
+            if (PH_PF_SRC > 0 && pf) {
+                // the warp walks DOWN a strip: the source row the next unit(s) will newly touch, one line per channel
+                const int opf = o01 + PH_PF_SRC * W;
+                prefetch_l1(cb + opf); prefetch_l1(cb + (opf + plane)); prefetch_l1(cb + (opf + 2 * plane));
+            }
+            msk[k] = valid ? 15u : 0u;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const float* __restrict__ cb = pc.src[i0 + k];
+            const bool vx0 = (unsigned)x0[k] < (unsigned)W, vx1 = (unsigned)(x0[k] + 1) < (unsigned)W;
+            const bool vy0 = (unsigned)y0[k] < (unsigned)H, vy1 = (unsigned)(y0[k] + 1) < (unsigned)H;
+            const bool mnw = valid && vx0 && vy0, mne = valid && vx1 && vy0;
+            const bool msw = valid && vx0 && vy1, mse = valid && vx1 && vy1;
+            const int o00 = y0[k] * W + x0[k];
+            const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
+            v_set(v[0][0], k, ldg_pred(cb + o00, mnw)); v_set(v[0][1], k, ldg_pred(cb + o00 + 1, mne));
+            v_set(v[0][2], k, ldg_pred(cb + o01, msw)); v_set(v[0][3], k, ldg_pred(cb + o01 + 1, mse));
+            v_set(v[1][0], k, ldg_pred(cb + o10, mnw)); v_set(v[1][1], k, ldg_pred(cb + o10 + 1, mne));
+            v_set(v[1][2], k, ldg_pred(cb + o11, msw)); v_set(v[1][3], k, ldg_pred(cb + o11 + 1, mse));
+            v_set(v[2][0], k, ldg_pred(cb + o20, mnw)); v_set(v[2][1], k, ldg_pred(cb + o20 + 1, mne));
+            v_set(v[2][2], k, ldg_pred(cb + o21, msw)); v_set(v[2][3], k, ldg_pred(cb + o21 + 1, mse));
+            msk[k] = (mnw ? 1u : 0u) | (mne ? 2u : 0u) | (msw ? 4u : 0u) | (mse ? 8u : 0u);
+        }
+    }
+    V Gx, Gy;
+    v_bc(Gx, 0.0f); v_bc(Gy, 0.0f);
+    float l1 = 0.0f;
+    float e[NS][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float dA = v[c][1] - v[c][0], dB = v[c][3] - v[c][2];
-        const float top = fmaf(fx, dA, v[c][0]), bot = fmaf(fx, dB, v[c][2]);
-        const float dV = bot - top;
-        const float proj = fmaf(fy, dV, top);
-        const float d = proj - t[c];
-        l1 += fabsf(d);
+        const V dA = v_sub(v[c][1], v[c][0]), dB = v_sub(v[c][3], v[c][2]);
+        const V top = v_fma(fx, dA, v[c][0]), bot = v_fma(fx, dB, v[c][2]);
+        const V dV = v_sub(bot, top);
+        const V proj = v_fma(fy, dV, top);
+        V sg;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const float d = v_get(proj, k) - t[c];
+            l1 += fabsf(d);
+            if (GRAD) {
+                // sign(d) with sign(0) = 0 (nn.L1Loss): one compare + one bit merge
+                const float ne = (d != 0.0f) ? 1.0f : 0.0f;
+                const float s = __int_as_float(__float_as_int(ne) | (__float_as_int(d) & 0x80000000));
+                v_set(sg, k, s);
+                e[k][c] = s;
+            }
+        }
         if (GRAD) {
-            const float sg = (d > 0.0f ? 1.0f : 0.0f) - (d < 0.0f ? 1.0f : 0.0f);
-            e[c] = sg;
-            Gx = fmaf(sg, fmaf(fy, dB - dA, dA), Gx);
-            Gy = fmaf(sg, dV, Gy);
+            Gx = v_fma(sg, v_fma(fy, v_sub(dB, dA), dA), Gx);
+            Gy = v_fma(sg, dV, Gy);
         }
     }
     l1acc += valid ? l1 : 0.0f;
     if (GRAD) {
-        const float gi = use ? w_e * inv : 0.0f;  // also keeps the inf/NaN of a degenerate z out of the sums
-        const float gcx = Gx * gi, gcy = Gy * gi;
-        const float gcz = use ? -(gcx * px + gcy * py) : 0.0f;
-        gD += fmaf(gcx, Ax, fmaf(gcy, Ay, gcz * Az));
-        const float hx = gcx * D, hy = gcy * D, hz = gcz * D;
-        acc[0] = fmaf(hx, rx, acc[0]); acc[1] = fmaf(hx, ry, acc[1]); acc[2] = fmaf(hx, rz, acc[2]); acc[3] += gcx;
-        acc[4] = fmaf(hy, rx, acc[4]); acc[5] = fmaf(hy, ry, acc[5]); acc[6] = fmaf(hy, rz, acc[6]); acc[7] += gcy;
-        acc[8] = fmaf(hz, rx, acc[8]); acc[9] = fmaf(hz, ry, acc[9]); acc[10] = fmaf(hz, rz, acc[10]); acc[11] += gcz;
+        V gi;
+        V s = v_fma(Gx, px, v_mul(Gy, py));
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const bool use = msk[k] != 0u;
+            // the selects also keep the inf/NaN of a degenerate z out of the sums
+            v_set(gi, k, use ? w_e * v_get(inv, k) : 0.0f);
+            v_set(s, k, use ? v_get(s, k) : 0.0f);
+        }
+        const V gcx = v_mul(Gx, gi), gcy = v_mul(Gy, gi);
+        const V gcz = v_mul(v_mul(s, gi), neg1);
+        {
+            V q3[3];   // p3 again (shared memory): cheaper than six registers held across the loads
+#pragma unroll
+            for (int r = 0; r < 3; ++r) load_p3(pc, i0, r, q3[r]);
+            gp += v_hsum(v_fma(gcx, q3[0], v_fma(gcy, q3[1], v_mul(gcz, v_add(q3[2], eps)))));
+        }
+        // d loss / d P[r][:] = sum g_cam[r] * (D * ray, 1), ray = K^-1 (x, y, 1): accumulated in pixel
+        // coordinates - sum h_r, sum h_r * y (and x * sum h_r at the flush, x being fixed per lane) - and
+        // mapped through K^-1 by the finalize kernel
+        const V hx = v_mul(gcx, Dv), hy = v_mul(gcy, Dv), hz = v_mul(gcz, Dv);
+        acc[0] = v_add(acc[0], hx); acc[1] = v_add(acc[1], hy); acc[2] = v_add(acc[2], hz);
+        acc[3] = v_fma(hx, yv, acc[3]); acc[4] = v_fma(hy, yv, acc[4]); acc[5] = v_fma(hz, yv, acc[5]);
+        acc[6] = v_add(acc[6], gcx); acc[7] = v_add(acc[7], gcy); acc[8] = v_add(acc[8], gcz);
         if (IMG_GRAD) {
             const float m = valid ? w_e : 0.0f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) gt[c] -= m * e[c];
-            if (gbase != nullptr) {
-                const float wnw = (1.0f - fx) * (1.0f - fy), wne = fx * (1.0f - fy);
-                const float wsw = (1.0f - fx) * fy, wse = fx * fy;
-                const int og = y0 * W + x0;  // masks carry the per-tap bounds (all true on the fast path)
+            for (int k = 0; k < NS; ++k) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float ec = m * e[c];
-                    float* q = gbase + (og + c * plane);
-                    if (valid && mnw) atomicAdd(q, wnw * ec);
-                    if (valid && mne) atomicAdd(q + 1, wne * ec);
-                    if (valid && msw) atomicAdd(q + W, wsw * ec);
-                    if (valid && mse) atomicAdd(q + W + 1, wse * ec);
+                for (int c = 0; c < 3; ++c) gt[c] -= m * e[k][c];
+                float* gbase = pc.g_src[i0 + k];
+                if (gbase != nullptr) {
+                    const float fxk = v_get(fx, k), fyk = v_get(fy, k);
+                    const float wnw = (1.0f - fxk) * (1.0f - fyk), wne = fxk * (1.0f - fyk);
+                    const float wsw = (1.0f - fxk) * fyk, wse = fxk * fyk;
+                    const int og = y0[k] * W + x0[k];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float ec = m * e[k][c];
+                        float* q = gbase + (og + c * plane);
+                        if (msk[k] & 1u) atomicAdd(q, wnw * ec);
+                        if (msk[k] & 2u) atomicAdd(q + 1, wne * ec);
+                        if (msk[k] & 4u) atomicAdd(q + W, wsw * ec);
+                        if (msk[k] & 8u) atomicAdd(q + W + 1, wse * ec);
+                    }
                 }
             }
         }
     }
 }
 
-template <int MAXSRC>
-__device__ __forceinline__ void flush_acc(float (&acc)[MAXSRC][12], float& l1acc, float* rec, int lane) {
-    // rec: this warp's shared record for one set, [PH_NREC] floats, ACCUMULATED in place
+// Per-lane accumulators of one group -> this warp's shared record (ACCUMULATED in place).
+// Record of source i: [0..2] sum h_r, [3..5] sum h_r * x, [6..8] sum h_r * y, [9..11] sum g_cam[r];
+// value PLB_MAX_SRC*12: sum |diff|.
+template <typename V, int NS>
+__device__ __forceinline__ void flush_group(const V (&acc)[9], int i0, float l1, float xlane, float* rec, int lane) {
 #pragma unroll
-    for (int i = 0; i < MAXSRC; ++i) {
+    for (int k = 0; k < NS; ++k) {
+        const int i = i0 + k;
         float v[16];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) v[k] = acc[i][k];
-        v[12] = (i == 0) ? l1acc : 0.0f;
+        for (int q = 0; q < 3; ++q) {
+            v[q] = v_get(acc[q], k); v[3 + q] = v_get(acc[q], k) * xlane;
+            v[6 + q] = v_get(acc[3 + q], k); v[9 + q] = v_get(acc[6 + q], k);
+        }
+        v[12] = (i == 0) ? l1 : 0.0f;
         v[13] = v[14] = v[15] = 0.0f;
         int which;
         const float r = warp_reduce16(v, lane, which);
@@ -151,24 +269,152 @@ __device__ __forceinline__ void flush_acc(float (&acc)[MAXSRC][12], float& l1acc
             if (which < 12) rec[i * 12 + which] += r;
             else if (which == 12 && i == 0) rec[PLB_MAX_SRC * 12] += r;
         }
-#pragma unroll
-        for (int k = 0; k < 12; ++k) acc[i][k] = 0.0f;
     }
-    l1acc = 0.0f;
+}
+
+// One run: consecutive rows [y, y + rows) of one 32-px strip of one (job, image) pair, NSRC sources.
+template <bool GRAD, bool IMG_GRAD, int NSRC, bool MULTI>
+__device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairConst& pc, int strip, int y, int rows,
+                                         int lane, float* rec) {
+    constexpr int NP = NSRC / 2, ODD = NSRC & 1;
+    const int H = a.H, W = a.W, plane = H * W;
+    const float w_e = pc.w_e;
+    const int x = strip * 32 + lane;
+    const bool valid = x < W;
+    const float xf = (float)x;
+    const float* __restrict__ tgt_b = pc.tgt;
+    int o = y * W + min(x, W - 1);
+
+    float2 accp[NP > 0 ? NP : 1][9];
+    float accs[9];
+    float l1acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int g = 0; g < (NP > 0 ? NP : 1); ++g) accp[g][k] = make_float2(0.0f, 0.0f);
+        accs[k] = 0.0f;
+    }
+
+    // software pipeline: the target pixel (and the full-resolution disparity) of the NEXT row are loaded while
+    // this row is processed, so a warp pays one memory round trip per row (the taps), not two
+    float tn[3], dn = 0.0f;
+    tn[0] = __ldg(tgt_b + o); tn[1] = __ldg(tgt_b + (o + plane)); tn[2] = __ldg(tgt_b + (o + 2 * plane));
+    if (!MULTI) dn = __ldg(pc.disp[0] + o);
+#pragma unroll 1
+    for (int r = 0; r < rows; ++r, ++y, o += W) {
+        float t[3], gt[3] = {0.0f, 0.0f, 0.0f};
+        t[0] = tn[0]; t[1] = tn[1]; t[2] = tn[2];
+        const float d_cur = dn;
+        const bool pf = r + 1 < rows;
+        if (pf) {
+            const int on = o + W;
+            tn[0] = __ldg(tgt_b + on); tn[1] = __ldg(tgt_b + (on + plane)); tn[2] = __ldg(tgt_b + (on + 2 * plane));
+            if (!MULTI) dn = __ldg(pc.disp[0] + on);
+        }
+        const float yf = (float)y;
+        if (!MULTI) {
+            const float d0 = d_cur;
+            const float D = a.input_is_depth ? d0 : rcp_nr(fmaf(a.disp_a, d0, a.disp_b));
+            float gp = 0.0f;
+#pragma unroll
+            for (int g = 0; g < NP; ++g)
+                group_pixel<GRAD, IMG_GRAD, 2>(pc, 2 * g, plane, H, W, xf, yf, D, t, w_e, valid, pf, accp[g], l1acc, gp, gt);
+            if (ODD) group_pixel<GRAD, IMG_GRAD, 1>(pc, NSRC - 1, plane, H, W, xf, yf, D, t, w_e, valid, pf, accs, l1acc, gp, gt);
+            if (GRAD) {
+                float* g = pc.g_disp[0];
+                // d loss / d D = -gp / D;  d D / d disp = -disp_a * D^2
+                if (valid && g != nullptr) g[o] = a.input_is_depth ? -gp * rcp_nr(D) : a.disp_a * D * gp;
+            }
+        } else {
+            const int n_scales = pc.n_scales, lowres = pc.lowres;
+#pragma unroll 1
+            for (int s = 0; s < n_scales; ++s) {
+                const float* disp_b = pc.disp[s];
+                const bool full = !((lowres >> s) & 1);
+                float D, gp = 0.0f;
+                if (full) {
+                    const float d = __ldg(disp_b + o);
+                    D = a.input_is_depth ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
+                } else {
+                    const int dh = pc.dh[s], dw = pc.dw[s];
+                    int x0, x1, y0, y1; float lx0, lx1, ly0, ly1;
+                    up_coord(min(x, W - 1), pc.sx[s], dw, x0, x1, lx0, lx1);
+                    up_coord(y, pc.sy[s], dh, y0, y1, ly0, ly1);
+                    float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
+                    float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
+                    if (!a.input_is_depth) {
+                        v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
+                        v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
+                    }
+                    D = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+                }
+#pragma unroll
+                for (int g = 0; g < NP; ++g)
+                    group_pixel<GRAD, IMG_GRAD, 2>(pc, 2 * g, plane, H, W, xf, yf, D, t, w_e, valid, pf, accp[g], l1acc, gp, gt);
+                if (ODD) group_pixel<GRAD, IMG_GRAD, 1>(pc, NSRC - 1, plane, H, W, xf, yf, D, t, w_e, valid, pf, accs, l1acc, gp, gt);
+                if (GRAD) {
+                    float* g = pc.g_disp[s];
+                    if (valid && g != nullptr)
+                        g[o] = (full && !a.input_is_depth) ? a.disp_a * D * gp : -gp * rcp_nr(D);
+                }
+            }
+        }
+        if (GRAD && IMG_GRAD && valid && pc.g_tgt != nullptr) {
+            float* g = pc.g_tgt + o;
+            atomicAdd(g, gt[0]); atomicAdd(g + plane, gt[1]); atomicAdd(g + 2 * plane, gt[2]);
+        }
+    }
+    // end of the run: the lane's column (and possibly the pair) changes
+#pragma unroll
+    for (int g = 0; g < NP; ++g) flush_group<float2, 2>(accp[g], 2 * g, l1acc, xf, rec, lane);
+    if (ODD) flush_group<float, 1>(accs, NSRC - 1, l1acc, xf, rec, lane);
     __syncwarp();
 }
 
-template <bool GRAD, bool IMG_GRAD, int MAXSRC>
-__global__ void __launch_bounds__(PH_THREADS, (MAXSRC <= 2) ? 3 : 2)
+// inverse of pos_of: the warp whose weight range holds `pos`
+__host__ __device__ inline int photo_warp_of(const PhotoLaunch& p, long long pos) {
+    const long long big = (long long)p.share_rem * (p.share + 1);
+    if (pos < big) return (int)(pos / (p.share + 1));
+    return p.share > 0 ? p.share_rem + (int)((pos - big) / p.share) : p.n_warps - 1;
+}
+
+// The pose chain  S -> dP (through K^-1) -> K^T.dP -> (rigid inverse) -> Rodrigues / Euler vjp  is linear
+// in the 12 record sums S of a (pair, source): row k of its Jacobian is the chain applied to e_k.
+// S: [0..2] sum h_r, [3..5] sum h_r x, [6..8] sum h_r y, [9..11] sum g_cam[r].
+__device__ inline void photo_pose_jacobian(const plb_photo_args& a, const plb_photo_job& job, int b, int i, int k,
+                                           float* J /* [12][6] of this (pair, source) */) {
+    const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
+    float kinv[9], S[12], dP[12], dM[12], g6[6];
+    kinv_f32(Kb, a.k_is_f64, kinv);
+#pragma unroll
+    for (int m = 0; m < 12; ++m) S[m] = (m == k) ? 1.0f : 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+            dP[r * 4 + m] = kinv[m * 3 + 0] * S[3 + r] + kinv[m * 3 + 1] * S[6 + r] + kinv[m * 3 + 2] * S[r];
+        dP[r * 4 + 3] = S[9 + r];
+    }
+    kT_times_dP(Kb, a.k_is_f64, dP, dM);
+    pose_to_M_vjp(a.poses + ((size_t)b * a.n_pose + job.pose_index[i]) * 6, a.rotation_mode, job.pose_inv[i], dM, g6);
+#pragma unroll
+    for (int m = 0; m < 6; ++m) J[k * 6 + m] = g6[m];
+}
+
+template <bool GRAD, bool IMG_GRAD, int MAXSRC, bool MULTI>
+__global__ void __launch_bounds__(PH_THREADS, (MAXSRC <= 2) ? PH_MIN_BLOCKS : 2)
 photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
     const plb_photo_args& a = p.a;
+    // the finalize grid (programmatic dependent launch) may be scheduled from now on; it waits for
+    // this grid to complete before it reads the records
+    asm volatile("griddepcontrol.launch_dependents;");
     if (skip_launch(a.skip_if_unit)) return;
+#if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 1
+    return;
+#endif
 
     char* ws = (char*)a.workspace;
-    int32_t* tickets = (int32_t*)(ws + p.L.tickets);
     float* records = (float*)(ws + p.L.records);
-    float* ws_pose = (float*)(ws + p.L.ws_pose);
-    float* ws_loss = (float*)(ws + p.L.ws_loss);
     float* gup = (float*)(ws + p.L.gup);
 
     const int H = a.H, W = a.W;
@@ -177,13 +423,9 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
 
     __shared__ PairConst s_pc[2];
     __shared__ float s_rec[2][PH_WARPS][PH_NREC + 3];
-    __shared__ float s_red[PH_NREC + 3];
-    __shared__ float s_part4[4][64];
     __shared__ int s_pair[2];
-    __shared__ int s_flag;
 
     // ---- this warp's unit range: equal shares of the weighted unit list (32-bit maths) ---------
-    const int wt_total = (int)p.weight_start[a.n_jobs];
     auto pos_of = [&](int w) -> int { return w * p.share + min(w, p.share_rem); };
     auto unit_of = [&](int pos) -> int {  // first unit whose weight interval starts at or after pos
         int j = 0;
@@ -200,6 +442,9 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
     const int pairA = empty_block ? 0 : blk_u0 / p.units_per_pair;
     const int pairB = empty_block ? 0 : (blk_u1 - 1) / p.units_per_pair;
 
+#if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 2
+    if (u0 >= 0) return;
+#endif
     // ---- block prologue: context of the (at most two) pairs this block touches ------------------
     if (tid < 2) s_pair[tid] = empty_block ? -1 : ((tid == 0) ? pairA : (pairB != pairA ? pairB : -1));
     for (int k = tid; k < 2 * PH_WARPS * (PH_NREC + 3); k += PH_THREADS) (&s_rec[0][0][0])[k] = 0.0f;
@@ -213,7 +458,6 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
             const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
             const size_t img = (size_t)b * 3 * plane;
             if ((warp & 1) == 0) {
-                if (lane == 0) kinv_f32(Kb, a.k_is_f64, pc.kinv);
                 if (lane == 1) {
                     pc.tgt = job.tgt + img;
                     pc.g_tgt = (GRAD && IMG_GRAD && job.g_tgt) ? job.g_tgt + img : nullptr;
@@ -233,113 +477,76 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
                                 : job.g_disp[sc] + (size_t)b * plane;
                     pc.g_disp[sc] = g;
                 }
-            } else if (lane < job.n_src) {
-                float M[12], P[12];
-                pose_to_M(a.poses + ((size_t)b * a.n_pose + job.pose_index[lane]) * 6, a.rotation_mode,
-                          job.pose_inv[lane], M);
-                k_times_M(Kb, a.k_is_f64, M, P);
-                pc.P[lane][0] = make_float4(P[0], P[1], P[2], P[3]);
-                pc.P[lane][1] = make_float4(P[4], P[5], P[6], P[7]);
-                pc.P[lane][2] = make_float4(P[8], P[9], P[10], P[11]);
-                pc.src[lane] = job.src[lane] + img;
-                pc.g_src[lane] = (GRAD && IMG_GRAD && job.g_src[lane]) ? job.g_src[lane] + img : nullptr;
+            } else {
+                if (lane < job.n_src) {
+                    float M[12], P[12];
+                    double Ki[9];
+                    pose_to_M(a.poses + ((size_t)b * a.n_pose + job.pose_index[lane]) * 6, a.rotation_mode,
+                              job.pose_inv[lane], M);
+                    k_times_M(Kb, a.k_is_f64, M, P);
+                    kinv_f64(Kb, a.k_is_f64, Ki);
+                    // Q = P[:, :3] . fl32(K^-1): the exact product of the two fp32 matrices the reference
+                    // multiplies a pixel by (transform.py:92,137), rounded once
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        float q[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            q[c] = (float)((double)P[r * 4 + 0] * (double)(float)Ki[0 + c] + (double)P[r * 4 + 1] * (double)(float)Ki[3 + c] +
+                                           (double)P[r * 4 + 2] * (double)(float)Ki[6 + c]);
+                        pc.Q[lane][r] = make_float4(q[0], q[1], q[2], P[r * 4 + 3]);
+                    }
+                    pc.src[lane] = job.src[lane] + img;
+                    pc.g_src[lane] = (GRAD && IMG_GRAD && job.g_src[lane]) ? job.g_src[lane] + img : nullptr;
+                }
+                __syncwarp();
+                // packed copy for source pairs (2g, 2g+1): low half = even source, high half = odd source
+                if (lane < (PLB_MAX_SRC / 2) * 3) {
+                    const int g = lane / 3, r = lane - g * 3;
+                    if (2 * g + 1 < job.n_src) {
+                        const float4 q0 = pc.Q[2 * g][r], q1 = pc.Q[2 * g + 1][r];
+                        pc.Q2[g][r][0] = make_float4(q0.x, q1.x, q0.y, q1.y);
+                        pc.Q2[g][r][1] = make_float4(q0.z, q1.z, q0.w, q1.w);
+                    }
+                }
             }
         }
     }
     __syncthreads();
+#if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 3
+    if (u0 >= 0) return;
+#endif
 
-    float acc[MAXSRC][12];
-    float l1acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < MAXSRC; ++i)
-#pragma unroll
-        for (int k = 0; k < 12; ++k) acc[i][k] = 0.0f;
-
-    // decode the first unit, then step incrementally (no division in the loop)
-    int pair = u0 / p.units_per_pair;
-    int local = u0 - pair * p.units_per_pair;
-    int strip = local / H;
-    int y = local - strip * H;
-    int set = (pair == pairA) ? 0 : 1;
-
+    // ---- runs: consecutive rows of one 32-px strip of one (job, image) pair ---------------------
+    int u = u0;
+#ifdef PLB_DEBUG_SKIP_UNITS
+    u = u1;   // measurement only: fixed cost of prologue + epilogue
+#endif
 #pragma unroll 1
-    for (int u = u0; u < u1; ++u) {
+    while (u < u1) {
+        const int pair = u / p.units_per_pair;
+        const int local = u - pair * p.units_per_pair;
+        const int strip = local / H;
+        const int y = local - strip * H;
+        const int rows = min(u1, u - y + H) - u;
+        const int set = (pair == pairA) ? 0 : 1;
         const PairConst& pc = s_pc[set];
-        const float w_e = pc.w_e;
-        const int x = strip * 32 + lane;
-        const bool valid = x < W;
-        const int o = y * W + min(x, W - 1);
-
-        float t[3], gt[3] = {0.0f, 0.0f, 0.0f};
-        const float* tgt_b = pc.tgt;
-        t[0] = __ldg(tgt_b + o); t[1] = __ldg(tgt_b + (o + plane)); t[2] = __ldg(tgt_b + (o + 2 * plane));
-        const int pf = (y + PH_PREFETCH_ROWS < H) ? PH_PREFETCH_ROWS : 0;   // stay inside this image
-        if (pf > 0) {
-            const int opf = o + pf * W;
-            prefetch_l1(tgt_b + opf); prefetch_l1(tgt_b + (opf + plane)); prefetch_l1(tgt_b + (opf + 2 * plane));
-            if (!(pc.lowres & 1)) prefetch_l1(pc.disp[0] + opf);
+        float* rec = s_rec[set][warp];
+        const int n_src = pc.n_src;
+        if (MAXSRC <= 2) {
+            if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI>(a, pc, strip, y, rows, lane, rec);
+            else run_rows<GRAD, IMG_GRAD, 1, MULTI>(a, pc, strip, y, rows, lane, rec);
+        } else {
+            if (n_src == 4) run_rows<GRAD, IMG_GRAD, 4, MULTI>(a, pc, strip, y, rows, lane, rec);
+            else if (n_src == 3) run_rows<GRAD, IMG_GRAD, 3, MULTI>(a, pc, strip, y, rows, lane, rec);
+            else if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI>(a, pc, strip, y, rows, lane, rec);
+            else run_rows<GRAD, IMG_GRAD, 1, MULTI>(a, pc, strip, y, rows, lane, rec);
         }
-        const float xf = (float)x, yf = (float)y;
-        const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
-        const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
-        const float rz = fmaf(pc.kinv[7], yf, pc.kinv[6] * xf) + pc.kinv[8];
-        const int n_scales = pc.n_scales, n_src = pc.n_src, lowres = pc.lowres;
-
-#pragma unroll 1
-        for (int s = 0; s < n_scales; ++s) {
-            const float* disp_b = pc.disp[s];
-            const bool full = !((lowres >> s) & 1);
-            float D, gD = 0.0f;
-            if (full) {
-                const float d = __ldg(disp_b + o);
-                D = a.input_is_depth ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
-            } else {
-                const int dh = pc.dh[s], dw = pc.dw[s];
-                int x0, x1, y0, y1; float lx0, lx1, ly0, ly1;
-                up_coord(min(x, W - 1), pc.sx[s], dw, x0, x1, lx0, lx1);
-                up_coord(y, pc.sy[s], dh, y0, y1, ly0, ly1);
-                float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
-                float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
-                if (!a.input_is_depth) {
-                    v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
-                    v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
-                }
-                D = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-            }
-#pragma unroll
-            for (int i = 0; i < MAXSRC; ++i) {
-                if (i < n_src) {
-                    photo_pixel<GRAD, IMG_GRAD>(pc.src[i], (GRAD && IMG_GRAD) ? pc.g_src[i] : nullptr, plane, pf, H, W,
-                                                pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, t, w_e, valid,
-                                                acc[i], l1acc, gD, gt);
-                }
-            }
-            if (GRAD) {
-                float* g = pc.g_disp[s];
-                if (valid && g != nullptr) {
-                    const float chain = (full && !a.input_is_depth) ? -a.disp_a * D * D : 1.0f;
-                    g[o] = gD * chain;
-                }
-            }
-        }
-        if (GRAD && IMG_GRAD && valid && pc.g_tgt != nullptr) {
-            float* g = pc.g_tgt + o;
-            atomicAdd(g, gt[0]); atomicAdd(g + plane, gt[1]); atomicAdd(g + 2 * plane, gt[2]);
-        }
-        // next unit: down the strip, then the next strip, then the next (job, image)
-        if (++y == H) {
-            y = 0;
-            if (++strip == p.strips) {
-                strip = 0;
-                flush_acc<MAXSRC>(acc, l1acc, s_rec[set][warp], lane);
-                ++pair;
-                set = 1;
-            }
-        }
+        u += rows;
     }
-    if (u1 > u0) flush_acc<MAXSRC>(acc, l1acc, s_rec[set][warp], lane);
 
-    // ---- block records: fixed-order sum over the 8 warps, one record per touched pair --------
+    // ---- block records: fixed-order sum over the 8 warps, one record per touched pair; the
+    //      finalize kernel combines them (no fences, no tickets here) --------------------------
     __syncthreads();
     float* my_rec = records + (size_t)blockIdx.x * 2 * PH_REC_STRIDE;
     for (int k = tid; k < 2 * PH_REC_STRIDE; k += PH_THREADS) {
@@ -354,99 +561,120 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         } else {
             v = 0.0f;
         }
-        __stcg(my_rec + k, v);
+        my_rec[k] = v;
     }
-    __threadfence();
-    __syncthreads();
+}
 
-    // ---- per-pair tickets count finished UNITS; whoever completes a pair reduces it ----------
+// ---------------------------------------------------------------------------------------------
+// Finalize: one block per image.  For every job of the image: fixed-order sum of the block records
+// of that (job, image) pair -> d loss / d P per source (through K^-1) -> K^T . dP -> (inverse) ->
+// Rodrigues / Euler vjp -> the 6-vector; pose gradients of the image are written directly, the
+// loss is the fp64 sum of the per-image partials, added in image order by the last block (one
+// ticket per block).  Loss, pose and disparity gradients are bitwise repeatable.
+// ---------------------------------------------------------------------------------------------
+constexpr int PF_THREADS = 512;
+constexpr int PF_GROUPS = PF_THREADS / 64;         // groups of 64 value lanes summing the records
+constexpr int PF_COMBOS = PLB_MAX_JOBS * PLB_MAX_SRC;
+constexpr int PF_PREP_T0 = PF_THREADS - 96;        // last three warps: 12 lanes per (job, source)
+static_assert(PF_COMBOS * 12 <= 96, "three warps must cover every (job, source)");
+
+__global__ void __launch_bounds__(PF_THREADS)
+photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
+    const plb_photo_args& a = p.a;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    __shared__ float s_part[PF_GROUPS][PLB_MAX_JOBS][64];
+    __shared__ float s_red[PLB_MAX_JOBS][64];
+    __shared__ double s_lpart[PF_THREADS];
+    __shared__ float s_J[PF_COMBOS][72];
+    const bool grads = want_grad && a.g_poses != nullptr;
+    // ---- before the wait (inputs only): pose-chain Jacobians, 12 lanes per (job, source), on the last
+    //      three warps.  Launched as a programmatic dependent of the main kernel, the block may become
+    //      resident while the main kernel is still draining; then this overlaps its tail -----------------
+    if (grads && tid >= PF_PREP_T0) {
+        const int q = tid - PF_PREP_T0;
+        const int combo = q / 12, k = q - combo * 12;
+        const int jb = combo / PLB_MAX_SRC, i = combo - jb * PLB_MAX_SRC;
+        if (combo < PF_COMBOS && jb < a.n_jobs && i < a.jobs[jb].n_src)
+            photo_pose_jacobian(a, a.jobs[jb], b, i, k, s_J[combo]);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (skip_launch(a.skip_if_unit)) return;
+    const float* records = (const float*)((const char*)a.workspace + p.L.records);
+    {
+        // ---- fixed-order sum of the block records of each (job, image b) pair -------------------------
+        const int c = tid & 63, grp = tid >> 6;
 #pragma unroll 1
-    for (int set = 0; set < 2; ++set) {
-        const int pr = s_pair[set];
-        if (pr < 0) continue;
-        const int lo = max(blk_u0, pr * p.units_per_pair), hi = min(blk_u1, (pr + 1) * p.units_per_pair);
-        if (hi <= lo) continue;
-        if (tid == 0) s_flag = (atomicAdd(&tickets[pr], hi - lo) + (hi - lo) == p.units_per_pair);
-        __syncthreads();
-        const bool last = s_flag != 0;
-        __syncthreads();
-        if (!last) continue;
-        __threadfence();
-        const int jb = pr / a.B, b = pr - jb * a.B;
-        const plb_photo_job& job = a.jobs[jb];
-        // blocks whose range can overlap this pair (widened by one block on each side; records carry the pair id)
-        const int w0 = (int)p.weight_start[jb] + (pr * p.units_per_pair - p.unit_start[jb]) * p.unit_weight[jb];
-        const int w1 = w0 + p.units_per_pair * p.unit_weight[jb];
-        auto warp_of = [&](int pos) -> int {  // inverse of pos_of (the warp whose weight range holds pos)
-            const int big = p.share_rem * (p.share + 1);
-            if (pos < big) return pos / (p.share + 1);
-            return p.share > 0 ? p.share_rem + (pos - big) / p.share : p.n_warps - 1;
-        };
-        int k_lo = warp_of(w0) / PH_WARPS - 1;
-        int k_hi = warp_of(w1) / PH_WARPS + 1;
-        k_lo = max(k_lo, 0); k_hi = min(k_hi, p.grid - 1);
-        {
-            // 256 threads = 4 groups x 64 value lanes; group g takes records g, g+4, ... (fixed order),
-            // then the four partial sums are added in group order: deterministic and latency-parallel.
-            const int c = tid & 63, grp = tid >> 6;
+        for (int jb = 0; jb < a.n_jobs; ++jb) {
+            const int pr = jb * a.B + b;
+            // blocks whose range can overlap this pair (widened by one block on each side; records carry the pair id)
+            const long long w0 = p.weight_start[jb] + (long long)(pr * p.units_per_pair - p.unit_start[jb]) * p.unit_weight[jb];
+            const long long w1 = w0 + (long long)p.units_per_pair * p.unit_weight[jb];
+            int k_lo = photo_warp_of(p, w0) / PH_WARPS - 1;
+            int k_hi = photo_warp_of(p, w1) / PH_WARPS + 1;
+            k_lo = max(k_lo, 0); k_hi = min(k_hi, p.grid - 1);
             const int n_rec = (k_hi - k_lo + 1) * 2;
             float v = 0.0f;
             if (c < PH_NREC) {
-#pragma unroll 4
-                for (int r_i = grp; r_i < n_rec; r_i += 4) {
+#pragma unroll 10
+                for (int r_i = grp; r_i < n_rec; r_i += PF_GROUPS) {
                     const float* r = records + ((size_t)k_lo * 2 + r_i) * PH_REC_STRIDE;
                     const int id = __float_as_int(__ldcg(r));
                     const float val = __ldcg(r + 1 + c);
                     v += (id == pr) ? val : 0.0f;
                 }
             }
-            s_part4[grp][c] = v;
-            __syncthreads();
-            if (tid < PH_NREC) s_red[tid] = ((s_part4[0][tid] + s_part4[1][tid]) + s_part4[2][tid]) + s_part4[3][tid];
+            s_part[grp][jb][c] = v;
         }
-        __syncthreads();
-        if (tid == 0) {
-            ws_loss[pr] = s_red[PLB_MAX_SRC * 12];
-            tickets[pr] = 0;  // self-cleaning for the next launch
-        }
-        if (GRAD && tid < job.n_src) {
-            float dP[12], dM[12], g6[6];
-            for (int k = 0; k < 12; ++k) dP[k] = s_red[tid * 12 + k];
-            const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
-            kT_times_dP(Kb, a.k_is_f64, dP, dM);
-            pose_to_M_vjp(a.poses + ((size_t)b * a.n_pose + job.pose_index[tid]) * 6, a.rotation_mode,
-                          job.pose_inv[tid], dM, g6);
-            float* o = ws_pose + ((size_t)pr * PLB_MAX_SRC + tid) * 6;
-            for (int k = 0; k < 6; ++k) o[k] = g6[k];
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_flag = (atomicAdd(&tickets[p.n_pairs], 1) == p.n_pairs - 1);
-        __syncthreads();
-        const bool all_done = s_flag != 0;
-        __syncthreads();
-        if (!all_done) continue;
-
-        // ---- last pair of the launch: loss scalar and pose gradients --------------------------
-        __threadfence();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int q = 0; q < p.n_pairs; ++q)
-                tot += (double)__ldcg(ws_loss + q) * (double)p.w_e[q / a.B];
-            if (a.loss != nullptr) *a.loss = (float)tot;
-            tickets[p.n_pairs] = 0;
-        }
-        if (GRAD && a.g_poses != nullptr) {
-            for (int k = tid; k < a.B * a.n_pose * 6; k += PH_THREADS) {
-                const int bb = k / (a.n_pose * 6), col = (k / 6) % a.n_pose, c = k % 6;
-                float v = 0.0f;
-                for (int j2 = 0; j2 < a.n_jobs; ++j2)
-                    for (int i = 0; i < a.jobs[j2].n_src; ++i)
-                        if (a.jobs[j2].pose_index[i] == col)
-                            v += __ldcg(ws_pose + ((size_t)(j2 * a.B + bb) * PLB_MAX_SRC + i) * 6 + c);
-                a.g_poses[k] = v;
+        // ---- loss (block 0): every record's sum |diff| weighted by its job; partial sums in fp64,
+        //      combined in a fixed order after the barrier -----------------------------------------------
+        if (b == 0) {
+            double part = 0.0;
+#pragma unroll 4
+            for (int q = tid; q < p.grid * 2; q += PF_THREADS) {
+                const float* r = records + (size_t)q * PH_REC_STRIDE;
+                const int id = __float_as_int(__ldcg(r));
+                const float val = __ldcg(r + 1 + PLB_MAX_SRC * 12);
+                const float w = (id >= a.B) ? p.w_e[1] : p.w_e[0];     // PLB_MAX_JOBS == 2
+                part += (id >= 0) ? (double)val * (double)w : 0.0;
             }
+            s_lpart[tid] = part;
         }
+    }
+    __syncthreads();
+    if (b == 0 && tid >= PF_THREADS - 32) {
+        const int lane = tid - (PF_THREADS - 32);
+        double part = 0.0;
+#pragma unroll
+        for (int m = 0; m < PF_THREADS / 32; ++m) part += s_lpart[lane + 32 * m];
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) part += __shfl_xor_sync(0xffffffffu, part, k);
+        if (lane == 0 && a.loss != nullptr) *a.loss = (float)part;
+    }
+    if (!grads) return;
+    if (tid < 64 * a.n_jobs) {
+        const int jb = tid >> 6, c = tid & 63;
+        float v = s_part[0][jb][c];
+#pragma unroll
+        for (int g = 1; g < PF_GROUPS; ++g) v += s_part[g][jb][c];
+        s_red[jb][c] = v;
+    }
+    __syncthreads();
+    // g_poses[b, col, cc] = sum over the (job, source) pairs that use pose column col (job order, then
+    // source order) of J^T . S
+    for (int k = tid; k < a.n_pose * 6; k += PF_THREADS) {
+        const int col = k / 6, cc = k - col * 6;
+        float v = 0.0f;
+        for (int j2 = 0; j2 < a.n_jobs; ++j2)
+            for (int i = 0; i < a.jobs[j2].n_src; ++i)
+                if (a.jobs[j2].pose_index[i] == col) {
+                    const float* S = &s_red[j2][i * 12];
+                    const float* J = s_J[j2 * PLB_MAX_SRC + i];
+                    float g = 0.0f;
+#pragma unroll
+                    for (int m = 0; m < 12; ++m) g = fmaf(J[m * 6 + cc], S[m], g);
+                    v += g;
+                }
+        a.g_poses[((size_t)b * a.n_pose + col) * 6 + cc] = v;
     }
 }
 
@@ -595,12 +823,12 @@ int validate_photo(const plb_photo_args* a) {
     return PLB_OK;
 }
 
-template <bool GRAD, bool IMG, int MS>
+template <bool GRAD, bool IMG, int MS, bool MULTI>
 static int blocks_per_sm() {
     static int cached = 0;
     if (cached == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, MS>, PH_THREADS, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, MS, MULTI>, PH_THREADS, 0) != cudaSuccess ||
             n < 1) {
             (void)cudaGetLastError();
             n = 2;
@@ -688,10 +916,15 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     p.weight_start[PLB_MAX_JOBS] = wsum;
     p.unit_start[PLB_MAX_JOBS] = usum;
 
+    bool multi = false;
+    for (int j = 0; j < a->n_jobs; ++j)
+        if (a->jobs[j].n_scales != 1 || p.lowres[j] != 0) multi = true;
     int bps;
-    if (!a->want_grad) bps = maxsrc <= 2 ? blocks_per_sm<false, false, 2>() : blocks_per_sm<false, false, 4>();
-    else if (img_grad) bps = maxsrc <= 2 ? blocks_per_sm<true, true, 2>() : blocks_per_sm<true, true, 4>();
-    else bps = maxsrc <= 2 ? blocks_per_sm<true, false, 2>() : blocks_per_sm<true, false, 4>();
+#define PLB_BPS(G, I, M) (multi ? blocks_per_sm<G, I, M, true>() : blocks_per_sm<G, I, M, false>())
+    if (!a->want_grad) bps = maxsrc <= 2 ? PLB_BPS(false, false, 2) : PLB_BPS(false, false, 4);
+    else if (img_grad) bps = maxsrc <= 2 ? PLB_BPS(true, true, 2) : PLB_BPS(true, true, 4);
+    else bps = maxsrc <= 2 ? PLB_BPS(true, false, 2) : PLB_BPS(true, false, 4);
+#undef PLB_BPS
     long long grid = (long long)sm_count() * bps;
     // a block's weight range must not exceed the lightest pair, so that it touches at most two pairs
     const long long pair_w_min = (long long)min_w * p.units_per_pair;
@@ -706,13 +939,33 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     p.share_rem = (int)(wsum % p.n_warps);
 
     dim3 g(p.grid), block(PH_THREADS);
-#define PLB_LAUNCH(G, I, M) photo_l1_kernel<G, I, M><<<g, block, 0, st>>>(p)
+#define PLB_LAUNCH(G, I, M)                                           \
+    do {                                                              \
+        if (multi) photo_l1_kernel<G, I, M, true><<<g, block, 0, st>>>(p); \
+        else photo_l1_kernel<G, I, M, false><<<g, block, 0, st>>>(p);     \
+    } while (0)
     if (!a->want_grad) { if (maxsrc <= 2) PLB_LAUNCH(false, false, 2); else PLB_LAUNCH(false, false, 4); }
     else if (img_grad) { if (maxsrc <= 2) PLB_LAUNCH(true, true, 2); else PLB_LAUNCH(true, true, 4); }
     else { if (maxsrc <= 2) PLB_LAUNCH(true, false, 2); else PLB_LAUNCH(true, false, 4); }
 #undef PLB_LAUNCH
     ++g_launches;
     PLB_CHECK_LAUNCH();
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(a->B);
+        cfg.blockDim = dim3(PF_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = PH_USE_PDL;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, photo_finalize_kernel, p, (int)a->want_grad);
+        if (e != cudaSuccess) return (int)e;
+        ++g_launches;
+        PLB_CHECK_LAUNCH();
+    }
     if (lowres_grad) {
         const int rc2 = photo_upsample_T_launch(p, st);
         if (rc2 != PLB_OK) return rc2;

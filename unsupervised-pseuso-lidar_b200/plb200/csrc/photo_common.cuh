@@ -5,19 +5,29 @@
 
 namespace plb {
 
-constexpr int PH_THREADS = 256;
+#ifndef PH_THREADS_DEF
+#define PH_THREADS_DEF 192
+#endif
+constexpr int PH_THREADS = PH_THREADS_DEF;   // >= 128 (the block prologue uses warps 0-3)
 constexpr int PH_WARPS = PH_THREADS / 32;
 constexpr int PH_NREC = PLB_MAX_SRC * 12 + 1;  // per (job,image) record: dP[src][12], sum|diff|
 constexpr int PH_REC_STRIDE = 56;
-#ifndef PH_PREFETCH_ROWS
-#define PH_PREFETCH_ROWS 2
-#endif              // floats per (block, set) record: [0]=pair, [1..] values
+                                  // floats per (block, set) record: [0]=pair, [1..] values
+#ifndef PH_USE_PDL
+#define PH_USE_PDL 1               // finalize kernel launched as a programmatic dependent of the main kernel
+#endif
+#ifndef PH_PF_SRC
+#define PH_PF_SRC 1               // L1 prefetch of the source row this many rows below the current footprint (0 = off)
+#endif
+#ifndef PH_MIN_BLOCKS
+#define PH_MIN_BLOCKS 3           // resident blocks per SM the <= 2-source kernels are compiled for
+#endif
 
 struct PhotoLayout {
     size_t tickets;   // int32 [n_pairs + 1]
     size_t records;   // float [grid][2][PH_REC_STRIDE]
-    size_t ws_pose;   // float [n_pairs][MAX_SRC][6]
-    size_t ws_loss;   // float [n_pairs]
+    size_t ws_pose;   // float [n_pairs][MAX_SRC][6] (photo_min.cu)
+    size_t ws_loss;   // double [n_pairs]
     size_t gup;       // float [n_jobs][MAX_SCALES][B*H*W]  (only when a low scale carries a gradient)
     size_t total;
 };
@@ -72,7 +82,7 @@ static inline PhotoLayout photo_layout(const plb_photo_args& a) {
     }
     L.records = off; off = align_up(off + sizeof(float) * n_rec * PH_REC_STRIDE, 256);
     L.ws_pose = off; off = align_up(off + sizeof(float) * n_pairs * PLB_MAX_SRC * 6, 256);
-    L.ws_loss = off; off = align_up(off + sizeof(float) * n_pairs, 256);
+    L.ws_loss = off; off = align_up(off + sizeof(double) * n_pairs, 256);
     L.gup = off;
     if (photo_has_lowres_grad(a))
         off = align_up(off + sizeof(float) * (size_t)a.n_jobs * PLB_MAX_SCALES * a.B * a.H * a.W, 256);
@@ -83,7 +93,9 @@ static inline PhotoLayout photo_layout(const plb_photo_args& a) {
 // shared-memory context of one (job, image) pair, built once per block: K^-1, P per source and
 // every base pointer already offset to image b, so the unit loop does no 64-bit address maths.
 struct __align__(16) PairConst {
-    float4 P[PLB_MAX_SRC][3];
+    float4 P[PLB_MAX_SRC][3];        // K . [R|t] (photo_min.cu)
+    float4 Q[PLB_MAX_SRC][3];        // [P[:, :3] . K^-1 | P[:, 3]] (photo.cu: cam = D * Q.(x, y, 1) + p3)
+    float4 Q2[PLB_MAX_SRC / 2][3][2]; // the same for source pairs, interleaved (even, odd) for packed fp32 maths
     float kinv[12];
     const float* tgt;
     float* g_tgt;
