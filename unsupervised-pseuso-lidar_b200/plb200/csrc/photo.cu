@@ -24,6 +24,20 @@
 
 namespace plb {
 
+#ifdef PLB_DEBUG_TIMERS
+__device__ unsigned long long g_dbg_t[32];
+__device__ unsigned long long g_dbg_blk[2048];
+__device__ unsigned int g_dbg_sm[2048];
+__device__ __forceinline__ void dbg_stamp(int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_dbg_t[slot] = t;
+}
+#define DBG_STAMP(cond, slot) do { if (cond) dbg_stamp(slot); } while (0)
+#else
+#define DBG_STAMP(cond, slot) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Per-pixel stages.  A "group" is one or two sources handled together.  For a pair of sources all
 // floating-point work runs on Blackwell's packed fp32 pipe (FFMA2 / FADD2 / FMUL2: source 0 in the
@@ -402,13 +416,15 @@ __device__ inline void photo_pose_jacobian(const plb_photo_args& a, const plb_ph
 }
 
 template <bool GRAD, bool IMG_GRAD, int MAXSRC, bool MULTI>
-__global__ void __launch_bounds__(PH_THREADS, (MAXSRC <= 2) ? PH_MIN_BLOCKS : 2)
+__global__ void __launch_bounds__(photo_threads(MAXSRC, MULTI), (MAXSRC <= 2) ? PH_MIN_BLOCKS : 2)
 photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
+    constexpr int PH_THREADS = photo_threads(MAXSRC, MULTI), PH_WARPS = PH_THREADS / 32;
     const plb_photo_args& a = p.a;
     // the finalize grid (programmatic dependent launch) may be scheduled from now on; it waits for
     // this grid to complete before it reads the records
     asm volatile("griddepcontrol.launch_dependents;");
     if (skip_launch(a.skip_if_unit)) return;
+    DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 0 : 4);
 #if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 1
     return;
 #endif
@@ -433,9 +449,14 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         const int rel = pos - (int)p.weight_start[j];
         return p.unit_start[j] + (rel + p.unit_weight[j] - 1) / p.unit_weight[j];
     };
-    const int gw = blockIdx.x * PH_WARPS + warp;
-    const int blk_u0 = unit_of(pos_of(blockIdx.x * PH_WARPS));
-    const int blk_u1 = unit_of(pos_of(blockIdx.x * PH_WARPS + PH_WARPS));
+#ifdef PLB_DEBUG_REVERSE_BLOCKS
+    const int vblk = gridDim.x - 1 - blockIdx.x;
+#else
+    const int vblk = blockIdx.x;     // virtual block index: which share of the unit list this block owns
+#endif
+    const int gw = vblk * PH_WARPS + warp;
+    const int blk_u0 = unit_of(pos_of(vblk * PH_WARPS));
+    const int blk_u1 = unit_of(pos_of(vblk * PH_WARPS + PH_WARPS));
     const int u0 = unit_of(pos_of(gw));
     const int u1 = unit_of(pos_of(gw + 1));
     const bool empty_block = blk_u1 <= blk_u0;  // more blocks than work: still publishes (empty) records
@@ -513,6 +534,7 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         }
     }
     __syncthreads();
+    DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 1 : 5);
 #if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 3
     if (u0 >= 0) return;
 #endif
@@ -548,7 +570,11 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
     // ---- block records: fixed-order sum over the 8 warps, one record per touched pair; the
     //      finalize kernel combines them (no fences, no tickets here) --------------------------
     __syncthreads();
-    float* my_rec = records + (size_t)blockIdx.x * 2 * PH_REC_STRIDE;
+    DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 2 : 6);
+#ifdef PLB_DEBUG_TIMERS
+    if (threadIdx.x == 0 && blockIdx.x < 2048) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g_dbg_blk[blockIdx.x] = t; unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); g_dbg_sm[blockIdx.x] = sm; }
+#endif
+    float* my_rec = records + (size_t)vblk * 2 * PH_REC_STRIDE;
     for (int k = tid; k < 2 * PH_REC_STRIDE; k += PH_THREADS) {
         const int set = k / PH_REC_STRIDE, c = k - set * PH_REC_STRIDE;
         float v;
@@ -563,6 +589,7 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         }
         my_rec[k] = v;
     }
+    DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 3 : 7);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -586,7 +613,14 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
     __shared__ float s_red[PLB_MAX_JOBS][64];
     __shared__ double s_lpart[PF_THREADS];
     __shared__ float s_J[PF_COMBOS][72];
+    __shared__ float s_g6[PF_COMBOS][6];
+    __shared__ int s_col[PF_COMBOS];                   // pose column of each (job, source), -1 = unused
     const bool grads = want_grad && a.g_poses != nullptr;
+    if (tid < PF_COMBOS) {
+        const int jb = tid / PLB_MAX_SRC, i = tid - jb * PLB_MAX_SRC;
+        s_col[tid] = (jb < a.n_jobs && i < a.jobs[jb].n_src) ? a.jobs[jb].pose_index[i] : -1;
+    }
+    DBG_STAMP(b == 0 && (tid == 0 || tid == PF_PREP_T0), tid == 0 ? 8 : 9);
     // ---- before the wait (inputs only): pose-chain Jacobians, 12 lanes per (job, source), on the last
     //      three warps.  Launched as a programmatic dependent of the main kernel, the block may become
     //      resident while the main kernel is still draining; then this overlaps its tail -----------------
@@ -597,10 +631,27 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
         if (combo < PF_COMBOS && jb < a.n_jobs && i < a.jobs[jb].n_src)
             photo_pose_jacobian(a, a.jobs[jb], b, i, k, s_J[combo]);
     }
+    DBG_STAMP(b == 0 && tid == PF_PREP_T0, 10);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (skip_launch(a.skip_if_unit)) return;
+    DBG_STAMP(b == 0 && (tid == 0 || tid == PF_PREP_T0), tid == 0 ? 11 : 12);
     const float* records = (const float*)((const char*)a.workspace + p.L.records);
     {
+        // ---- loss (block 0): every record's sum |diff|, weighted by its job; the loads are issued first
+        //      so that they share one L2 round trip with the record loads below --------------------------
+        constexpr int LQ = 6;                         // covers grids up to 6 * 512 / 2 = 1536 blocks
+        float lval[LQ];
+        int lid[LQ];
+        if (b == 0) {
+#pragma unroll
+            for (int m = 0; m < LQ; ++m) {
+                const int q = tid + m * PF_THREADS;
+                const bool in = q < p.grid * 2;
+                const float* r = records + (size_t)(in ? q : 0) * PH_REC_STRIDE;
+                lid[m] = in ? __float_as_int(__ldcg(r)) : -1;
+                lval[m] = in ? __ldcg(r + 1 + PLB_MAX_SRC * 12) : 0.0f;
+            }
+        }
         // ---- fixed-order sum of the block records of each (job, image b) pair -------------------------
         const int c = tid & 63, grp = tid >> 6;
 #pragma unroll 1
@@ -609,8 +660,8 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
             // blocks whose range can overlap this pair (widened by one block on each side; records carry the pair id)
             const long long w0 = p.weight_start[jb] + (long long)(pr * p.units_per_pair - p.unit_start[jb]) * p.unit_weight[jb];
             const long long w1 = w0 + (long long)p.units_per_pair * p.unit_weight[jb];
-            int k_lo = photo_warp_of(p, w0) / PH_WARPS - 1;
-            int k_hi = photo_warp_of(p, w1) / PH_WARPS + 1;
+            int k_lo = photo_warp_of(p, w0) / p.warps_per_block - 1;
+            int k_hi = photo_warp_of(p, w1) / p.warps_per_block + 1;
             k_lo = max(k_lo, 0); k_hi = min(k_hi, p.grid - 1);
             const int n_rec = (k_hi - k_lo + 1) * 2;
             float v = 0.0f;
@@ -625,22 +676,26 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
             }
             s_part[grp][jb][c] = v;
         }
-        // ---- loss (block 0): every record's sum |diff| weighted by its job; partial sums in fp64,
-        //      combined in a fixed order after the barrier -----------------------------------------------
         if (b == 0) {
             double part = 0.0;
-#pragma unroll 4
-            for (int q = tid; q < p.grid * 2; q += PF_THREADS) {
+#pragma unroll
+            for (int m = 0; m < LQ; ++m) {
+                const float w = (lid[m] >= a.B) ? p.w_e[1] : p.w_e[0];     // PLB_MAX_JOBS == 2
+                part += (lid[m] >= 0) ? (double)lval[m] * (double)w : 0.0;
+            }
+            // grids beyond LQ * PF_THREADS / 2 blocks (never launched today: <= 148 x 8)
+            for (int q = tid + LQ * PF_THREADS; q < p.grid * 2; q += PF_THREADS) {
                 const float* r = records + (size_t)q * PH_REC_STRIDE;
                 const int id = __float_as_int(__ldcg(r));
-                const float val = __ldcg(r + 1 + PLB_MAX_SRC * 12);
-                const float w = (id >= a.B) ? p.w_e[1] : p.w_e[0];     // PLB_MAX_JOBS == 2
-                part += (id >= 0) ? (double)val * (double)w : 0.0;
+                const float w = (id >= a.B) ? p.w_e[1] : p.w_e[0];
+                part += (id >= 0) ? (double)__ldcg(r + 1 + PLB_MAX_SRC * 12) * (double)w : 0.0;
             }
             s_lpart[tid] = part;
         }
     }
+    DBG_STAMP(b == 0 && tid == 0, 13);
     __syncthreads();
+    DBG_STAMP(b == 0 && tid == 0, 14);
     if (b == 0 && tid >= PF_THREADS - 32) {
         const int lane = tid - (PF_THREADS - 32);
         double part = 0.0;
@@ -659,24 +714,42 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
         s_red[jb][c] = v;
     }
     __syncthreads();
-    // g_poses[b, col, cc] = sum over the (job, source) pairs that use pose column col (job order, then
-    // source order) of J^T . S
+    // 6-vector of every (job, source): J^T . S, one thread per element
+    if (tid < PF_COMBOS * 6) {
+        const int combo = tid / 6, cc = tid - combo * 6;
+        const int jb = combo / PLB_MAX_SRC, i = combo - jb * PLB_MAX_SRC;
+        float g = 0.0f;
+        if (s_col[combo] >= 0) {
+            const float* S = &s_red[jb][i * 12];
+#pragma unroll
+            for (int m = 0; m < 12; ++m) g = fmaf(s_J[combo][m * 6 + cc], S[m], g);
+        }
+        s_g6[combo][cc] = g;
+    }
+    __syncthreads();
+    // g_poses[b, col, cc] = sum over the (job, source) pairs that use pose column col (job order, then source order)
     for (int k = tid; k < a.n_pose * 6; k += PF_THREADS) {
         const int col = k / 6, cc = k - col * 6;
         float v = 0.0f;
-        for (int j2 = 0; j2 < a.n_jobs; ++j2)
-            for (int i = 0; i < a.jobs[j2].n_src; ++i)
-                if (a.jobs[j2].pose_index[i] == col) {
-                    const float* S = &s_red[j2][i * 12];
-                    const float* J = s_J[j2 * PLB_MAX_SRC + i];
-                    float g = 0.0f;
 #pragma unroll
-                    for (int m = 0; m < 12; ++m) g = fmaf(J[m * 6 + cc], S[m], g);
-                    v += g;
-                }
+        for (int combo = 0; combo < PF_COMBOS; ++combo)
+            if (s_col[combo] == col) v += s_g6[combo][cc];
         a.g_poses[((size_t)b * a.n_pose + col) * 6 + cc] = v;
     }
+    DBG_STAMP(b == 0 && tid == 0, 15);
 }
+
+#ifdef PLB_DEBUG_TIMERS
+extern "C" int plb_debug_timers(unsigned long long* out32) {
+    return (int)cudaMemcpyFromSymbol(out32, g_dbg_t, sizeof(unsigned long long) * 32);
+}
+extern "C" int plb_debug_block_ends(unsigned long long* out2048) {
+    return (int)cudaMemcpyFromSymbol(out2048, g_dbg_blk, sizeof(unsigned long long) * 2048);
+}
+extern "C" int plb_debug_block_sms(unsigned int* out2048) {
+    return (int)cudaMemcpyFromSymbol(out2048, g_dbg_sm, sizeof(unsigned int) * 2048);
+}
+#endif
 
 // Transposed bilinear upsample (gather form, deterministic) + disp->depth chain:
 // g_disp[s][b,j,i] = dD/dd * sum over the full-resolution pixels whose align_corners=False
@@ -828,7 +901,7 @@ static int blocks_per_sm() {
     static int cached = 0;
     if (cached == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, MS, MULTI>, PH_THREADS, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, MS, MULTI>, photo_threads(MS, MULTI), 0) != cudaSuccess ||
             n < 1) {
             (void)cudaGetLastError();
             n = 2;
@@ -934,11 +1007,12 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     if (grid > photo_max_grid(*a)) grid = photo_max_grid(*a);
     if (grid < 1) grid = 1;
     p.grid = (int)grid;
-    p.n_warps = p.grid * PH_WARPS;
+    p.warps_per_block = photo_threads(maxsrc <= 2 ? 2 : 4, multi) / 32;
+    p.n_warps = p.grid * p.warps_per_block;
     p.share = (int)(wsum / p.n_warps);
     p.share_rem = (int)(wsum % p.n_warps);
 
-    dim3 g(p.grid), block(PH_THREADS);
+    dim3 g(p.grid), block(photo_threads(maxsrc <= 2 ? 2 : 4, multi));
 #define PLB_LAUNCH(G, I, M)                                           \
     do {                                                              \
         if (multi) photo_l1_kernel<G, I, M, true><<<g, block, 0, st>>>(p); \

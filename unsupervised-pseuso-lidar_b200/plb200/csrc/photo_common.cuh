@@ -5,11 +5,19 @@
 
 namespace plb {
 
-#ifndef PH_THREADS_DEF
-#define PH_THREADS_DEF 192
+// Threads per block of the fused L1 kernel, per variant (tuned on B200, profiles/README.md): the
+// single-scale <= 2-source kernel runs best with 96 registers and no spills (3 x 192 threads per SM);
+// the multi-scale / many-source variants prefer 256-thread blocks.  >= 128: the prologue uses warps 0-3.
+#ifndef PH_THREADS_SINGLE
+#define PH_THREADS_SINGLE 192
 #endif
-constexpr int PH_THREADS = PH_THREADS_DEF;   // >= 128 (the block prologue uses warps 0-3)
-constexpr int PH_WARPS = PH_THREADS / 32;
+#ifndef PH_THREADS_MULTI
+#define PH_THREADS_MULTI 256
+#endif
+__host__ __device__ constexpr int photo_threads(int maxsrc, bool multi) {
+    return (maxsrc <= 2 && !multi) ? PH_THREADS_SINGLE : PH_THREADS_MULTI;
+}
+constexpr int PH_MAX_WARPS = 8;
 constexpr int PH_NREC = PLB_MAX_SRC * 12 + 1;  // per (job,image) record: dP[src][12], sum|diff|
 constexpr int PH_REC_STRIDE = 56;
                                   // floats per (block, set) record: [0]=pair, [1..] values
@@ -37,7 +45,8 @@ struct PhotoLaunch {
     plb_photo_args a;
     PhotoLayout L;
     int grid;                            // number of blocks
-    int n_warps;                         // grid * PH_WARPS
+    int warps_per_block;                 // photo_threads() / 32 of the launched variant
+    int n_warps;                         // grid * warps_per_block
     int strips;                          // ceil(W / 32)
     int units_per_pair;                  // strips * H
     int n_pairs;                         // n_jobs * B
