@@ -11,6 +11,9 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(raw.splitlines()))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
+end_i = next((i for i, r in enumerate(rows) if i > hdr_i and r and r[0] == "Kernel Name"), len(rows))
+print(" ".join(rows[hdr_i - 1][:2])[:110])
+rows = rows[:end_i]   # first kernel of the report only
 iS, iE, iSmp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 data = [(r[iS].strip(), int(r[iE] or 0), int(r[iSmp] or 0)) for r in rows[hdr_i + 1:] if len(r) > iE]
 tot_e = sum(d[1] for d in data)
