@@ -133,6 +133,36 @@ size_t plb_smooth_workspace_bytes(const plb_smooth_args* args);
 int plb_smooth_loss(const plb_smooth_args* args, void* stream);
 
 /*
+ * Edge-aware first-order disparity smoothness, forward + gradient.
+ * NOT IN THE REFERENCE (its live smoothness is plb_smooth_loss); north_star asks for it.  Formula of the
+ * monodepth2 lineage the reference's model files cite (models/depth/layers.py:1-2):
+ *   sum_s (1/f_s) [ mean(|dx d'| exp(-mean_c |dx I_s|)) + mean(|dy d'| exp(-mean_c |dy I_s|)) ],
+ *   d' = d / (mean_hw(d) + 1e-7) when `normalize`, I_s = avg_pool2d(tgt, f_s), f_s = H / dh[s].
+ * Parity unpinned: checked against oracle/restated.py::edge_aware_smooth_loss only.
+ */
+typedef struct plb_edge_args {
+    int32_t B, H, W;
+    int32_t n_scales;
+    const float* tgt;                   /* [B,3,H,W] target image                                  */
+    const float* disp[PLB_MAX_SCALES];  /* [B,1,dh,dw] disparity pyramid; H % dh == 0, dw == W / (H/dh) */
+    int32_t dh[PLB_MAX_SCALES];
+    int32_t dw[PLB_MAX_SCALES];
+    float* g_disp[PLB_MAX_SCALES];      /* out; NULL = not wanted                                   */
+    float* g_scratch[PLB_MAX_SCALES];   /* [B,1,dh,dw] scratch, required when normalize && g_disp   */
+    int32_t accumulate;                 /* 1: g_disp += grad, 0: g_disp = grad                      */
+    int32_t normalize;
+    int32_t want_grad;
+    int32_t reserved;
+    float* loss;                        /* out (written) [1]                                        */
+    const float* upstream;              /* device scalar or NULL (=1)                               */
+    void* workspace;                    /* plb_edge_smooth_workspace_bytes() bytes                  */
+    size_t workspace_bytes;
+} plb_edge_args;
+
+size_t plb_edge_smooth_workspace_bytes(const plb_edge_args* args);
+int plb_edge_smooth_loss(const plb_edge_args* args, void* stream);
+
+/*
  * Stand-alone inverse warp (image out) and its vjp.
  * Replaces inverse_warp (geometry/pose_geometry.py:201-228) incl. F.grid_sample
  * (bilinear, zeros padding, align_corners=True).

@@ -64,6 +64,14 @@ class Losses:
             pred_map = [pred_map]
         return ops.smooth_only(list(pred_map), fused_backward=self.fused_backward)
 
+    def edge_aware_smooth_loss(self, disparity, tgt_img, normalize=True):
+        """NOT in the reference (its smoothness is `smooth_loss`): the edge-aware first-order term of the
+        monodepth2 lineage the model files cite (`models/depth/layers.py:1-2`), which north_star lists.
+        `disparity`: one [B,1,h,w] map or a pyramid of them (scale s weighs 1/2^s)."""
+        if type(disparity) not in [tuple, list]:
+            disparity = [disparity]
+        return ops.edge_aware_smooth(list(disparity), tgt_img, normalize=normalize)
+
     # ---- dormant path ----------------------------------------------------
     def compute_photometric_loss(self, pred, target, no_ssim=False):
         """`losses.py:66-84`: 0.85*SSIM + 0.15*L1 per channel, clamped at mean+0.5*std."""

@@ -83,6 +83,27 @@ class SmoothArgs(C.Structure):
     ]
 
 
+class EdgeArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("n_scales", C.c_int32),
+        ("tgt", _fp),
+        ("disp", _fp * MAX_SCALES),
+        ("dh", C.c_int32 * MAX_SCALES),
+        ("dw", C.c_int32 * MAX_SCALES),
+        ("g_disp", _fp * MAX_SCALES),
+        ("g_scratch", _fp * MAX_SCALES),
+        ("accumulate", C.c_int32),
+        ("normalize", C.c_int32),
+        ("want_grad", C.c_int32),
+        ("reserved", C.c_int32),
+        ("loss", _fp),
+        ("upstream", _fp),
+        ("workspace", _fp),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class WarpArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
@@ -147,6 +168,8 @@ SYMBOLS = {
     "plb_photo_loss": (C.c_int, [C.POINTER(PhotoArgs), C.c_void_p]),
     "plb_smooth_workspace_bytes": (C.c_size_t, [C.POINTER(SmoothArgs)]),
     "plb_smooth_loss": (C.c_int, [C.POINTER(SmoothArgs), C.c_void_p]),
+    "plb_edge_smooth_workspace_bytes": (C.c_size_t, [C.POINTER(EdgeArgs)]),
+    "plb_edge_smooth_loss": (C.c_int, [C.POINTER(EdgeArgs), C.c_void_p]),
     "plb_warp_workspace_bytes": (C.c_size_t, [C.POINTER(WarpArgs)]),
     "plb_warp_forward": (C.c_int, [C.POINTER(WarpArgs), C.c_void_p]),
     "plb_warp_backward": (C.c_int, [C.POINTER(WarpArgs), C.c_void_p]),

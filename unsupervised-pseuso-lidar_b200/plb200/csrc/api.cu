@@ -18,6 +18,8 @@ int pose_matrix_launch(const float*, int, int, int, int, float*, cudaStream_t);
 int pose_matrix_bwd_launch(const float*, int, int, int, int, const float*, float*, cudaStream_t);
 int disp_to_depth_launch(const float*, int64_t, float, float, float*, cudaStream_t);
 int disp_to_depth_bwd_launch(const float*, const float*, int64_t, float, float, float*, cudaStream_t);
+int edge_launch(const plb_edge_args*, cudaStream_t);
+size_t edge_workspace_bytes(const plb_edge_args*);
 int photomap_launch(const plb_photomap_args*, cudaStream_t);
 int photomap_bwd_launch(const plb_photomap_args*, cudaStream_t);
 size_t photomap_workspace_bytes(const plb_photomap_args*);
@@ -32,6 +34,9 @@ int plb_photo_loss(const plb_photo_args* a, void* stream) { return plb::photo_l1
 
 size_t plb_smooth_workspace_bytes(const plb_smooth_args* a) { return a ? plb::smooth_workspace_bytes(a) : 0; }
 int plb_smooth_loss(const plb_smooth_args* a, void* stream) { return plb::smooth_launch(a, (cudaStream_t)stream); }
+
+size_t plb_edge_smooth_workspace_bytes(const plb_edge_args* a) { return a ? plb::edge_workspace_bytes(a) : 0; }
+int plb_edge_smooth_loss(const plb_edge_args* a, void* stream) { return plb::edge_launch(a, (cudaStream_t)stream); }
 
 size_t plb_warp_workspace_bytes(const plb_warp_args* a) { return a ? plb::warp_workspace_bytes(a) : 0; }
 int plb_warp_forward(const plb_warp_args* a, void* stream) { return plb::warp_forward_launch(a, (cudaStream_t)stream); }

@@ -413,6 +413,58 @@ def photometric_map(pred, target, no_ssim=False, clip=0.5, C1=1e-4, C2=9e-4):
 
 
 # ---------------------------------------------------------------------------
+# edge-aware smoothness (not in the reference; north_star's kernel list)
+# ---------------------------------------------------------------------------
+class EdgeSmoothFn(torch.autograd.Function):
+    """(tgt, normalize, disp_0..disp_{S-1}) -> scalar loss; gradients for the disparities only."""
+
+    @staticmethod
+    def _launch(tgt, disps, normalize, want_grad, g_disp, g_scratch, loss, upstream):
+        a = _lib.EdgeArgs()
+        a.B, _, a.H, a.W = tgt.shape
+        a.n_scales = len(disps)
+        a.tgt = tgt.data_ptr()
+        for s, d in enumerate(disps):
+            a.disp[s] = d.data_ptr()
+            a.dh[s], a.dw[s] = d.shape[-2], d.shape[-1]
+            a.g_disp[s] = _ptr(g_disp[s]) if want_grad else 0
+            a.g_scratch[s] = _ptr(g_scratch[s]) if (want_grad and normalize) else 0
+        a.accumulate, a.normalize, a.want_grad = 0, int(bool(normalize)), int(bool(want_grad))
+        a.loss, a.upstream = loss.data_ptr(), _ptr(upstream)
+        ws = _workspace("edge", lib.plb_edge_smooth_workspace_bytes(a), tgt.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        check(lib.plb_edge_smooth_loss(a, _stream()), "plb_edge_smooth_loss")
+
+    @staticmethod
+    def forward(ctx, tgt, normalize, *disps):
+        _need_cuda(tgt, *disps)
+        if len(disps) < 1 or len(disps) > _lib.MAX_SCALES:
+            raise ValueError("1..%d scales" % _lib.MAX_SCALES)
+        tgt = _f32c(tgt)
+        disps = [_f32c(d) for d in disps]
+        loss = torch.empty((), dtype=torch.float32, device=tgt.device)
+        EdgeSmoothFn._launch(tgt, disps, normalize, False, None, None, loss, None)
+        ctx.normalize = normalize
+        ctx.save_for_backward(tgt, *disps)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        tgt, *disps = ctx.saved_tensors
+        g = g.detach().to(torch.float32).reshape(()).contiguous()
+        g_disp = [torch.empty_like(d) for d in disps]
+        g_scratch = [torch.empty_like(d) for d in disps] if ctx.normalize else None
+        scratch_loss = torch.empty((), dtype=torch.float32, device=tgt.device)
+        EdgeSmoothFn._launch(tgt, disps, ctx.normalize, True, g_disp, g_scratch, scratch_loss, g)
+        return (None, None) + tuple(g_disp)
+
+
+def edge_aware_smooth(disps, tgt, normalize=True):
+    """Edge-aware smoothness over a disparity pyramid ([B,1,H/2^s,W/2^s]) against the target image."""
+    return EdgeSmoothFn.apply(tgt, bool(normalize), *disps)
+
+
+# ---------------------------------------------------------------------------
 # pseudo-LiDAR
 # ---------------------------------------------------------------------------
 def cloud_project(depth, P, Tinv, sparsity=0, want_f64=True, want_f32=False, want_index=False, want_valid=False):
