@@ -310,6 +310,10 @@ def run_ours(args, cfg):
             except ValueError:
                 pass
         cpu = cpu_reference_run(cfg, 6, 1) if (world == 1 and not args.no_cpu) else None
+        cloud = None
+        if world == 1 and not args.no_cloud:
+            cloud = time_cloud(dev)
+            cloud["frac"] = cloud["achieved_gbs"] / peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -327,6 +331,7 @@ def run_ours(args, cfg):
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "cloud": cloud,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -380,6 +385,35 @@ def time_photo_kernel(criterion, gpu_sets, cfg, dev, iters):
     return e0.elapsed_time(e1) / (reps * per_graph)
 
 
+def time_cloud(dev, B=32, H=375, W=1242, iters=20):
+    """Config C4 (BASELINE.json configs[3]): depth -> pseudo-LiDAR back-projection, fp64 parity layout.
+    Returns Mpix/s, kept points, and the HBM fraction on the algorithmic bytes of SURVEY.md section 8(d):
+    4 B/px read + 32 B per kept point."""
+    import tempfile
+    from plb200 import synth
+    from utils.PseudoLiDAR import PseudoLiDAR
+    with tempfile.TemporaryDirectory() as d:
+        pl = PseudoLiDAR(synth.write_kitti_calib(d), 0, device=dev)
+    sets = [synth.make_depth_images(B, H, W, seed=40 + k).to(dev) for k in range(3)]   # 3 x 60 MB in, 3 x 477 MB out > L2
+    outs = [pl.project_batch(s) for s in sets]
+    torch.cuda.synchronize()
+    kept = int(outs[0]["count"].sum())
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    del outs
+    e0.record(st)
+    for i in range(iters):
+        pl.project_batch(sets[i % len(sets)])
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    px = B * H * W
+    abytes = 4.0 * px + 32.0 * kept
+    return {"workload": "c4: %dx%d depth -> pseudo-LiDAR, batch %d, f64 x,y,z,0 parity layout" % (H, W, B),
+            "ms": ms, "mpix_s": px / 1e6 / (ms / 1e3), "kept_points": kept, "algorithmic_bytes": abytes,
+            "achieved_gbs": abytes / (ms / 1e3) / 1e9}
+
+
 def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier):
     """Public API with HOST buffers: pinned inputs copied H2D every step, loss read D2H."""
     from plb200 import synth
@@ -422,6 +456,7 @@ def main():
     ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated between steps (L2 defeat)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cloud", action="store_true", help="skip the secondary pseudo-LiDAR (config C4) timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = WORKLOADS[args.workload]
