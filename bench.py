@@ -33,14 +33,18 @@ WORKLOADS = {
     "c3": dict(B=8, H=320, W=1024, n_src=3, n_scales=4, variant="live"),
     "c5": dict(B=64, H=192, W=640, n_src=2, n_scales=4, variant="live"),
     "headline": dict(B=12, H=192, W=640, n_src=2, n_scales=1, variant="dir0"),
+    # BASELINE.json configs[1] read literally: the dormant SSIM + per-pixel min-reprojection + automask
+    # composition (losses.py:12-84,94-96,154-162) at 4 scales, one direction
+    "c2min": dict(B=12, H=192, W=640, n_src=2, n_scales=4, variant="min"),
 }
 
 
 def workload_name(wl, cfg):
     return "%s: %dx%d batch %d/GPU, 1 target + %d source frames, %d-scale %s loss fwd+bwd" % (
         wl, cfg["H"], cfg["W"], cfg["B"], cfg["n_src"], cfg["n_scales"],
-        {"live": "reference-live (2 directions, L1 mean + 2nd-order smoothness)",
-         "dir0": "single-direction L1"}[cfg["variant"]])
+        {"live": "reference-live Losses.forward (mode='min', which the reference computes as a MEAN over sources, losses.py:226-228; 2 directions, L1 + 2nd-order smoothness)",
+         "dir0": "single-direction L1",
+         "min": "single-direction SSIM+L1 min-reprojection + automask (dormant path)"}[cfg["variant"]])
 
 
 def algorithmic_bytes_per_px(cfg):
@@ -53,7 +57,7 @@ def algorithmic_bytes_per_px(cfg):
     total = direction(cfg["n_src"])
     if cfg["variant"] == "live":
         total += direction(1)
-    return total
+    return total   # "min": same streams as one direction (the automask re-reads the sources it already holds)
 
 
 class ClockSampler:
@@ -136,6 +140,10 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=25.0):
         if cfg["variant"] == "live":
             loss = O.losses_forward(inp["tgt"], inp["ref_imgs"], disp, poses, inp["intrinsics"])
             sum(loss).backward()
+        elif cfg["variant"] == "min":
+            depths = O.disp_to_depth(disp)
+            loss = O.min_reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[0], poses, inp["intrinsics"])
+            loss.backward()
         else:
             depths = O.disp_to_depth(disp)
             loss = O.reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[:1], poses, inp["intrinsics"])
@@ -202,6 +210,11 @@ def step_fn(criterion, g, cfg):
     if cfg["variant"] == "live":
         loss = criterion.forward(g["tgt"], g["ref_imgs"], disp, poses, g["intrinsics"], None)
         total = loss[0] + loss[1]
+    elif cfg["variant"] == "min":
+        from plb200 import ops, _lib
+        mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp[:1], poses, g["intrinsics"], do_smooth=False,
+                                  mode=_lib.PHOTO_MIN_REPROJ)
+        total = mam
     else:
         from plb200 import ops
         mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp[:1], poses, g["intrinsics"], do_smooth=False)
@@ -310,6 +323,21 @@ def run_ours(args, cfg):
             except ValueError:
                 pass
         cpu = cpu_reference_run(cfg, 6, 1) if (world == 1 and not args.no_cpu) else None
+        others = None
+        if world == 1 and not args.no_cloud:
+            # the other photometric compositions on the same frames (kernel-only, same method as `roofline`)
+            others = {}
+            for name in ("headline", "c2min", "c2"):
+                if name == args.workload:
+                    continue
+                ocfg = WORKLOADS[name]
+                osets = [synth.to_device(s_, dev) for s_ in make_sets(ocfg, n_sets, 1234, dev)]
+                oms = time_photo_kernel(criterion, osets, ocfg, dev, 64)
+                ob = algorithmic_bytes_per_px(ocfg) * ocfg["B"] * ocfg["H"] * ocfg["W"]
+                others[name] = {"workload": workload_name(name, ocfg), "kernel_ms": oms,
+                                "mpix_s": ocfg["B"] * ocfg["H"] * ocfg["W"] / 1e6 / (oms / 1e3),
+                                "achieved_gbs": ob / (oms / 1e3) / 1e9, "frac": ob / (oms / 1e3) / 1e9 / peak}
+                del osets
         cloud = None
         if world == 1 and not args.no_cloud:
             cloud = time_cloud(dev)
@@ -332,6 +360,7 @@ def run_ours(args, cfg):
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "cloud": cloud,
+            "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -351,7 +380,9 @@ def time_photo_kernel(criterion, gpu_sets, cfg, dev, iters):
     calls = []
     for g in gpu_sets:
         pyr = g["disparity"] if cfg["variant"] == "live" else g["disparity"][:1]
-        lcfg = ops.LossConfig(cfg["n_src"], [len(p) for p in pyr], do_smooth=False)
+        from plb200 import _lib
+        lcfg = ops.LossConfig(cfg["n_src"], [len(p) for p in pyr], do_smooth=False,
+                              mode=_lib.PHOTO_MIN_REPROJ if cfg["variant"] == "min" else _lib.PHOTO_L1_MEAN)
         g_pyr = [[torch.empty_like(d) for d in p] for p in pyr]
         g_poses = torch.zeros_like(g["poses"])
         out = torch.zeros(2, device=dev)
