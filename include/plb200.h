@@ -259,7 +259,7 @@ typedef struct plb_cloud_args {
     int32_t* index;            /* out [B, H*W] row-major pixel index of each kept point, or NULL   */
     uint8_t* valid;            /* out [B, H*W] mask (cloud_x>=0 & cloud_z<1) before decimation, or NULL */
     int32_t* count;            /* out [B] number of points written per image                       */
-    void* workspace;           /* plb_cloud_workspace_bytes() bytes, zero-filled once              */
+    void* workspace;           /* plb_cloud_workspace_bytes() bytes (no initialisation needed)     */
     size_t workspace_bytes;
 } plb_cloud_args;
 

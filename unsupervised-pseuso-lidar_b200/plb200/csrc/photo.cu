@@ -755,14 +755,23 @@ extern "C" int plb_debug_block_sms(unsigned int* out2048) {
 // g_disp[s][b,j,i] = dD/dd * sum over the full-resolution pixels whose align_corners=False
 // footprint touches low-res pixel (j,i).  Separable and streaming: one block owns UT_ROWS
 // consecutive low-res rows of one image and a chunk of UT_CHUNK full-res columns (+ halo).
-// Stage 1: every thread walks DOWN one full-res column of the scratch plane once (coalesced,
-// independent loads) and adds each value into the (at most two) low-res rows it feeds; stage 2:
-// every low-res pixel gathers its ~2f column sums from shared memory with the exact up_coord
-// weights.  The launch is a compact list of (job, scale, image, row group, chunk) work items.
+// Stage 1: every thread walks DOWN one full-res column of the scratch plane ONCE (coalesced,
+// four loads in flight) and adds each value into the two low-res rows it feeds - two sliding
+// accumulators, emitted to shared memory when the low-res row index advances (it is monotone);
+// the per-row weights come from a shared table built with the exact up_coord rule.  Stage 2: every
+// low-res pixel gathers the ~2f column sums of its footprint from shared memory.  The launch is a
+// compact list of (job, scale, image, row group, chunk) work items.
 constexpr int UT_THREADS = 256;
 constexpr int UT_CHUNK = 192;   // full-res columns owned per block (a multiple of every factor <= 64)
 constexpr int UT_HALO = 32;     // >= 1.5 * factor + 2 for factor <= 16
-constexpr int UT_ROWS = 8;      // low-res rows per block
+#ifndef UT_ROWS_DEF
+#define UT_ROWS_DEF 8
+#endif
+#ifndef UT_UNROLL
+#define UT_UNROLL 8
+#endif
+constexpr int UT_ROWS = UT_ROWS_DEF;     // low-res rows per block (8 rows / 8 loads in flight: best of the B200 sweep)
+constexpr int UT_WIN = UT_ROWS * 16 + 2 * 16 + 8;   // full-res rows feeding UT_ROWS low-res rows at factor <= 16
 
 struct UpTItem { int jb, s, first_block, groups, chunks; };
 struct UpTLaunch {
@@ -791,54 +800,72 @@ photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_cons
     const float sx = (float)dw / (float)W, sy = (float)dh / (float)H;
     const float fy = (float)H / (float)dh, fx = (float)W / (float)dw;
 
-    constexpr int CW = UT_CHUNK + 2 * UT_HALO;   // 256 columns staged per block
+    constexpr int CW = UT_CHUNK + 2 * UT_HALO;   // 256 columns staged per block, one per thread
+    static_assert(CW == UT_THREADS, "one staged column per thread");
     __shared__ float s_col[UT_ROWS][CW];
     __shared__ float s_l0[CW], s_l1[CW];
     __shared__ int s_x0[CW];
-    constexpr int UT_TAPS = 40;                  // >= 2*16 + 5 full-res rows feed one low-res row
-    __shared__ float s_wr[UT_ROWS][UT_TAPS];     // per local low-res row: weights of its full-res rows
-    __shared__ int s_ybeg[UT_ROWS], s_ycnt[UT_ROWS];
+    __shared__ float4 s_tab[UT_WIN];             // per full-res row: weight to row y0, weight to row y0 + 1, y0
 
     const float* gup = (const float*)((const char*)a.workspace + p.L.gup);
     const float* g = gup + ((size_t)(jb * PLB_MAX_SCALES + s) * a.B + b) * (size_t)H * W;
-    // per low-res row j: conservative full-res window, exact up_coord weights (zero outside the footprint)
-    for (int q = tid; q < UT_ROWS * UT_TAPS; q += UT_THREADS) {
-        const int r = q / UT_TAPS, k = q - r * UT_TAPS;
-        const int j = j0 + r;
-        const int ylo = max((int)floorf(((float)j - 0.5f) * fy - 0.5f) - 1, 0);
-        const int yhi = min((int)ceilf(((float)j + 1.5f) * fy - 0.5f) + 1, H - 1);
-        float wgt = 0.0f;
-        if (j < j1 && ylo + k <= yhi) {
-            int y0, y1; float ly0, ly1;
-            up_coord(ylo + k, sy, dh, y0, y1, ly0, ly1);
-            wgt = (y0 == j ? ly0 : 0.0f) + (y1 == j ? ly1 : 0.0f);
-        }
-        s_wr[r][k] = wgt;
-        if (k == 0) { s_ybeg[r] = ylo; s_ycnt[r] = (j < j1) ? min(yhi - ylo + 1, UT_TAPS) : 0; }
+    // conservative full-res row window of the block; exact up_coord weights (zero outside the footprint)
+    const int ylo = max((int)floorf(((float)j0 - 0.5f) * fy - 0.5f) - 1, 0);
+    const int yhi = min((int)ceilf(((float)(j1 - 1) + 1.5f) * fy - 0.5f) + 1, H - 1);
+    const int nwin = min(yhi - ylo + 1, UT_WIN);
+    for (int t = tid; t < nwin; t += UT_THREADS) {
+        int y0, y1; float ly0, ly1;
+        up_coord(ylo + t, sy, dh, y0, y1, ly0, ly1);
+        if (y1 == y0) { ly0 += ly1; ly1 = 0.0f; }      // clamped at the bottom border: both taps are y0
+        s_tab[t] = make_float4(ly0, ly1, __int_as_float(y0), 0.0f);
     }
-    __syncthreads();
+    for (int q = tid; q < UT_ROWS * CW; q += UT_THREADS) (&s_col[0][0])[q] = 0.0f;
     {
-        const int k = tid;             // CW == UT_THREADS: one staged column per thread
+        const int k = tid;
         const int x = xc0 - UT_HALO + k;
         float l0 = 0.0f, l1 = 0.0f;
         int x0 = -1000000;
-        const bool xin = x >= 0 && x < W;
-        if (xin) {
+        if (x >= 0 && x < W) {
             int x1;
             up_coord(x, sx, dw, x0, x1, l0, l1);
             if (x1 == x0) { l0 += l1; l1 = 0.0f; }   // clamped at the right border: both taps are x0
         }
         s_x0[k] = x0; s_l0[k] = l0; s_l1[k] = l1;
+    }
+    __syncthreads();
+    {
+        const int k = tid;
+        const int x = xc0 - UT_HALO + k;
+        if (x >= 0 && x < W) {
+            const float* gx = g + ((size_t)ylo * W + x);
+            int jcur = __float_as_int(s_tab[0].z);    // a_lo belongs to low-res row jcur, a_hi to jcur + 1
+            float a_lo = 0.0f, a_hi = 0.0f;
+            auto emit = [&](int j, float v) { if (j >= j0 && j < j1) s_col[j - j0][k] = v; };
+            int t = 0;
 #pragma unroll 1
-        for (int r = 0; r < UT_ROWS; ++r) {
-            float acc = 0.0f;
-            if (xin) {
-                const float* gx = g + (s_ybeg[r] * W + x);
-                const int cnt = s_ycnt[r];
-#pragma unroll 4
-                for (int t = 0; t < cnt; ++t) acc = fmaf(s_wr[r][t], __ldg(gx + t * W), acc);
+            for (; t + UT_UNROLL <= nwin; t += UT_UNROLL) {
+                float v[UT_UNROLL];
+#pragma unroll
+                for (int q = 0; q < UT_UNROLL; ++q) v[q] = __ldg(gx + (size_t)(t + q) * W);
+#pragma unroll
+                for (int q = 0; q < UT_UNROLL; ++q) {
+                    const float4 e = s_tab[t + q];
+                    const int y0 = __float_as_int(e.z);
+                    if (y0 > jcur) { emit(jcur, a_lo); a_lo = a_hi; a_hi = 0.0f; ++jcur; }   // y0 advances by <= 1 per row
+                    a_lo = fmaf(e.x, v[q], a_lo);
+                    a_hi = fmaf(e.y, v[q], a_hi);
+                }
             }
-            s_col[r][k] = acc;
+            for (; t < nwin; ++t) {
+                const float4 e = s_tab[t];
+                const int y0 = __float_as_int(e.z);
+                if (y0 > jcur) { emit(jcur, a_lo); a_lo = a_hi; a_hi = 0.0f; ++jcur; }
+                const float v = __ldg(gx + (size_t)t * W);
+                a_lo = fmaf(e.x, v, a_lo);
+                a_hi = fmaf(e.y, v, a_hi);
+            }
+            emit(jcur, a_lo);
+            emit(jcur + 1, a_hi);
         }
     }
     __syncthreads();
