@@ -100,19 +100,28 @@ __device__ __forceinline__ void load_p3(const PairConst& pc, int i0, int r, floa
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w.x), "=f"(w.y) : "r"(a));
 }
 
-template <bool GRAD, bool IMG_GRAD, int NS>
-__device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int plane, int H, int W, float xf, float yf,
-                                            float D, const float (&t)[3], float w_e, bool valid, bool pf,
-                                            typename Vec<NS>::T (&acc)[9], float& l1acc, float& gp, float (&gt)[3]) {
+// coordinates of one group of sources at one depth (stage A output)
+template <int NS>
+struct GState {
+    typename Vec<NS>::T inv, px, py, fx, fy;
+    int x0[NS], y0[NS];
+    bool all_in;
+};
+
+// stage A: project the pixel into every source of the group
+template <int NS>
+__device__ __forceinline__ void group_project(const PairConst& pc, int i0, int H, int W, float xf, float yf, float D,
+                                              GState<NS>& g) {
     typedef typename Vec<NS>::T V;
     V xv, yv, Dv, eps, neg1, two;
     v_bc(xv, xf); v_bc(yv, yf); v_bc(Dv, D); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f); v_bc(two, 2.0f);
-    V p3[3], cam[3];
+    V cam[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         V qx, qy, qz;
-        load_q(pc, i0, r, qx, qy, qz, p3[r]);
-        cam[r] = v_fma(Dv, v_fma(qx, xv, v_fma(qy, yv, qz)), p3[r]);
+        V p3;
+        load_q(pc, i0, r, qx, qy, qz, p3);
+        cam[r] = v_fma(Dv, v_fma(qx, xv, v_fma(qy, yv, qz)), p3);
     }
     const V ze = v_add(cam[2], eps);
     const V nze = v_mul(ze, neg1);
@@ -127,8 +136,6 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
     V px = v_mul(cam[0], inv), py = v_mul(cam[1], inv);
     px = v_fma(v_fma(px, nze, cam[0]), inv, px);             // residual correction: IEEE-accurate quotient
     py = v_fma(v_fma(py, nze, cam[1]), inv, py);
-    V fx, fy;
-    int x0[NS], y0[NS];
     bool all_in = true;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
@@ -136,17 +143,24 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
         const float ixc = fminf(fmaxf(v_get(px, k), -2.0f), (float)(W + 1));
         const float iyc = fminf(fmaxf(v_get(py, k), -2.0f), (float)(H + 1));
         const float xfl = floorf(ixc), yfl = floorf(iyc);
-        x0[k] = (int)xfl; y0[k] = (int)yfl;
-        v_set(fx, k, ixc - xfl); v_set(fy, k, iyc - yfl);
-        all_in = all_in && ((unsigned)x0[k] < (unsigned)(W - 1)) && ((unsigned)y0[k] < (unsigned)(H - 1));
+        g.x0[k] = (int)xfl; g.y0[k] = (int)yfl;
+        v_set(g.fx, k, ixc - xfl); v_set(g.fy, k, iyc - yfl);
+        all_in = all_in && ((unsigned)g.x0[k] < (unsigned)(W - 1)) && ((unsigned)g.y0[k] < (unsigned)(H - 1));
     }
-    V v[3][4];
-    unsigned msk[NS];
+    g.inv = inv; g.px = px; g.py = py; g.all_in = all_in;
+}
+
+// stage B: issue the 12 x NS tap loads (one warp vote picks unpredicated or predicated loads)
+template <int NS>
+__device__ __forceinline__ void group_load(const PairConst& pc, int i0, int plane, int H, int W, bool valid, bool pf,
+                                           const GState<NS>& g, typename Vec<NS>::T (&v)[3][4], unsigned (&msk)[NS]) {
+    typedef typename Vec<NS>::T V;
+    const bool all_in = g.all_in;
     if (__all_sync(0xffffffffu, all_in || !valid)) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const float* __restrict__ cb = pc.src[i0 + k];
-            const int o00 = (all_in && valid) ? y0[k] * W + x0[k] : 0;
+            const int o00 = (all_in && valid) ? g.y0[k] * W + g.x0[k] : 0;
             const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
             v_set(v[0][0], k, __ldg(cb + o00)); v_set(v[0][1], k, __ldg(cb + o00 + 1));
             v_set(v[0][2], k, __ldg(cb + o01)); v_set(v[0][3], k, __ldg(cb + o01 + 1));
@@ -165,11 +179,11 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const float* __restrict__ cb = pc.src[i0 + k];
-            const bool vx0 = (unsigned)x0[k] < (unsigned)W, vx1 = (unsigned)(x0[k] + 1) < (unsigned)W;
-            const bool vy0 = (unsigned)y0[k] < (unsigned)H, vy1 = (unsigned)(y0[k] + 1) < (unsigned)H;
+            const bool vx0 = (unsigned)g.x0[k] < (unsigned)W, vx1 = (unsigned)(g.x0[k] + 1) < (unsigned)W;
+            const bool vy0 = (unsigned)g.y0[k] < (unsigned)H, vy1 = (unsigned)(g.y0[k] + 1) < (unsigned)H;
             const bool mnw = valid && vx0 && vy0, mne = valid && vx1 && vy0;
             const bool msw = valid && vx0 && vy1, mse = valid && vx1 && vy1;
-            const int o00 = y0[k] * W + x0[k];
+            const int o00 = g.y0[k] * W + g.x0[k];
             const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
             v_set(v[0][0], k, ldg_pred(cb + o00, mnw)); v_set(v[0][1], k, ldg_pred(cb + o00 + 1, mne));
             v_set(v[0][2], k, ldg_pred(cb + o01, msw)); v_set(v[0][3], k, ldg_pred(cb + o01 + 1, mse));
@@ -180,6 +194,17 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
             msk[k] = (mnw ? 1u : 0u) | (mne ? 2u : 0u) | (msw ? 4u : 0u) | (mse ? 8u : 0u);
         }
     }
+}
+
+// stage C: blend, L1, gradient terms
+template <bool GRAD, bool IMG_GRAD, int NS>
+__device__ __forceinline__ void group_blend(const PairConst& pc, int i0, int plane, int W, float yf, float D,
+                                            const float (&t)[3], float w_e, bool valid, const GState<NS>& g,
+                                            const typename Vec<NS>::T (&v)[3][4], const unsigned (&msk)[NS],
+                                            typename Vec<NS>::T (&acc)[9], float& l1acc, float& gp, float (&gt)[3]) {
+    typedef typename Vec<NS>::T V;
+    V yv, Dv, eps, neg1;
+    v_bc(yv, yf); v_bc(Dv, D); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f);
     V Gx, Gy;
     v_bc(Gx, 0.0f); v_bc(Gy, 0.0f);
     float l1 = 0.0f;
@@ -187,9 +212,9 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const V dA = v_sub(v[c][1], v[c][0]), dB = v_sub(v[c][3], v[c][2]);
-        const V top = v_fma(fx, dA, v[c][0]), bot = v_fma(fx, dB, v[c][2]);
+        const V top = v_fma(g.fx, dA, v[c][0]), bot = v_fma(g.fx, dB, v[c][2]);
         const V dV = v_sub(bot, top);
-        const V proj = v_fma(fy, dV, top);
+        const V proj = v_fma(g.fy, dV, top);
         V sg;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -204,19 +229,19 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
             }
         }
         if (GRAD) {
-            Gx = v_fma(sg, v_fma(fy, v_sub(dB, dA), dA), Gx);
+            Gx = v_fma(sg, v_fma(g.fy, v_sub(dB, dA), dA), Gx);
             Gy = v_fma(sg, dV, Gy);
         }
     }
     l1acc += valid ? l1 : 0.0f;
     if (GRAD) {
         V gi;
-        V s = v_fma(Gx, px, v_mul(Gy, py));
+        V s = v_fma(Gx, g.px, v_mul(Gy, g.py));
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
             const bool use = msk[k] != 0u;
             // the selects also keep the inf/NaN of a degenerate z out of the sums
-            v_set(gi, k, use ? w_e * v_get(inv, k) : 0.0f);
+            v_set(gi, k, use ? w_e * v_get(g.inv, k) : 0.0f);
             v_set(s, k, use ? v_get(s, k) : 0.0f);
         }
         const V gcx = v_mul(Gx, gi), gcy = v_mul(Gy, gi);
@@ -242,10 +267,10 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
                 for (int c = 0; c < 3; ++c) gt[c] -= m * e[k][c];
                 float* gbase = pc.g_src[i0 + k];
                 if (gbase != nullptr) {
-                    const float fxk = v_get(fx, k), fyk = v_get(fy, k);
+                    const float fxk = v_get(g.fx, k), fyk = v_get(g.fy, k);
                     const float wnw = (1.0f - fxk) * (1.0f - fyk), wne = fxk * (1.0f - fyk);
                     const float wsw = (1.0f - fxk) * fyk, wse = fxk * fyk;
-                    const int og = y0[k] * W + x0[k];
+                    const int og = g.y0[k] * W + g.x0[k];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float ec = m * e[k][c];
@@ -259,6 +284,19 @@ __device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int pla
             }
         }
     }
+}
+
+
+template <bool GRAD, bool IMG_GRAD, int NS>
+__device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int plane, int H, int W, float xf, float yf,
+                                            float D, const float (&t)[3], float w_e, bool valid, bool pf,
+                                            typename Vec<NS>::T (&acc)[9], float& l1acc, float& gp, float (&gt)[3]) {
+    GState<NS> g;
+    typename Vec<NS>::T v[3][4];
+    unsigned msk[NS];
+    group_project<NS>(pc, i0, H, W, xf, yf, D, g);
+    group_load<NS>(pc, i0, plane, H, W, valid, pf, g, v, msk);
+    group_blend<GRAD, IMG_GRAD, NS>(pc, i0, plane, W, yf, D, t, w_e, valid, g, v, msk, acc, l1acc, gp, gt);
 }
 
 // Per-lane accumulators of one group -> this warp's shared record (ACCUMULATED in place).
