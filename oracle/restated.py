@@ -105,7 +105,9 @@ def pose_vec2mat(vec, mode="euler"):
         return vec
     if mode != "euler":
         raise ValueError("Rotation mode not supported {}".format(mode))
-    return torch.cat([euler2mat(vec[:, :3]), vec[:, 3:].unsqueeze(-1)], dim=2).float()
+    M = torch.cat([euler2mat(vec[:, :3]), vec[:, 3:].unsqueeze(-1)], dim=2)
+    # `.float()` in the reference; fp64 input (the accuracy study in the tests) stays fp64
+    return M if vec.dtype == torch.float64 else M.float()
 
 
 # --------------------------------------------------------------------------
