@@ -338,10 +338,12 @@ def run_ours(args, cfg):
                                 "mpix_s": ocfg["B"] * ocfg["H"] * ocfg["W"] / 1e6 / (oms / 1e3),
                                 "achieved_gbs": ob / (oms / 1e3) / 1e9, "frac": ob / (oms / 1e3) / 1e9 / peak}
                 del osets
-        cloud = None
+        cloud = velo = None
         if world == 1 and not args.no_cloud:
             cloud = time_cloud(dev)
             cloud["frac"] = cloud["achieved_gbs"] / peak
+            velo = time_velo(dev)
+            velo["frac"] = velo["achieved_gbs"] / peak
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -360,6 +362,7 @@ def run_ours(args, cfg):
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "cloud": cloud,
+            "velo": velo,
             "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
@@ -443,6 +446,32 @@ def time_cloud(dev, B=32, H=375, W=1242, iters=20):
     return {"workload": "c4: %dx%d depth -> pseudo-LiDAR, batch %d, f64 x,y,z,0 parity layout" % (H, W, B),
             "ms": ms, "mpix_s": px / 1e6 / (ms / 1e3), "kept_points": kept, "algorithmic_bytes": abytes,
             "achieved_gbs": abytes / (ms / 1e3) / 1e9}
+
+
+def time_velo(dev, B=32, N=123577, H=375, W=1242, iters=20):
+    """Velodyne sweep -> sparse depth image (Transform.py:69-104), B sweeps of one
+    KITTI frame's point count.  Algorithmic bytes: 16 B per point read + 8 B per cell written (fp64 image)."""
+    import tempfile
+    import numpy as np
+    from plb200 import synth
+    from Transform.Transform import Transform
+    with tempfile.TemporaryDirectory() as d:
+        tr = Transform(synth.write_kitti_calib(d), W, H, device=dev)
+    one = [torch.from_numpy(synth.make_velodyne_cloud(N, seed=60 + k)) for k in range(4)]
+    sets = [torch.stack([one[(k + j) % 4] for j in range(B)]).to(dev) for k in range(3)]
+    tr.project_batch(sets[0])
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(iters):
+        tr.project_batch(sets[i % len(sets)])
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    abytes = 16.0 * B * N + 8.0 * B * H * W
+    return {"workload": "velodyne -> image: %d sweeps x %d points -> %dx%d f64 depth" % (B, N, H, W), "ms": ms,
+            "mpoints_s": B * N / 1e6 / (ms / 1e3), "algorithmic_bytes": abytes, "achieved_gbs": abytes / (ms / 1e3) / 1e9}
 
 
 def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier):

@@ -266,6 +266,32 @@ typedef struct plb_cloud_args {
 size_t plb_cloud_workspace_bytes(const plb_cloud_args* args);
 int plb_cloud_project(const plb_cloud_args* args, void* stream);
 
+/*
+ * Velodyne sweep -> sparse depth image: the inverse of plb_cloud_project.
+ * Replaces Transform.project_velo_to_img (pseudo-lidar/Transform/Transform.py:69-104): per point
+ * dist = sqrt(x^2+y^2+z^2) in fp32, xyz = T.[x y z 1], uv = P.xyz in fp64 (the rounding order of the
+ * per-point np.matmul), uv /= uv[2]; kept when 0 <= u < W, 0 <= v < H, dist <= 120, x > 0; the cell
+ * (int(v), int(u)) takes xyz[2] of the LAST kept point in sweep order (largest index), 0 elsewhere.
+ */
+typedef struct plb_velo_args {
+    int32_t B, N;              /* B sweeps of up to N points each                                   */
+    int32_t H, W;              /* image height (Transform.height) and width (Transform.width)       */
+    int32_t point_stride;      /* floats per point: 4 = KITTI .bin x,y,z,reflectance (16-byte aligned), >= 3 */
+    int32_t reserved;
+    const float* points;       /* [B, N, point_stride] f32                                          */
+    const int32_t* counts;     /* [B] points used per sweep (<= N), or NULL = N everywhere          */
+    double T[16];              /* velodyne->camera 4x4 row-major, last row 0 0 0 1 (Transform.py:61-62) */
+    double P[12];              /* camera->image 3x4 row-major (Transform.py:65)                     */
+    double* depth_f64;         /* out [B,H,W] f64 (parity layout) or NULL                           */
+    float* depth_f32;          /* out [B,H,W] f32 or NULL (at least one of the two)                 */
+    int32_t* winner;           /* out [B,H,W] index of the point that owns the cell, -1 = empty, or NULL */
+    void* workspace;           /* plb_velo_workspace_bytes() bytes, zero-filled once (self-cleaning) */
+    size_t workspace_bytes;
+} plb_velo_args;
+
+size_t plb_velo_workspace_bytes(const plb_velo_args* args);
+int plb_velo_project(const plb_velo_args* args, void* stream);
+
 /* Library identification: "plb200 <version> sm_100a". */
 const char* plb_version(void);
 /* Number of kernel launches issued by this library since load (all entry points). */

@@ -73,3 +73,18 @@ def quiet():
     """The reference prints inside the loss (`losses.py:191`)."""
     with contextlib.redirect_stdout(io.StringIO()):
         yield
+
+
+def load_velo_transform():
+    """The reference's `pseudo-lidar/Transform/Transform.py::Transform` (Velodyne -> image depth map),
+    imported unmodified by file path (the directory name has a hyphen)."""
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    spec = importlib.util.spec_from_file_location(
+        "ref_velo_transform", os.path.join(REFERENCE_ROOT, "pseudo-lidar", "Transform", "Transform.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.Transform

@@ -362,3 +362,42 @@ def velo_to_cam_matrix(R, t):
     T = np.concatenate((np.asarray(R, dtype=np.float64).reshape(3, 3),
                         np.asarray(t, dtype=np.float64).reshape(3, 1)), axis=1)
     return np.vstack([T, [0, 0, 0, 1]])
+
+
+# --------------------------------------------------------------------------
+# pseudo-lidar/Transform/Transform.py  (SURVEY.md section 8(f) rank 2: the inverse of project_PL)
+# --------------------------------------------------------------------------
+
+def _matvec4_like_numpy(M, v):
+    """[N,4] vectors through a [R,4] matrix with the rounding order of the per-point `np.matmul(M, pnt)`
+    the reference runs (a 4-wide SIMD product followed by the horizontal add (p0 + p2) + (p1 + p3));
+    found by matching candidates against the unmodified reference's output bit for bit, and held to it
+    by tests/golden/velo_kitti.npz."""
+    p = v[:, None, :] * M[None, :, :]                       # [N,R,4] rounded products
+    return (p[..., 0] + p[..., 2]) + (p[..., 1] + p[..., 3])
+
+
+def project_velo_to_img(point_cloud, T, P, width, height):
+    """`pseudo-lidar/Transform/Transform.py:69-104`: Velodyne points [N,>=3] (float32 as read from a KITTI
+    .bin) -> depth image [height, width] float64.  Per point, in order: dist = sqrt(x^2+y^2+z^2) in the
+    cloud's dtype; xyz = T @ [x,y,z,1] and uv = P @ xyz in fp64 (vstack with the int 1 promotes to
+    float64); uv /= uv[2]; kept when 0 <= u < width, 0 <= v < height, dist <= 120, x > 0; the cell
+    (int(u), int(v)) takes xyz[2] and LATER POINTS OVERWRITE EARLIER ONES.  Vectorised: the winner of a
+    cell is the kept point with the largest index.  Returns (depth [height,width], winner index map)."""
+    pc = np.asarray(point_cloud)[:, :3]
+    x, y, z = pc[:, 0], pc[:, 1], pc[:, 2]
+    dist = np.sqrt(x ** 2 + y ** 2 + z ** 2)
+    hom = np.concatenate([pc.astype(np.float64), np.ones((pc.shape[0], 1))], axis=1)
+    xyz = _matvec4_like_numpy(np.asarray(T, dtype=np.float64), hom)          # [N,4]
+    uvw = _matvec4_like_numpy(np.asarray(P, dtype=np.float64), xyz)          # [N,3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u, v = uvw[:, 0] / uvw[:, 2], uvw[:, 1] / uvw[:, 2]
+        keep = (u >= 0) & (u < width) & (v >= 0) & (v < height) & (dist <= 120) & (x > 0)
+    idx = np.nonzero(keep)[0]
+    cell = u[idx].astype(np.int64) * height + v[idx].astype(np.int64)      # depth_array[int(u)][int(v)]
+    winner = np.full(width * height, -1, dtype=np.int64)
+    np.maximum.at(winner, cell, idx)
+    depth = np.zeros(width * height, dtype=np.float64)
+    has = winner >= 0
+    depth[has] = xyz[winner[has], 2]
+    return np.transpose(depth.reshape(width, height)), winner.reshape(width, height).T

@@ -181,6 +181,36 @@ def cloud_case(ref, name):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+def velo_case(ref_unused, name):
+    """`Transform.project_velo_to_img` (pseudo-lidar/Transform/Transform.py:69-104, the unmodified class) on a
+    small sweep projected into a 124x37 image (P scaled by 0.1: many cells hit several times, so the
+    later-point-wins rule is exercised; inputs and full output stored) and on one KITTI-sized sweep into
+    1242x375 (regenerated from the seed; count, checksum and the non-zero cells stored)."""
+    Transform = reference_shim.load_velo_transform()
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        calib = synth.write_kitti_calib(d)
+        tr = Transform(calib, 124, 37)
+        tr.P = tr.P * np.array([[0.1], [0.1], [1.0]])
+        small = synth.make_velodyne_cloud(3000, seed=91)
+        small[7] = [np.nan, 1.0, 1.0, 0.0]          # NaN fails every test
+        small[8] = [0.0, 0.0, 0.0, 0.0]             # x > 0 fails; also uv/0
+        small[9] = [150.0, 0.5, -1.0, 0.0]          # beyond the 120 m cut
+        out["small_points"] = small
+        out["small_P"], out["T"] = tr.P.copy(), tr.T.copy()
+        out["small_depth"] = tr.project_velo_to_img(small)
+        tr = Transform(calib, 1242, 375)
+        out["P"] = tr.P.copy()
+        full = synth.make_velodyne_cloud(123577, seed=92)
+        depth = tr.project_velo_to_img(full)
+        out["full_seed"], out["full_n"] = np.array(92), np.array(123577)
+        nz = np.flatnonzero(depth)
+        out["full_nz_index"], out["full_nz_value"] = nz.astype(np.int32), depth.reshape(-1)[nz]
+        out["full_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(depth).tobytes()).digest(), dtype=np.uint8)
+        print(name, out["small_depth"].shape, int((out["small_depth"] != 0).sum()), depth.shape, nz.size, depth.dtype)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)  # fixed reduction order for the committed vectors
@@ -191,6 +221,7 @@ def main():
     warp_case(ref, "warp_b4_24x40", 4, 24, 40, seed=21)
     dormant_case(ref, "dormant_b4_s2_32x48", 4, 32, 48, 2, seed=31)
     cloud_case(ref, "cloud_kitti")
+    velo_case(ref, "velo_kitti")
     ref = reference_shim.load(patch_batch=True)
     live_case(ref, "live_b2_s2_32x48_patched", 2, 32, 48, 2, seed=14, regime="trained")
     live_case(ref, "live_b3_s1_24x40_patched", 3, 24, 40, 1, seed=15, regime="trained")

@@ -35,15 +35,15 @@ def test_struct_sizes_match_header(L):
     src = r'''
     #include <stdio.h>
     #include "plb200.h"
-    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(plb_photo_job), sizeof(plb_photo_args),
-        sizeof(plb_smooth_args), sizeof(plb_warp_args), sizeof(plb_cloud_args)); return 0; }'''
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(plb_photo_job), sizeof(plb_photo_args),
+        sizeof(plb_smooth_args), sizeof(plb_warp_args), sizeof(plb_cloud_args), sizeof(plb_velo_args)); return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    got = [ctypes.sizeof(t) for t in (L.PhotoJob, L.PhotoArgs, L.SmoothArgs, L.WarpArgs, L.CloudArgs)]
+    got = [ctypes.sizeof(t) for t in (L.PhotoJob, L.PhotoArgs, L.SmoothArgs, L.WarpArgs, L.CloudArgs, L.VeloArgs)]
     assert got == sizes, (got, sizes)
 
 
@@ -59,6 +59,10 @@ def test_argument_validation_without_gpu(L):
     assert L.lib.plb_cloud_project(c, None) == -1
     c.B, c.H, c.W = 1, 4, 4
     assert L.lib.plb_cloud_project(c, None) == -2
+    v = L.VeloArgs()
+    assert L.lib.plb_velo_project(v, None) == -1
+    v.B, v.H, v.W, v.N, v.point_stride = 1, 4, 4, 0, 4
+    assert L.lib.plb_velo_project(v, None) == -2         # no output
     w = L.WarpArgs()
     assert L.lib.plb_warp_forward(w, None) == -1
     with pytest.raises(L.PlbError):

@@ -101,6 +101,24 @@ def test_cloud_small_and_full():
     assert O.project_PL(full, T, P, sparsity=10).shape[0] == int(g["full_count_sp10"])
 
 
+def test_velo_projection_bit_exact():
+    """Velodyne -> image (Transform.py:69-104): the vectorised oracle equals the unmodified reference's
+    per-point loop bit for bit, collisions (later point wins) included."""
+    from plb200 import synth
+    g = load_golden("velo_kitti")
+    depth, winner = O.project_velo_to_img(g["small_points"], g["T"], g["small_P"], 124, 37)
+    assert depth.dtype == np.float64 and depth.shape == (37, 124)
+    assert np.array_equal(depth, g["small_depth"])
+    kept = O.project_velo_to_img(g["small_points"], g["T"], g["small_P"], 124, 37)[1]
+    assert (kept >= 0).sum() == (g["small_depth"] != 0).sum()
+    full = synth.make_velodyne_cloud(int(g["full_n"]), seed=int(g["full_seed"]))
+    depth, _ = O.project_velo_to_img(full, g["T"], g["P"], 1242, 375)
+    digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(depth).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, g["full_sha256"])
+    nz = np.flatnonzero(depth)
+    assert np.array_equal(nz, g["full_nz_index"]) and np.array_equal(depth.reshape(-1)[nz], g["full_nz_value"])
+
+
 def test_live_reference_if_present():
     """When the reference tree is mounted (build container), run it live against
     the oracle at B=4 once more - guards against a stale fixture."""

@@ -162,6 +162,22 @@ class CloudArgs(C.Structure):
     ]
 
 
+class VeloArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("point_stride", C.c_int32), ("reserved", C.c_int32),
+        ("points", _fp),
+        ("counts", _fp),
+        ("T", C.c_double * 16),
+        ("P", C.c_double * 12),
+        ("depth_f64", _fp),
+        ("depth_f32", _fp),
+        ("winner", _fp),
+        ("workspace", _fp),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # every symbol include/plb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "plb_photo_workspace_bytes": (C.c_size_t, [C.POINTER(PhotoArgs)]),
@@ -184,6 +200,8 @@ SYMBOLS = {
     "plb_photometric_map_backward": (C.c_int, [C.POINTER(PhotomapArgs), C.c_void_p]),
     "plb_cloud_workspace_bytes": (C.c_size_t, [C.POINTER(CloudArgs)]),
     "plb_cloud_project": (C.c_int, [C.POINTER(CloudArgs), C.c_void_p]),
+    "plb_velo_workspace_bytes": (C.c_size_t, [C.POINTER(VeloArgs)]),
+    "plb_velo_project": (C.c_int, [C.POINTER(VeloArgs), C.c_void_p]),
     "plb_version": (C.c_char_p, []),
     "plb_launch_count": (C.c_uint64, []),
 }

@@ -25,6 +25,8 @@ int photomap_bwd_launch(const plb_photomap_args*, cudaStream_t);
 size_t photomap_workspace_bytes(const plb_photomap_args*);
 int cloud_launch(const plb_cloud_args*, cudaStream_t);
 size_t cloud_workspace_bytes(const plb_cloud_args*);
+int velo_launch(const plb_velo_args*, cudaStream_t);
+size_t velo_workspace_bytes(const plb_velo_args*);
 }  // namespace plb
 
 extern "C" {
@@ -74,6 +76,9 @@ int plb_photometric_map_backward(const plb_photomap_args* a, void* stream) {
 
 size_t plb_cloud_workspace_bytes(const plb_cloud_args* a) { return a ? plb::cloud_workspace_bytes(a) : 0; }
 int plb_cloud_project(const plb_cloud_args* a, void* stream) { return plb::cloud_launch(a, (cudaStream_t)stream); }
+
+size_t plb_velo_workspace_bytes(const plb_velo_args* a) { return a ? plb::velo_workspace_bytes(a) : 0; }
+int plb_velo_project(const plb_velo_args* a, void* stream) { return plb::velo_launch(a, (cudaStream_t)stream); }
 
 const char* plb_version(void) { return "plb200 0.1 sm_100a"; }
 uint64_t plb_launch_count(void) { return plb::g_launches; }

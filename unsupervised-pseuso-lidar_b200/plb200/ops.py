@@ -500,6 +500,39 @@ def cloud_project(depth, P, Tinv, sparsity=0, want_f64=True, want_f32=False, wan
     return res
 
 
+def velo_project(points, T, P, height, width, counts=None, want_f64=True, want_f32=False, want_winner=False):
+    """points [B,N,C>=3] f32 CUDA (KITTI .bin rows: x,y,z,reflectance) -> dict(depth_f64 [B,H,W], ...): the
+    sparse depth image of `Transform.project_velo_to_img` (pseudo-lidar/Transform/Transform.py:69-104).  No sync."""
+    _need_cuda(points)
+    points = _f32c(points)
+    B, N, Cs = points.shape
+    dev = points.device
+    a = _lib.VeloArgs()
+    a.B, a.N, a.H, a.W, a.point_stride = B, N, int(height), int(width), Cs
+    a.points = points.data_ptr() if N > 0 else 0
+    if counts is not None:
+        counts = counts.to(dev, torch.int32).contiguous()
+        a.counts = counts.data_ptr()
+    for i, v in enumerate([float(x) for x in T.reshape(-1)]):
+        a.T[i] = v
+    for i, v in enumerate([float(x) for x in P.reshape(-1)]):
+        a.P[i] = v
+    res = {}
+    if want_f64:
+        res["depth_f64"] = torch.empty(B, a.H, a.W, dtype=torch.float64, device=dev)
+        a.depth_f64 = res["depth_f64"].data_ptr()
+    if want_f32:
+        res["depth_f32"] = torch.empty(B, a.H, a.W, dtype=torch.float32, device=dev)
+        a.depth_f32 = res["depth_f32"].data_ptr()
+    if want_winner:
+        res["winner"] = torch.empty(B, a.H, a.W, dtype=torch.int32, device=dev)
+        a.winner = res["winner"].data_ptr()
+    ws = _workspace("velo", lib.plb_velo_workspace_bytes(a), dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    check(lib.plb_velo_project(a, _stream()), "plb_velo_project")
+    return res
+
+
 def smooth_only(depth_maps, input_is_depth=True, fused_backward=True):
     """Losses.smooth_loss on a list of [B,1,h,w] maps (no photometric launch)."""
     d0 = depth_maps[0]

@@ -130,5 +130,22 @@ def write_kitti_calib(calib_dir):
     with open(os.path.join(calib_dir, "calib_cam_to_cam.txt"), "w") as f:
         f.write("calib_time: 09-Jan-2012 13:57:47\n")
         f.write("P_rect_02: " + " ".join("%.6e" % v for v in KITTI_P_RECT_02.reshape(-1)) + "\n")
+        # key read by the Velodyne -> image class (`pseudo-lidar/Transform/Transform.py:66`)
+        f.write("P: " + " ".join("%.6e" % v for v in KITTI_P_RECT_02.reshape(-1)) + "\n")
     d = str(calib_dir)
     return d if d.endswith("/") else d + "/"
+
+
+def make_velodyne_cloud(n=123577, seed=1234):
+    """[n,4] float32 x,y,z,reflectance shaped like one KITTI Velodyne sweep (64 beams, 360 degrees, ranges
+    3..130 m - some beyond the 120 m cut, half of them behind the car), in azimuth-major order as the
+    sensor writes them.  123 577 is the point count the reference quotes for a real frame
+    (`pseudo-lidar/test_pipeline.py:72-73`)."""
+    gen = np.random.default_rng(seed)
+    az = np.sort(gen.uniform(-np.pi, np.pi, n))
+    el = np.deg2rad(gen.uniform(-24.8, 2.0, n))
+    rng = 3.0 + 127.0 * gen.beta(1.2, 4.0, n)
+    x = rng * np.cos(el) * np.cos(az)
+    y = rng * np.cos(el) * np.sin(az)
+    z = rng * np.sin(el)
+    return np.stack([x, y, z, gen.uniform(0, 1, n)], 1).astype(np.float32)
