@@ -791,34 +791,45 @@ extern "C" int plb_debug_block_sms(unsigned int* out2048) {
 
 // Transposed bilinear upsample (gather form, deterministic) + disp->depth chain:
 // g_disp[s][b,j,i] = dD/dd * sum over the full-resolution pixels whose align_corners=False
-// footprint touches low-res pixel (j,i).  Separable and streaming: one block owns UT_ROWS
-// consecutive low-res rows of one image and a chunk of UT_CHUNK full-res columns (+ halo).
-// Stage 1: every thread walks DOWN one full-res column of the scratch plane ONCE (coalesced,
-// four loads in flight) and adds each value into the two low-res rows it feeds - two sliding
-// accumulators, emitted to shared memory when the low-res row index advances (it is monotone);
-// the per-row weights come from a shared table built with the exact up_coord rule.  Stage 2: every
-// low-res pixel gathers the ~2f column sums of its footprint from shared memory.  The launch is a
-// compact list of (job, scale, image, row group, chunk) work items.
-constexpr int UT_THREADS = 256;
-constexpr int UT_CHUNK = 192;   // full-res columns owned per block (a multiple of every factor <= 64)
-constexpr int UT_HALO = 32;     // >= 1.5 * factor + 2 for factor <= 16
-#ifndef UT_ROWS_DEF
-#define UT_ROWS_DEF 8
+// footprint touches low-res pixel (j,i).  Separable and streaming: one block owns `rows`
+// consecutive low-res rows of one image (about UT_SPAN full-res rows) and a chunk of UT_OWN
+// full-res columns (+ halo).
+// Stage 1: every thread walks DOWN four adjacent full-res columns of the scratch plane ONCE (one
+// 128-bit load per row, UT_UNROLL rows in flight) and adds each value into the two low-res rows it
+// feeds - two sliding accumulators per column, emitted to shared memory when the low-res row index
+// advances (it is monotone); the per-row weights come from a shared table built with the exact
+// up_coord rule.  Stage 2: one thread per low-res column gathers the ~2f column sums of its footprint
+// for all rows of the block (the column weights are read once, the row accumulators stay in registers).
+// The launch is a compact list of (job, scale, image, row group, chunk) work items.
+constexpr int UT_THREADS = 192;
+constexpr int UT_CW = UT_THREADS * 4;          // full-res columns staged per block, four per thread
+constexpr int UT_HALO = 32;                    // >= 1.5 * factor + 2 for factor <= 16
+constexpr int UT_OWN = UT_CW - 2 * UT_HALO;    // full-res columns owned per block
+#ifndef UT_MAXROWS_DEF
+#define UT_MAXROWS_DEF 8
+#endif
+constexpr int UT_MAXROWS = UT_MAXROWS_DEF;     // low-res rows per block (stage-2 accumulators)
+#ifndef UT_SPAN
+#define UT_SPAN 48                             // full-res rows walked per block (the per-thread serial chain), halo included
 #endif
 #ifndef UT_UNROLL
 #define UT_UNROLL 8
 #endif
-constexpr int UT_ROWS = UT_ROWS_DEF;     // low-res rows per block (8 rows / 8 loads in flight: best of the B200 sweep)
-constexpr int UT_WIN = UT_ROWS * 16 + 2 * 16 + 8;   // full-res rows feeding UT_ROWS low-res rows at factor <= 16
+constexpr int UT_WIN = (UT_MAXROWS + 1) * 16 + 8;   // full-res rows feeding one block at factor <= 16
 
-struct UpTItem { int jb, s, first_block, groups, chunks; };
+struct UpTItem { int jb, s, first_block, groups, chunks, rows; };
 struct UpTLaunch {
     int n_items;
     int total_blocks;
     UpTItem items[PLB_MAX_JOBS * PLB_MAX_SCALES];
 };
 
-__global__ void __launch_bounds__(UT_THREADS)
+constexpr size_t UT_SMEM = sizeof(float) * ((size_t)UT_MAXROWS * UT_CW + 3 * UT_CW) + sizeof(float4) * UT_WIN;
+
+#ifndef UT_MINBLOCKS
+#define UT_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(UT_THREADS, UT_MINBLOCKS)
 photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_constant__ UpTLaunch u) {
     const plb_photo_args& a = p.a;
     if (skip_launch(a.skip_if_unit)) return;
@@ -832,18 +843,18 @@ photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_cons
     const int jb = item.jb, s = item.s;
     const plb_photo_job& job = a.jobs[jb];
     const int dh = job.dh[s], dw = job.dw[s], H = a.H, W = a.W;
-    const int j0 = grp * UT_ROWS, j1 = min(j0 + UT_ROWS, dh);   // low-res rows [j0, j1)
-    const int xc0 = chunk * UT_CHUNK;
+    const int j0 = grp * item.rows, j1 = min(j0 + item.rows, dh);   // low-res rows [j0, j1)
+    const int xc0 = chunk * UT_OWN;
     const int tid = threadIdx.x;
     const float sx = (float)dw / (float)W, sy = (float)dh / (float)H;
     const float fy = (float)H / (float)dh, fx = (float)W / (float)dw;
 
-    constexpr int CW = UT_CHUNK + 2 * UT_HALO;   // 256 columns staged per block, one per thread
-    static_assert(CW == UT_THREADS, "one staged column per thread");
-    __shared__ float s_col[UT_ROWS][CW];
-    __shared__ float s_l0[CW], s_l1[CW];
-    __shared__ int s_x0[CW];
-    __shared__ float4 s_tab[UT_WIN];             // per full-res row: weight to row y0, weight to row y0 + 1, y0
+    extern __shared__ __align__(16) unsigned char ut_smem[];
+    float4* s_tab = reinterpret_cast<float4*>(ut_smem);        // per full-res row: weight to row y0, to row y0 + 1, y0
+    float* s_col = reinterpret_cast<float*>(s_tab + UT_WIN);   // [UT_MAXROWS][UT_CW] column sums per low-res row
+    float* s_l0 = s_col + UT_MAXROWS * UT_CW;                  // per staged column: weight to x0, to x0 + 1, x0
+    float* s_l1 = s_l0 + UT_CW;
+    int* s_x0 = reinterpret_cast<int*>(s_l1 + UT_CW);
 
     const float* gup = (const float*)((const char*)a.workspace + p.L.gup);
     const float* g = gup + ((size_t)(jb * PLB_MAX_SCALES + s) * a.B + b) * (size_t)H * W;
@@ -857,10 +868,14 @@ photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_cons
         if (y1 == y0) { ly0 += ly1; ly1 = 0.0f; }      // clamped at the bottom border: both taps are y0
         s_tab[t] = make_float4(ly0, ly1, __int_as_float(y0), 0.0f);
     }
-    for (int q = tid; q < UT_ROWS * CW; q += UT_THREADS) (&s_col[0][0])[q] = 0.0f;
     {
-        const int k = tid;
-        const int x = xc0 - UT_HALO + k;
+        float4* z = reinterpret_cast<float4*>(s_col);
+        for (int q = tid; q < (j1 - j0) * (UT_CW / 4); q += UT_THREADS) z[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    const int xq = xc0 - UT_HALO + 4 * tid;            // first of this thread's four columns
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int x = xq + c;
         float l0 = 0.0f, l1 = 0.0f;
         int x0 = -1000000;
         if (x >= 0 && x < W) {
@@ -868,68 +883,86 @@ photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_cons
             up_coord(x, sx, dw, x0, x1, l0, l1);
             if (x1 == x0) { l0 += l1; l1 = 0.0f; }   // clamped at the right border: both taps are x0
         }
-        s_x0[k] = x0; s_l0[k] = l0; s_l1[k] = l1;
+        s_x0[4 * tid + c] = x0; s_l0[4 * tid + c] = l0; s_l1[4 * tid + c] = l1;
     }
     __syncthreads();
-    {
-        const int k = tid;
-        const int x = xc0 - UT_HALO + k;
-        if (x >= 0 && x < W) {
-            const float* gx = g + ((size_t)ylo * W + x);
-            int jcur = __float_as_int(s_tab[0].z);    // a_lo belongs to low-res row jcur, a_hi to jcur + 1
-            float a_lo = 0.0f, a_hi = 0.0f;
-            auto emit = [&](int j, float v) { if (j >= j0 && j < j1) s_col[j - j0][k] = v; };
+    if (xq + 3 >= 0 && xq < W) {
+        const bool vec = ((W & 3) == 0) && xq >= 0 && xq + 3 < W;   // rows are 16-byte aligned when W % 4 == 0
+        const float* row = g + ((size_t)ylo * W + xq);
+        int jcur = __float_as_int(s_tab[0].z);    // a_lo belongs to low-res row jcur, a_hi to jcur + 1
+        float4 a_lo = make_float4(0.0f, 0.0f, 0.0f, 0.0f), a_hi = a_lo;
+        float4* out = reinterpret_cast<float4*>(s_col) + tid;
+        auto emit = [&](int j, const float4& v) { if (j >= j0 && j < j1) out[(j - j0) * (UT_CW / 4)] = v; };
+        auto step = [&](int t, const float4& v) {
+            const float4 e = s_tab[t];
+            const int y0 = __float_as_int(e.z);
+            if (y0 > jcur) {                           // y0 advances by <= 1 per row (block-uniform branch)
+                emit(jcur, a_lo);
+                a_lo = a_hi; a_hi = make_float4(0.0f, 0.0f, 0.0f, 0.0f); ++jcur;
+            }
+            a_lo.x = fmaf(e.x, v.x, a_lo.x); a_lo.y = fmaf(e.x, v.y, a_lo.y);
+            a_lo.z = fmaf(e.x, v.z, a_lo.z); a_lo.w = fmaf(e.x, v.w, a_lo.w);
+            a_hi.x = fmaf(e.y, v.x, a_hi.x); a_hi.y = fmaf(e.y, v.y, a_hi.y);
+            a_hi.z = fmaf(e.y, v.z, a_hi.z); a_hi.w = fmaf(e.y, v.w, a_hi.w);
+        };
+        if (vec) {
             int t = 0;
 #pragma unroll 1
             for (; t + UT_UNROLL <= nwin; t += UT_UNROLL) {
-                float v[UT_UNROLL];
+                float4 v[UT_UNROLL];
 #pragma unroll
-                for (int q = 0; q < UT_UNROLL; ++q) v[q] = __ldg(gx + (size_t)(t + q) * W);
+                for (int q = 0; q < UT_UNROLL; ++q) { v[q] = __ldcs(reinterpret_cast<const float4*>(row)); row += W; }
 #pragma unroll
-                for (int q = 0; q < UT_UNROLL; ++q) {
-                    const float4 e = s_tab[t + q];
-                    const int y0 = __float_as_int(e.z);
-                    if (y0 > jcur) { emit(jcur, a_lo); a_lo = a_hi; a_hi = 0.0f; ++jcur; }   // y0 advances by <= 1 per row
-                    a_lo = fmaf(e.x, v[q], a_lo);
-                    a_hi = fmaf(e.y, v[q], a_hi);
-                }
+                for (int q = 0; q < UT_UNROLL; ++q) step(t + q, v[q]);
             }
-            for (; t < nwin; ++t) {
-                const float4 e = s_tab[t];
-                const int y0 = __float_as_int(e.z);
-                if (y0 > jcur) { emit(jcur, a_lo); a_lo = a_hi; a_hi = 0.0f; ++jcur; }
-                const float v = __ldg(gx + (size_t)t * W);
-                a_lo = fmaf(e.x, v, a_lo);
-                a_hi = fmaf(e.y, v, a_hi);
+            for (; t < nwin; ++t) { step(t, __ldcs(reinterpret_cast<const float4*>(row))); row += W; }
+        } else {
+            const bool in0 = xq >= 0 && xq < W, in1 = xq + 1 >= 0 && xq + 1 < W;
+            const bool in2 = xq + 2 >= 0 && xq + 2 < W, in3 = xq + 3 >= 0 && xq + 3 < W;
+#pragma unroll 2
+            for (int t = 0; t < nwin; ++t, row += W) {
+                float4 v;
+                v.x = in0 ? __ldcs(row) : 0.0f; v.y = in1 ? __ldcs(row + 1) : 0.0f;
+                v.z = in2 ? __ldcs(row + 2) : 0.0f; v.w = in3 ? __ldcs(row + 3) : 0.0f;
+                step(t, v);
             }
-            emit(jcur, a_lo);
-            emit(jcur + 1, a_hi);
         }
+        emit(jcur, a_lo);
+        emit(jcur + 1, a_hi);
     }
     __syncthreads();
     // low-res columns whose centre of mass lies in the owned chunk: i in [i_lo, i_hi)
     const int i_lo = (int)ceilf((float)xc0 * sx - 1e-4f);
-    const int i_hi = min((int)ceilf((float)min(xc0 + UT_CHUNK, W) * sx - 1e-4f), dw);
-    const int ni = i_hi - i_lo;
-    for (int q = tid; q < ni * (j1 - j0); q += UT_THREADS) {
-        const int r = q / ni, i = i_lo + (q - r * ni);
+    const int i_hi = min((int)ceilf((float)min(xc0 + UT_OWN, W) * sx - 1e-4f), dw);
+    const int nr = j1 - j0;
+    for (int i = i_lo + tid; i < i_hi; i += UT_THREADS) {
         const int xlo = max((int)floorf(((float)i - 0.5f) * fx - 0.5f) - 1, 0);
         const int xhi = min((int)ceilf(((float)i + 1.5f) * fx - 0.5f) + 1, W - 1);
-        float acc = 0.0f;
-        for (int x = xlo; x <= xhi; ++x) {
-            const int k = x - (xc0 - UT_HALO);
-            if (k < 0 || k >= CW) continue;   // cannot happen while factor <= 16
+        float acc[UT_MAXROWS];
+#pragma unroll
+        for (int r = 0; r < UT_MAXROWS; ++r) acc[r] = 0.0f;
+        const int k_lo = max(xlo - (xc0 - UT_HALO), 0), k_hi = min(xhi - (xc0 - UT_HALO), UT_CW - 1);
+        for (int k = k_lo; k <= k_hi; ++k) {
             const int x0 = s_x0[k];
             const float w = (x0 == i ? s_l0[k] : 0.0f) + (x0 + 1 == i ? s_l1[k] : 0.0f);
-            acc = fmaf(w, s_col[r][k], acc);
+            if (w != 0.0f) {
+#pragma unroll
+                for (int r = 0; r < UT_MAXROWS; ++r)
+                    if (r < nr) acc[r] = fmaf(w, s_col[r * UT_CW + k], acc[r]);
+            }
         }
-        float chain = 1.0f;
-        const size_t o = (size_t)b * dh * dw + (size_t)(j0 + r) * dw + i;
-        if (!a.input_is_depth) {
-            const float D = 1.0f / (a.disp_a * __ldg(job.disp[s] + o) + a.disp_b);
-            chain = -a.disp_a * D * D;
+#pragma unroll
+        for (int r = 0; r < UT_MAXROWS; ++r) {
+            if (r < nr) {
+                float chain = 1.0f;
+                const size_t o = (size_t)b * dh * dw + (size_t)(j0 + r) * dw + i;
+                if (!a.input_is_depth) {
+                    const float D = 1.0f / (a.disp_a * __ldg(job.disp[s] + o) + a.disp_b);
+                    chain = -a.disp_a * D * D;
+                }
+                job.g_disp[s][o] = acc[r] * chain;
+            }
         }
-        job.g_disp[s][o] = acc * chain;
     }
 }
 
@@ -992,21 +1025,39 @@ static int sm_count() {
 
 int photo_upsample_T_launch(const PhotoLaunch& p, cudaStream_t st) {
     const plb_photo_args* a = &p.a;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(photo_upsample_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UT_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
     {
         UpTLaunch u;
         u.n_items = 0;
         u.total_blocks = 0;
-        for (int j = 0; j < a->n_jobs; ++j)
-            for (int s = 0; s < a->jobs[j].n_scales; ++s) {
-                const plb_photo_job& job = a->jobs[j];
-                if (!job.g_disp[s] || (job.dh[s] == a->H && job.dw[s] == a->W)) continue;
-                UpTItem& it = u.items[u.n_items++];
-                it.jb = j; it.s = s; it.first_block = u.total_blocks;
-                it.groups = (job.dh[s] + UT_ROWS - 1) / UT_ROWS;
-                it.chunks = (a->W + UT_CHUNK - 1) / UT_CHUNK;
-                u.total_blocks += it.groups * it.chunks * a->B;
-            }
-        photo_upsample_T_kernel<<<u.total_blocks, UT_THREADS, 0, st>>>(p, u);
+        // the blocks of a coarse scale walk more full-resolution rows: they go first (no long tail)
+        for (int pass = 0; pass < PLB_MAX_JOBS * PLB_MAX_SCALES; ++pass) {
+            int bj = -1, bs = -1;
+            for (int j = 0; j < a->n_jobs; ++j)
+                for (int s = 0; s < a->jobs[j].n_scales; ++s) {
+                    const plb_photo_job& job = a->jobs[j];
+                    if (!job.g_disp[s] || (job.dh[s] == a->H && job.dw[s] == a->W)) continue;
+                    bool taken = false;
+                    for (int k = 0; k < u.n_items; ++k) taken = taken || (u.items[k].jb == j && u.items[k].s == s);
+                    if (taken) continue;
+                    if (bj < 0 || job.dh[s] < a->jobs[bj].dh[bs]) { bj = j; bs = s; }
+                }
+            if (bj < 0) break;
+            const plb_photo_job& job = a->jobs[bj];
+            UpTItem& it = u.items[u.n_items++];
+            it.jb = bj; it.s = bs; it.first_block = u.total_blocks;
+            int rows = (int)((float)UT_SPAN * (float)job.dh[bs] / (float)a->H) - 1;
+            it.rows = rows < 1 ? 1 : (rows > UT_MAXROWS ? UT_MAXROWS : rows);
+            it.groups = (job.dh[bs] + it.rows - 1) / it.rows;
+            it.chunks = (a->W + UT_OWN - 1) / UT_OWN;
+            u.total_blocks += it.groups * it.chunks * a->B;
+        }
+        photo_upsample_T_kernel<<<u.total_blocks, UT_THREADS, UT_SMEM, st>>>(p, u);
         ++g_launches;
         PLB_CHECK_LAUNCH();
     }
