@@ -971,7 +971,7 @@ int validate_photo(const plb_photo_args* a) {
     if (a->B < 1 || a->H < 2 || a->W < 2 || a->n_jobs < 1 || a->n_jobs > PLB_MAX_JOBS || a->n_pose < 1)
         return PLB_EINVAL;
     if ((long long)a->H * a->W * 3 >= (1LL << 31)) return PLB_EINVAL;
-    if ((long long)a->H * ((a->W + 31) / 32) * a->B * a->n_jobs * PLB_MAX_SCALES * PLB_MAX_SRC >= (1LL << 31)) return PLB_EINVAL;
+    if ((long long)a->H * ((a->W + 31) / 32) * a->B * a->n_jobs * PLB_MAX_SCALES * PLB_MAX_SRC * 8 >= (1LL << 31)) return PLB_EINVAL;
     if (a->rotation_mode != PLB_ROT_AXISANGLE && a->rotation_mode != PLB_ROT_EULER) return PLB_EINVAL;
     if (a->poses == nullptr || a->K == nullptr || a->loss == nullptr) return PLB_ENULL;
     for (int j = 0; j < a->n_jobs; ++j) {
@@ -1093,7 +1093,12 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
         p.w_e[j] = 0.0f;
         p.lowres[j] = 0;
         if (j < a->n_jobs) {
-            p.unit_weight[j] = a->jobs[j].n_scales * a->jobs[j].n_src;
+            // cost model of a unit: a PAIR of sources runs on the packed fp32 pipe and costs less than two single
+            // (scalar) sources; the ratio is tuned per kernel variant (profiles/README.md)
+            {
+                const int wp = maxsrc <= 2 ? PH_W_PAIR : PH_W_PAIR4, wo = maxsrc <= 2 ? PH_W_ODD : PH_W_ODD4;
+                p.unit_weight[j] = a->jobs[j].n_scales * (wp * (a->jobs[j].n_src / 2) + wo * (a->jobs[j].n_src & 1));
+            }
             if (p.unit_weight[j] < min_w) min_w = p.unit_weight[j];
             wsum += (long long)p.unit_weight[j] * p.units_per_pair * a->B;
             usum += p.units_per_pair * a->B;

@@ -31,6 +31,19 @@ constexpr int PH_REC_STRIDE = 56;
 #define PH_MIN_BLOCKS 3           // resident blocks per SM the <= 2-source kernels are compiled for
 #endif
 
+#ifndef PH_W_PAIR
+#define PH_W_PAIR 8               // relative cost of a source pair (packed pipe) ...
+#endif
+#ifndef PH_W_ODD
+#define PH_W_ODD 5                // ... and of a single source (scalar pipe) in the unit weights, <= 2-source kernels
+#endif
+#ifndef PH_W_PAIR4
+#define PH_W_PAIR4 4              // the same for the 3-4-source kernels (both <= 8)
+#endif
+#ifndef PH_W_ODD4
+#define PH_W_ODD4 5                // (measured: the odd source of the 4-source variant costs MORE than a packed pair)
+#endif
+
 struct PhotoLayout {
     size_t tickets;   // int32 [n_pairs + 1]
     size_t records;   // float [grid][2][PH_REC_STRIDE]
@@ -50,7 +63,7 @@ struct PhotoLaunch {
     int strips;                          // ceil(W / 32)
     int units_per_pair;                  // strips * H
     int n_pairs;                         // n_jobs * B
-    int unit_weight[PLB_MAX_JOBS];       // n_scales * n_src
+    int unit_weight[PLB_MAX_JOBS];       // n_scales * (PH_W_PAIR * pairs + PH_W_ODD * odd source)
     long long weight_start[PLB_MAX_JOBS + 1];  // cumulative weight at the start of each job
     int unit_start[PLB_MAX_JOBS + 1];    // cumulative unit index at the start of each job
     float w_e[PLB_MAX_JOBS];             // term_weight / (3*B*H*W)
