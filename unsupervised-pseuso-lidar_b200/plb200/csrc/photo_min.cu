@@ -99,26 +99,28 @@ __device__ __forceinline__ float pm_depth(const plb_photo_args& a, const PairCon
     return ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
 }
 
-// 3x3 window statistics of one channel at tile+1 position (px1, py1): x from sx (tile+2 layout), y from sy
-struct WinY { float sy, syy; };
-__device__ __forceinline__ WinY win_y(const float* __restrict__ sy_, int k2) {
-    WinY w; w.sy = 0.0f; w.syy = 0.0f;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const float y = sy_[k2 + dy * PM_W2 + dx];
-            w.sy += y; w.syy = fmaf(y, y, w.syy);
-        }
-    return w;
-}
+// Shared memory of one block (dynamic: ~55 KB, three blocks per SM).
+struct __align__(16) PminSmem {
+    float4 coef[3][PM_N1];                  // per channel, the min-source term: d rp / d x_q = ca + cb x_q + cc y_q (+ cl at the centre)
+    PairConst pc;
+    float T[3][PM_N2];                      // target, tile + 2 (reflected at the border)
+    float X[PLB_MAX_SRC][3][PM_N2];         // warped (or, for the automask pass, raw) sources
+    float aut[3][PM_N1];                    // min_i photo(src_i, tgt) per channel
+    float val[3][PM_N1];                    // min_i rp_i per channel
+    signed char src[3][PM_N1];              // argmin_i
+    signed char sel[PM_N1];                 // channel + 4 * source of the term max_c selects, -1 = none
+    float rec[PM_THREADS / 32][PH_NREC + 3];
+    float red[PH_NREC + 3];
+    float part4[4][64];
+    int flag;
+};
 
-// photometric value of one (pixel, channel) and the coefficients of its derivative w.r.t. the
-// predicted image at window position q:  d rp / d x_q = ca + cb * x_q + cc * y_q   (+ cl at the centre)
+// photometric value of one (pixel, channel) from its 3x3 window sums, and the coefficients of its
+// derivative w.r.t. the predicted image at window position q:
+//   d rp / d x_q = ca + cb * x_q + cc * y_q   (+ cl at the centre)
 struct Photo { float rp, ca, cb, cc, cl; };
-__device__ __forceinline__ Photo photo_term(const float* __restrict__ sx_, const float* __restrict__ sy_, int k2,
-                                            const WinY wy, float C1, float C2, bool no_ssim) {
-    const float xc = sx_[k2], yc = sy_[k2];
+__device__ __forceinline__ Photo photo_from_sums(float sx, float sxx, float sxy, float sy, float syy, float xc, float yc,
+                                                 float C1, float C2, bool no_ssim) {
     Photo r;
     const float diff = xc - yc;
     const float sg = (diff > 0.0f ? 1.0f : 0.0f) - (diff < 0.0f ? 1.0f : 0.0f);
@@ -126,36 +128,108 @@ __device__ __forceinline__ Photo photo_term(const float* __restrict__ sx_, const
         r.rp = fabsf(diff); r.ca = r.cb = r.cc = 0.0f; r.cl = sg;
         return r;
     }
-    float sx = 0.0f, sxx = 0.0f, sxy = 0.0f;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const float x = sx_[k2 + dy * PM_W2 + dx], y = sy_[k2 + dy * PM_W2 + dx];
-            sx += x; sxx = fmaf(x, x, sxx); sxy = fmaf(x, y, sxy);
-        }
     const float i9 = 1.0f / 9.0f;
-    const float mux = sx * i9, muy = wy.sy * i9;
+    const float mux = sx * i9, muy = sy * i9;
     const float mxx = mux * mux, myy = muy * muy, mxy = mux * muy;
-    const float sigx = sxx * i9 - mxx, sigy = wy.syy * i9 - myy, sigxy = sxy * i9 - mxy;
-    const float N1 = 2.0f * mxy + C1, N2 = 2.0f * sigxy + C2;
+    const float sigx = fmaf(sxx, i9, -mxx), sigy = fmaf(syy, i9, -myy), sigxy = fmaf(sxy, i9, -mxy);
+    const float N1 = fmaf(2.0f, mxy, C1), N2 = fmaf(2.0f, sigxy, C2);
     const float D1 = mxx + myy + C1, D2 = sigx + sigy + C2;
-    const float iD1 = 1.0f / D1, iD2 = 1.0f / D2;
-    const float ssim = (N1 * N2) * (iD1 * iD2);
+    const float iD = rcp_nr(D1 * D2);                    // one reciprocal for both denominators
+    const float iD1 = D2 * iD, iD2 = D1 * iD;
+    const float ssim = (N1 * N2) * iD;
     const float h = (1.0f - ssim) * 0.5f;
-    r.rp = 0.85f * fminf(fmaxf(h, 0.0f), 1.0f) + 0.15f * fabsf(diff);
+    r.rp = fmaf(0.85f, fminf(fmaxf(h, 0.0f), 1.0f), 0.15f * fabsf(diff));
     // d ssim / d x_q = (2/9) { [mu_y (N2 - N1)]/(D1 D2) - ssim mu_x (1/D1 - 1/D2) }  +  x_q (-(2/9) ssim / D2)
     //                  + y_q ((2/9) N1 / (D1 D2));   d rp / d x_q = -0.425 * (that) inside the clamp
     const float k = (h > 0.0f && h < 1.0f) ? (-0.425f * 2.0f * i9) : 0.0f;
-    r.ca = k * (muy * (N2 - N1) * (iD1 * iD2) - ssim * mux * (iD1 - iD2));
+    r.ca = k * (muy * (N2 - N1) * iD - ssim * mux * (iD1 - iD2));
     r.cb = k * (-ssim * iD2);
-    r.cc = k * (N1 * (iD1 * iD2));
+    r.cc = k * (N1 * iD);
     r.cl = 0.15f * sg;
     return r;
 }
 
-template <bool GRAD>
-__global__ void __launch_bounds__(PM_THREADS)
+// Stage 2 work item = (channel, column of tile + 1, group of 5 rows): 3 x 34 x 2 = 204 threads.  The
+// thread walks DOWN its column keeping the last three horizontal 3-sums of y, y^2 and, per source, x,
+// x^2, x y in registers (separable box filter: 3 shared loads per source and row instead of 18), and
+// emits one photometric term per row: min over the NS sources of this call.
+//   MODE 0: first sources of the scale: write val / src / coef;  MODE 1: later sources: update when smaller;
+//   MODE 2 / 3: the same for the automask reference (raw sources), value only.
+constexpr int PM_S2_ITEMS = 3 * PM_W1 * 2;
+template <int NS, int MODE>
+__device__ __forceinline__ void pm_stage2(PminSmem& S, int i0, int tid, int tx0, int ty0, int H, int W, float C1, float C2,
+                                          bool no_ssim) {
+    if (tid >= PM_S2_ITEMS) return;
+    const int ch = tid / (2 * PM_W1), r = tid - ch * (2 * PM_W1);
+    const int grp = r / PM_W1, col = r - grp * PM_W1;
+    const float* __restrict__ T = S.T[ch];
+    int k = (5 * grp) * PM_W2 + col;        // tile + 2 index of the window's top-left corner
+    float hy[3], hyy[3], hx[NS][3], hxx[NS][3], hxy[NS][3];
+    float yc = 0.0f, xc[NS];
+    const int gx = tx0 + col - 1;
+    const bool colin = gx >= 0 && gx < W;
+#pragma unroll
+    for (int rr = 0; rr < 7; ++rr, k += PM_W2) {
+        const int slot = rr % 3;
+        const float y0 = T[k], y1 = T[k + 1], y2 = T[k + 2];
+        hy[slot] = (y0 + y1) + y2;
+        hyy[slot] = fmaf(y2, y2, fmaf(y1, y1, y0 * y0));
+        float xn[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const float* __restrict__ X = S.X[i0 + q][ch];
+            const float x0 = X[k], x1 = X[k + 1], x2 = X[k + 2];
+            hx[q][slot] = (x0 + x1) + x2;
+            hxx[q][slot] = fmaf(x2, x2, fmaf(x1, x1, x0 * x0));
+            hxy[q][slot] = fmaf(x2, y2, fmaf(x1, y1, x0 * y0));
+            xn[q] = x1;
+        }
+        if (rr >= 2) {
+            const int o = 5 * grp + rr - 2;            // row of tile + 1
+            const int p1 = o * PM_W1 + col;
+            const int gy = ty0 + o - 1;
+            const bool in = colin && gy >= 0 && gy < H;
+            const float sy = (hy[0] + hy[1]) + hy[2], syy = (hyy[0] + hyy[1]) + hyy[2];
+            Photo m; m.rp = 3.0e38f; m.ca = m.cb = m.cc = m.cl = 0.0f;
+            int mi = 0;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                const Photo t = photo_from_sums((hx[q][0] + hx[q][1]) + hx[q][2], (hxx[q][0] + hxx[q][1]) + hxx[q][2],
+                                                (hxy[q][0] + hxy[q][1]) + hxy[q][2], sy, syy, xc[q], yc, C1, C2, no_ssim);
+                if (t.rp < m.rp) { m = t; mi = i0 + q; }
+            }
+            if (MODE >= 2) {
+                S.aut[ch][p1] = (MODE == 2) ? m.rp : fminf(m.rp, S.aut[ch][p1]);
+            } else {
+                const bool take = (MODE == 0) || m.rp < S.val[ch][p1];
+                if (take) {
+                    S.val[ch][p1] = in ? m.rp : 3.0e38f;
+                    S.src[ch][p1] = (signed char)mi;
+                    S.coef[ch][p1] = make_float4(m.ca, m.cb, m.cc, m.cl);
+                }
+            }
+        }
+        yc = y1;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) xc[q] = xn[q];
+    }
+}
+
+template <int MODE0>
+__device__ __forceinline__ void pm_stage2_all(PminSmem& S, int n_src, int tid, int tx0, int ty0, int H, int W, float C1,
+                                              float C2, bool no_ssim) {
+    // sources two at a time (they share the target's window sums); block-uniform control flow
+    if (n_src >= 2) pm_stage2<2, MODE0>(S, 0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+    else pm_stage2<1, MODE0>(S, 0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+    if (n_src > 2) {
+        __syncthreads();
+        if (n_src == 4) pm_stage2<2, MODE0 + 1>(S, 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+        else pm_stage2<1, MODE0 + 1>(S, 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+    }
+}
+
+template <bool GRAD, int NSMAX>
+__global__ void __launch_bounds__(PM_THREADS, 3)
 photo_min_kernel(const __grid_constant__ PminLaunch p) {
     const plb_photo_args& a = p.a;
     if (skip_launch(a.skip_if_unit)) return;
@@ -173,16 +247,9 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     const plb_photo_job& job = a.jobs[0];
     const bool no_ssim = job.flags & PLB_PHOTO_NO_SSIM, automask = !(job.flags & PLB_PHOTO_NO_AUTOMASK);
 
-    __shared__ PairConst pc;
-    __shared__ float sT[3][PM_N2];                     // target, tile + 2 (reflected at the border)
-    __shared__ float sX[PLB_MAX_SRC][3][PM_N2];        // warped (or, for the automask pass, raw) sources
-    __shared__ float sAuto[3][PM_N1];                  // min_i photo(src_i, tgt) per channel
-    __shared__ float sCa[PM_N1], sCb[PM_N1], sCc[PM_N1], sCl[PM_N1];
-    __shared__ signed char sSel[PM_N1];                // channel + 4 * source of the selected term, -1 = none
-    __shared__ float s_rec[PM_THREADS / 32][PH_NREC + 3];
-    __shared__ float s_red[PH_NREC + 3];
-    __shared__ float s_part4[4][64];
-    __shared__ int s_flag;
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    PminSmem& S = *reinterpret_cast<PminSmem*>(pm_smem);
+    PairConst& pc = S.pc;
 
     // ---- prologue: K^-1, P per source, base pointers of image b ------------------------------------
     {
@@ -216,10 +283,12 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
             pc.src[lane] = job.src[lane] + img;
         }
     }
-    for (int k = tid; k < (PM_THREADS / 32) * (PH_NREC + 3); k += PM_THREADS) (&s_rec[0][0])[k] = 0.0f;
+    for (int k = tid; k < (PM_THREADS / 32) * (PH_NREC + 3); k += PM_THREADS) (&S.rec[0][0])[k] = 0.0f;
     __syncthreads();
     const int n_src = pc.n_src, n_scales = pc.n_scales;
     const float w_e = pc.w_e / (float)n_scales;        // scales are averaged
+    // does the tile (+1 halo) touch the image border?  (reflection multiplicities in stage 3)
+    const bool border = tx0 == 0 || ty0 == 0 || tx0 + PM_TW + 1 >= W || ty0 + PM_TH + 1 >= H;
 
     // ---- target tile (+2, reflected) and the automask reference min_i photo(src_i, tgt) -------------
     for (int k = tid; k < PM_N2; k += PM_THREADS) {
@@ -227,32 +296,20 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
         const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
         const int o = gy * W + gx;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sT[c][k] = __ldg(pc.tgt + (o + c * plane));
+        for (int c = 0; c < 3; ++c) S.T[c][k] = __ldg(pc.tgt + (o + c * plane));
         if (automask)
             for (int i = 0; i < n_src; ++i)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) sX[i][c][k] = __ldg(pc.src[i] + (o + c * plane));
+                for (int c = 0; c < 3; ++c) S.X[i][c][k] = __ldg(pc.src[i] + (o + c * plane));
     }
     __syncthreads();
-    if (automask) {
-        for (int k1 = tid; k1 < PM_N1; k1 += PM_THREADS) {
-            const int ly = k1 / PM_W1, lx = k1 - ly * PM_W1;
-            const int k2 = (ly + 1) * PM_W2 + (lx + 1);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const WinY wy = win_y(sT[c], k2);
-                float m = 3.0e38f;
-                for (int i = 0; i < n_src; ++i) m = fminf(m, photo_term(sX[i][c], sT[c], k2, wy, p.C1, p.C2, no_ssim).rp);
-                sAuto[c][k1] = m;
-            }
-        }
-    }
+    if (automask) pm_stage2_all<2>(S, n_src, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
     __syncthreads();
 
-    float acc[PLB_MAX_SRC][12];
+    float acc[NSMAX][12];
     float lsum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < PLB_MAX_SRC; ++i)
+    for (int i = 0; i < NSMAX; ++i)
 #pragma unroll
         for (int k = 0; k < 12; ++k) acc[i][k] = 0.0f;
 
@@ -273,106 +330,107 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
             const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
             const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
             const float rz = fmaf(pc.kinv[7], yf, pc.kinv[6] * xf) + pc.kinv[8];
-            for (int i = 0; i < n_src; ++i) {
-                MinProj q;
-                pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
-                float v[3][4];
-                pm_taps(pc.src[i], plane, W, q, v);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float top = fmaf(q.fx, v[c][1] - v[c][0], v[c][0]), bot = fmaf(q.fx, v[c][3] - v[c][2], v[c][2]);
-                    sX[i][c][k] = fmaf(q.fy, bot - top, top);
+            for (int i = 0; i < NSMAX; ++i) {
+                if (i < n_src) {
+                    MinProj q;
+                    pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
+                    float v[3][4];
+                    pm_taps(pc.src[i], plane, W, q, v);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float top = fmaf(q.fx, v[c][1] - v[c][0], v[c][0]), bot = fmaf(q.fx, v[c][3] - v[c][2], v[c][2]);
+                        S.X[i][c][k] = fmaf(q.fy, bot - top, top);
+                    }
                 }
             }
         }
         __syncthreads();
-        // ---- (2) photometric mix, min over sources, automask, max over channels on tile + 1 -------
+        // ---- (2) photometric mix and min over sources per channel (separable, sliding) ------------
+        pm_stage2_all<0>(S, n_src, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
+        __syncthreads();
+        // ---- (2b) automask, max over channels on tile + 1 ------------------------------------------
         for (int k1 = tid; k1 < PM_N1; k1 += PM_THREADS) {
             const int ly = k1 / PM_W1, lx = k1 - ly * PM_W1;
-            const int gx = tx0 + lx - 1, gy = ty0 + ly - 1;
-            const int k2 = (ly + 1) * PM_W2 + (lx + 1);
-            float best = 0.0f, bca = 0.0f, bcb = 0.0f, bcc = 0.0f, bcl = 0.0f;
+            float best = 0.0f;
             int bsel = -1;
-            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const WinY wy = win_y(sT[c], k2);
-                    Photo m; m.rp = 3.0e38f; m.ca = m.cb = m.cc = m.cl = 0.0f;
-                    int mi = 0;
-                    for (int i = 0; i < n_src; ++i) {
-                        const Photo r = photo_term(sX[i][c], sT[c], k2, wy, p.C1, p.C2, no_ssim);
-                        if (r.rp < m.rp) { m = r; mi = i; }
-                    }
-                    const bool keep = !automask || m.rp < sAuto[c][k1];
-                    const float val = keep ? m.rp : 0.0f;
+            for (int c = 0; c < 3; ++c) {
+                const float rp = S.val[c][k1];
+                if (rp < 1.0e38f) {                       // inside the image
+                    const bool keep = !automask || rp < S.aut[c][k1];
+                    const float val = keep ? rp : 0.0f;
                     // torch.max over channels: first maximal channel wins; a masked channel carries no gradient
                     if (bsel == -1 || val > best) {
                         best = val;
-                        bsel = keep ? (c + 4 * mi) : -2;
-                        bca = m.ca; bcb = m.cb; bcc = m.cc; bcl = m.cl;
+                        bsel = keep ? (c + 4 * (int)S.src[c][k1]) : -2;
                     }
                 }
-                const bool interior = lx >= 1 && lx <= PM_TW && ly >= 1 && ly <= PM_TH;
-                if (interior) lsum += best;
             }
-            sSel[k1] = (signed char)(bsel >= 0 ? bsel : -1);
-            sCa[k1] = bca; sCb[k1] = bcb; sCc[k1] = bcc; sCl[k1] = bcl;
+            const bool interior = lx >= 1 && lx <= PM_TW && ly >= 1 && ly <= PM_TH;
+            if (interior) lsum += best;
+            S.sel[k1] = (signed char)(bsel >= 0 ? bsel : -1);
         }
         __syncthreads();
         // ---- (3) gradient of the tile pixels ------------------------------------------------------
         if (GRAD) {
             float gD = 0.0f, D = 0.0f;
             if (qin) {
+                // d loss / d warped_i(q, c): the selected terms of the 3x3 neighbours p, by (source, channel)
+                float e[NSMAX][3];
+#pragma unroll
+                for (int i = 0; i < NSMAX; ++i) e[i][0] = e[i][1] = e[i][2] = 0.0f;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int pk1 = qk1 + dy * PM_W1 + dx;
+                        const int sel = S.sel[pk1];
+                        const int sc = max(sel, 0), c = sc & 3, i = sc >> 2;
+                        const float4 cf = S.coef[c][pk1];
+                        float g = fmaf(cf.y, S.X[i][c][qk2], fmaf(cf.z, S.T[c][qk2], cf.x));
+                        if (border) {
+                            // multiplicity of q in p's reflection-padded window
+                            const int pxg = qx + dx, pyg = qy + dy;
+                            const float mx = 1.0f + ((pxg == 0 && dx == -1) ? 1.0f : 0.0f) + ((pxg == W - 1 && dx == 1) ? 1.0f : 0.0f);
+                            const float my = 1.0f + ((pyg == 0 && dy == -1) ? 1.0f : 0.0f) + ((pyg == H - 1 && dy == 1) ? 1.0f : 0.0f);
+                            g *= mx * my;
+                        }
+                        if (dx == 0 && dy == 0) g += cf.w;
+#pragma unroll
+                        for (int ii = 0; ii < NSMAX; ++ii)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) e[ii][cc] += (sel == cc + 4 * ii) ? g : 0.0f;
+                    }
                 D = pm_depth(a, pc, s, full, qx, qy, W);
                 const float xf = (float)qx, yf = (float)qy;
                 const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
                 const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
                 const float rz = fmaf(pc.kinv[7], yf, pc.kinv[6] * xf) + pc.kinv[8];
 #pragma unroll
-                for (int i = 0; i < PLB_MAX_SRC; ++i) {
-                    if (i < n_src) {
-                        // d loss / d warped_i(q, c): the selected terms of the 3x3 neighbours p that use source i
-                        float e[3] = {0.0f, 0.0f, 0.0f};
+                for (int i = 0; i < NSMAX; ++i) {
+                    if (i < n_src && (e[i][0] != 0.0f || e[i][1] != 0.0f || e[i][2] != 0.0f)) {
+                        MinProj q;
+                        pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
+                        float v[3][4];
+                        pm_taps(pc.src[i], plane, W, q, v);
+                        float Gx = 0.0f, Gy = 0.0f;
 #pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const int pk1 = qk1 + dy * PM_W1 + dx;
-                                const int sel = sSel[pk1];
-                                if (sel >= 0 && (sel >> 2) == i) {
-                                    const int c = sel & 3;
-                                    const int pxg = qx + dx, pyg = qy + dy;
-                                    // multiplicity of q in p's reflection-padded window
-                                    const float mx = 1.0f + ((pxg == 0 && dx == -1) ? 1.0f : 0.0f) + ((pxg == W - 1 && dx == 1) ? 1.0f : 0.0f);
-                                    const float my = 1.0f + ((pyg == 0 && dy == -1) ? 1.0f : 0.0f) + ((pyg == H - 1 && dy == 1) ? 1.0f : 0.0f);
-                                    float g = mx * my * fmaf(sCb[pk1], sX[i][c][qk2], fmaf(sCc[pk1], sT[c][qk2], sCa[pk1]));
-                                    if (dx == 0 && dy == 0) g += sCl[pk1];
-                                    e[c] += g;
-                                }
-                            }
-                        if (e[0] != 0.0f || e[1] != 0.0f || e[2] != 0.0f) {
-                            MinProj q;
-                            pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
-                            float v[3][4];
-                            pm_taps(pc.src[i], plane, W, q, v);
-                            float Gx = 0.0f, Gy = 0.0f;
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const float dA = v[c][1] - v[c][0], dB = v[c][3] - v[c][2];
-                                const float top = fmaf(q.fx, dA, v[c][0]), bot = fmaf(q.fx, dB, v[c][2]);
-                                Gx = fmaf(e[c], fmaf(q.fy, dB - dA, dA), Gx);
-                                Gy = fmaf(e[c], bot - top, Gy);
-                            }
-                            const bool use = q.mask != 0u;
-                            const float gi = use ? w_e * q.inv : 0.0f;
-                            const float gcx = Gx * gi, gcy = Gy * gi;
-                            const float gcz = use ? -(gcx * q.px + gcy * q.py) : 0.0f;
-                            gD += fmaf(gcx, q.Ax, fmaf(gcy, q.Ay, gcz * q.Az));
-                            const float hx = gcx * D, hy = gcy * D, hz = gcz * D;
-                            acc[i][0] = fmaf(hx, rx, acc[i][0]); acc[i][1] = fmaf(hx, ry, acc[i][1]); acc[i][2] = fmaf(hx, rz, acc[i][2]); acc[i][3] += gcx;
-                            acc[i][4] = fmaf(hy, rx, acc[i][4]); acc[i][5] = fmaf(hy, ry, acc[i][5]); acc[i][6] = fmaf(hy, rz, acc[i][6]); acc[i][7] += gcy;
-                            acc[i][8] = fmaf(hz, rx, acc[i][8]); acc[i][9] = fmaf(hz, ry, acc[i][9]); acc[i][10] = fmaf(hz, rz, acc[i][10]); acc[i][11] += gcz;
+                        for (int c = 0; c < 3; ++c) {
+                            const float dA = v[c][1] - v[c][0], dB = v[c][3] - v[c][2];
+                            const float top = fmaf(q.fx, dA, v[c][0]), bot = fmaf(q.fx, dB, v[c][2]);
+                            Gx = fmaf(e[i][c], fmaf(q.fy, dB - dA, dA), Gx);
+                            Gy = fmaf(e[i][c], bot - top, Gy);
                         }
+                        const bool use = q.mask != 0u;
+                        const float gi = use ? w_e * q.inv : 0.0f;
+                        const float gcx = Gx * gi, gcy = Gy * gi;
+                        const float gcz = use ? -(gcx * q.px + gcy * q.py) : 0.0f;
+                        gD += fmaf(gcx, q.Ax, fmaf(gcy, q.Ay, gcz * q.Az));
+                        const float hx = gcx * D, hy = gcy * D, hz = gcz * D;
+                        acc[i][0] = fmaf(hx, rx, acc[i][0]); acc[i][1] = fmaf(hx, ry, acc[i][1]); acc[i][2] = fmaf(hx, rz, acc[i][2]); acc[i][3] += gcx;
+                        acc[i][4] = fmaf(hy, rx, acc[i][4]); acc[i][5] = fmaf(hy, ry, acc[i][5]); acc[i][6] = fmaf(hy, rz, acc[i][6]); acc[i][7] += gcy;
+                        acc[i][8] = fmaf(hz, rx, acc[i][8]); acc[i][9] = fmaf(hz, ry, acc[i][9]); acc[i][10] = fmaf(hz, rz, acc[i][10]); acc[i][11] += gcz;
                     }
                 }
                 float* g = pc.g_disp[s];
@@ -382,12 +440,12 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
                 }
             }
         }
-        __syncthreads();   // sX / selection arrays are rewritten by the next scale
+        __syncthreads();   // X / selection arrays are rewritten by the next scale
     }
 
     // ---- block record: warp butterflies, fixed-order sum over warps --------------------------------
 #pragma unroll
-    for (int i = 0; i < PLB_MAX_SRC; ++i) {
+    for (int i = 0; i < NSMAX; ++i) {
         float v[16];
 #pragma unroll
         for (int k = 0; k < 12; ++k) v[k] = acc[i][k];
@@ -396,8 +454,8 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
         int which;
         const float r = warp_reduce16(v, lane, which);
         if ((lane & 1) == 0) {
-            if (which < 12) s_rec[warp][i * 12 + which] = r;
-            else if (which == 12 && i == 0) s_rec[warp][PLB_MAX_SRC * 12] = r;
+            if (which < 12) S.rec[warp][i * 12 + which] = r;
+            else if (which == 12 && i == 0) S.rec[warp][PLB_MAX_SRC * 12] = r;
         }
     }
     __syncthreads();
@@ -405,14 +463,14 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     if (tid < PH_NREC) {
         float v = 0.0f;
 #pragma unroll
-        for (int w = 0; w < PM_THREADS / 32; ++w) v += s_rec[w][tid];
+        for (int w = 0; w < PM_THREADS / 32; ++w) v += S.rec[w][tid];
         __stcg(my_rec + tid, v);
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_flag = (atomicAdd(&tickets[b], 1) == p.tiles - 1);
+    if (tid == 0) S.flag = (atomicAdd(&tickets[b], 1) == p.tiles - 1);
     __syncthreads();
-    if (!s_flag) return;
+    if (!S.flag) return;
 
     // ---- last tile of image b: sum its records (4 groups x 64 lanes, fixed order), pose chain -------
     __threadfence();
@@ -423,15 +481,15 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
 #pragma unroll 4
             for (int t = grp; t < p.tiles; t += 4) v += __ldcg(records + ((size_t)b * p.tiles + t) * PH_REC_STRIDE + c);
         }
-        s_part4[grp][c] = v;
+        S.part4[grp][c] = v;
         __syncthreads();
-        if (tid < PH_NREC) s_red[tid] = ((s_part4[0][tid] + s_part4[1][tid]) + s_part4[2][tid]) + s_part4[3][tid];
+        if (tid < PH_NREC) S.red[tid] = ((S.part4[0][tid] + S.part4[1][tid]) + S.part4[2][tid]) + S.part4[3][tid];
     }
     __syncthreads();
-    if (tid == 0) { ws_loss[b] = s_red[PLB_MAX_SRC * 12]; tickets[b] = 0; }
+    if (tid == 0) { ws_loss[b] = S.red[PLB_MAX_SRC * 12]; tickets[b] = 0; }
     if (GRAD && tid < n_src) {
         float dP[12], dM[12], g6[6];
-        for (int k = 0; k < 12; ++k) dP[k] = s_red[tid * 12 + k];
+        for (int k = 0; k < 12; ++k) dP[k] = S.red[tid * 12 + k];
         const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
         kT_times_dP(Kb, a.k_is_f64, dP, dM);
         pose_to_M_vjp(a.poses + ((size_t)b * a.n_pose + job.pose_index[tid]) * 6, a.rotation_mode, job.pose_inv[tid], dM, g6);
@@ -440,9 +498,9 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_flag = (atomicAdd(&tickets[a.B], 1) == a.B - 1);
+    if (tid == 0) S.flag = (atomicAdd(&tickets[a.B], 1) == a.B - 1);
     __syncthreads();
-    if (!s_flag) return;
+    if (!S.flag) return;
 
     // ---- last image of the launch -----------------------------------------------------------------
     __threadfence();
@@ -463,6 +521,19 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     }
 }
 
+template <bool GRAD, int NSMAX>
+static int pm_launch_variant(const PminLaunch& p, dim3 grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(photo_min_kernel<GRAD, NSMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)sizeof(PminSmem));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    photo_min_kernel<GRAD, NSMAX><<<grid, PM_THREADS, sizeof(PminSmem), st>>>(p);
+    return PLB_OK;
+}
+
 int photo_min_launch(const plb_photo_args* a, cudaStream_t st) {
     int rc = validate_photo(a);
     if (rc != PLB_OK) return rc;
@@ -479,8 +550,9 @@ int photo_min_launch(const plb_photo_args* a, cudaStream_t st) {
     p.w_e = job.term_weight / ((float)a->B * (float)a->H * (float)a->W);
     p.C1 = 1e-4f; p.C2 = 9e-4f;
     dim3 grid(p.tiles, a->B);
-    if (a->want_grad) photo_min_kernel<true><<<grid, PM_THREADS, 0, st>>>(p);
-    else photo_min_kernel<false><<<grid, PM_THREADS, 0, st>>>(p);
+    if (a->want_grad) rc = job.n_src <= 2 ? pm_launch_variant<true, 2>(p, grid, st) : pm_launch_variant<true, PLB_MAX_SRC>(p, grid, st);
+    else rc = job.n_src <= 2 ? pm_launch_variant<false, 2>(p, grid, st) : pm_launch_variant<false, PLB_MAX_SRC>(p, grid, st);
+    if (rc != PLB_OK) return rc;
     ++g_launches;
     PLB_CHECK_LAUNCH();
     if (photo_has_lowres_grad(*a)) {
