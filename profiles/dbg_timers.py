@@ -24,7 +24,7 @@ t0 = t[0]
 names = {0: "main blk0 start", 1: "main blk0 prologue done", 2: "main blk0 units done", 3: "main blk0 end",
          4: "main blkN start", 5: "main blkN prologue done", 6: "main blkN units done", 7: "main blkN end",
          8: "fin start (t0)", 9: "fin start (prep thread)", 10: "fin prep done", 11: "fin after wait (t0)",
-         12: "fin after wait (prep)", 13: "fin loads done", 14: "fin barrier 1", 15: "fin end"}
+         12: "fin after wait (prep)", 16: "fin loads issued", 17: "fin first load back", 18: "fin pair loads back", 13: "fin loads done", 14: "fin barrier 1", 15: "fin end"}
 print("kernel_ms %.4f" % ms)
 for k in sorted(names):
     print("%-28s %8.2f us" % (names[k], (t[k] - t0) / 1e3))

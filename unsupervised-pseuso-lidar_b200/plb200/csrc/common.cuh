@@ -260,6 +260,7 @@ __device__ __forceinline__ float rcp_nr(float z) {
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ float ldg_pred(const float* __restrict__ p, bool ok) {
     return ok ? __ldg(p) : 0.0f;

@@ -536,37 +536,55 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
                                 : job.g_disp[sc] + (size_t)b * plane;
                     pc.g_disp[sc] = g;
                 }
+                if (lane == 8) {
+                    // K^-1 (fp64 adjugate, rounded to fp32 as transform.py:92 does) - in parallel with the pose chain
+                    // of the odd warp: executed once per block, this code runs cold, and two short dependent
+                    // chains on two warps finish sooner than one long chain
+                    float ki[9];
+                    kinv_f32(Kb, a.k_is_f64, ki);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) pc.kinv[k] = ki[k];
+                }
             } else {
                 if (lane < job.n_src) {
                     float M[12], P[12];
-                    double Ki[9];
                     pose_to_M(a.poses + ((size_t)b * a.n_pose + job.pose_index[lane]) * 6, a.rotation_mode,
                               job.pose_inv[lane], M);
                     k_times_M(Kb, a.k_is_f64, M, P);
-                    kinv_f64(Kb, a.k_is_f64, Ki);
-                    // Q = P[:, :3] . fl32(K^-1): the exact product of the two fp32 matrices the reference
-                    // multiplies a pixel by (transform.py:92,137), rounded once
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        float q[3];
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            q[c] = (float)((double)P[r * 4 + 0] * (double)(float)Ki[0 + c] + (double)P[r * 4 + 1] * (double)(float)Ki[3 + c] +
-                                           (double)P[r * 4 + 2] * (double)(float)Ki[6 + c]);
-                        pc.Q[lane][r] = make_float4(q[0], q[1], q[2], P[r * 4 + 3]);
-                    }
+                    for (int r = 0; r < 3; ++r) pc.P[lane][r] = make_float4(P[r * 4], P[r * 4 + 1], P[r * 4 + 2], P[r * 4 + 3]);
                     pc.src[lane] = job.src[lane] + img;
                     pc.g_src[lane] = (GRAD && IMG_GRAD && job.g_src[lane]) ? job.g_src[lane] + img : nullptr;
                 }
-                __syncwarp();
-                // packed copy for source pairs (2g, 2g+1): low half = even source, high half = odd source
-                if (lane < (PLB_MAX_SRC / 2) * 3) {
-                    const int g = lane / 3, r = lane - g * 3;
-                    if (2 * g + 1 < job.n_src) {
-                        const float4 q0 = pc.Q[2 * g][r], q1 = pc.Q[2 * g + 1][r];
-                        pc.Q2[g][r][0] = make_float4(q0.x, q1.x, q0.y, q1.y);
-                        pc.Q2[g][r][1] = make_float4(q0.z, q1.z, q0.w, q1.w);
-                    }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int set = warp >> 1;
+        if (!empty_block && warp < 4 && (warp & 1) == 1 && (set == 0 || pairB != pairA)) {
+            PairConst& pc = s_pc[set];
+            const int n_src = pc.n_src;
+            // Q = P[:, :3] . fl32(K^-1): the exact product of the two fp32 matrices the reference multiplies a
+            // pixel by (transform.py:92,137), rounded once; one lane per (source, row)
+            if (lane < 3 * n_src) {
+                const int i = lane / 3, r = lane - 3 * i;
+                const float4 P = pc.P[i][r];
+                float q[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    q[c] = (float)((double)P.x * (double)pc.kinv[0 + c] + (double)P.y * (double)pc.kinv[3 + c] +
+                                   (double)P.z * (double)pc.kinv[6 + c]);
+                pc.Q[i][r] = make_float4(q[0], q[1], q[2], P.w);
+            }
+            __syncwarp();
+            // packed copy for source pairs (2g, 2g+1): low half = even source, high half = odd source
+            if (lane < (PLB_MAX_SRC / 2) * 3) {
+                const int g = lane / 3, r = lane - g * 3;
+                if (2 * g + 1 < n_src) {
+                    const float4 q0 = pc.Q[2 * g][r], q1 = pc.Q[2 * g + 1][r];
+                    pc.Q2[g][r][0] = make_float4(q0.x, q1.x, q0.y, q1.y);
+                    pc.Q2[g][r][1] = make_float4(q0.z, q1.z, q0.w, q1.w);
                 }
             }
         }
@@ -616,16 +634,22 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
     for (int k = tid; k < 2 * PH_REC_STRIDE; k += PH_THREADS) {
         const int set = k / PH_REC_STRIDE, c = k - set * PH_REC_STRIDE;
         float v;
-        if (c == 0) {
+        if (c == PH_REC_ID) {
             v = __int_as_float(s_pair[set]);
-        } else if (c <= PH_NREC) {
+        } else if (c < PH_NREC) {
             v = 0.0f;
 #pragma unroll
-            for (int w = 0; w < PH_WARPS; ++w) v += s_rec[set][w][c - 1];
+            for (int w = 0; w < PH_WARPS; ++w) v += s_rec[set][w][c];
         } else {
             v = 0.0f;
         }
         my_rec[k] = v;
+    }
+    if (tid < 2) {   // compact copy of (pair id, sum |diff|) for the loss reduction
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < PH_WARPS; ++w) v += s_rec[tid][w][PLB_MAX_SRC * 12];
+        reinterpret_cast<float2*>(ws + p.L.lossrec)[vblk * 2 + tid] = make_float2(__int_as_float(s_pair[tid]), v);
     }
     DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 3 : 7);
 }
@@ -669,31 +693,18 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
         if (combo < PF_COMBOS && jb < a.n_jobs && i < a.jobs[jb].n_src)
             photo_pose_jacobian(a, a.jobs[jb], b, i, k, s_J[combo]);
     }
-    DBG_STAMP(b == 0 && tid == PF_PREP_T0, 10);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (skip_launch(a.skip_if_unit)) return;
-    DBG_STAMP(b == 0 && (tid == 0 || tid == PF_PREP_T0), tid == 0 ? 11 : 12);
+    // ---- still before the wait (launch constants only): where this thread will read.  After the wait every
+    //      load is base + compile-time offset under one count compare - the post-wait section is issue-bound
+    //      (16 warps on one SM), so its address arithmetic is what the caller waits for -----------------------
     const float* records = (const float*)((const char*)a.workspace + p.L.records);
-    {
-        // ---- loss (block 0): every record's sum |diff|, weighted by its job; the loads are issued first
-        //      so that they share one L2 round trip with the record loads below --------------------------
-        constexpr int LQ = 6;                         // covers grids up to 6 * 512 / 2 = 1536 blocks
-        float lval[LQ];
-        int lid[LQ];
-        if (b == 0) {
+    const int c = tid & 63, grp = tid >> 6;
+    constexpr int PF_FIRST = 12;                      // records per (thread, job) loaded in the unrolled batch
+    const float* rp[PLB_MAX_JOBS];
+    int rcnt[PLB_MAX_JOBS], rcnt_all[PLB_MAX_JOBS], rpair[PLB_MAX_JOBS];
 #pragma unroll
-            for (int m = 0; m < LQ; ++m) {
-                const int q = tid + m * PF_THREADS;
-                const bool in = q < p.grid * 2;
-                const float* r = records + (size_t)(in ? q : 0) * PH_REC_STRIDE;
-                lid[m] = in ? __float_as_int(__ldcg(r)) : -1;
-                lval[m] = in ? __ldcg(r + 1 + PLB_MAX_SRC * 12) : 0.0f;
-            }
-        }
-        // ---- fixed-order sum of the block records of each (job, image b) pair -------------------------
-        const int c = tid & 63, grp = tid >> 6;
-#pragma unroll 1
-        for (int jb = 0; jb < a.n_jobs; ++jb) {
+    for (int jb = 0; jb < PLB_MAX_JOBS; ++jb) {
+        rp[jb] = records; rcnt[jb] = 0; rcnt_all[jb] = 0; rpair[jb] = -1;
+        if (jb < a.n_jobs) {
             const int pr = jb * a.B + b;
             // blocks whose range can overlap this pair (widened by one block on each side; records carry the pair id)
             const long long w0 = p.weight_start[jb] + (long long)(pr * p.units_per_pair - p.unit_start[jb]) * p.unit_weight[jb];
@@ -702,17 +713,66 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
             int k_hi = photo_warp_of(p, w1) / p.warps_per_block + 1;
             k_lo = max(k_lo, 0); k_hi = min(k_hi, p.grid - 1);
             const int n_rec = (k_hi - k_lo + 1) * 2;
-            float v = 0.0f;
-            if (c < PH_NREC) {
-#pragma unroll 10
-                for (int r_i = grp; r_i < n_rec; r_i += PF_GROUPS) {
-                    const float* r = records + ((size_t)k_lo * 2 + r_i) * PH_REC_STRIDE;
-                    const int id = __float_as_int(__ldcg(r));
-                    const float val = __ldcg(r + 1 + c);
-                    v += (id == pr) ? val : 0.0f;
-                }
+            rp[jb] = records + ((size_t)k_lo * 2 + grp) * PH_REC_STRIDE;
+            rcnt_all[jb] = n_rec > grp ? (n_rec - grp + PF_GROUPS - 1) / PF_GROUPS : 0;               // r_i = grp, grp + 8, ...
+            rcnt[jb] = c < PH_NREC ? rcnt_all[jb] : 0;
+            rpair[jb] = pr;
+        }
+    }
+    constexpr int LQ = 6;                             // covers grids up to 6 * 512 / 2 = 1536 blocks
+    const float2* lp = reinterpret_cast<const float2*>((const char*)a.workspace + p.L.lossrec) + tid;
+    const int lcnt = (b == 0 && p.grid * 2 > tid) ? (p.grid * 2 - tid + PF_THREADS - 1) / PF_THREADS : 0;
+    DBG_STAMP(b == 0 && tid == PF_PREP_T0, 10);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (skip_launch(a.skip_if_unit)) return;
+    DBG_STAMP(b == 0 && (tid == 0 || tid == PF_PREP_T0), tid == 0 ? 11 : 12);
+    {
+        // ---- loss (block 0): every record's sum |diff|, weighted by its job; the loads are issued first
+        //      so that they share one L2 round trip with the record loads below --------------------------
+        float lval[LQ];
+        int lid[LQ];
+#pragma unroll
+        for (int m = 0; m < LQ; ++m) {
+            lid[m] = -1; lval[m] = 0.0f;
+            if (m < lcnt) {
+                const float2 q = __ldcg(lp + m * PF_THREADS);
+                lid[m] = __float_as_int(q.x);
+                lval[m] = q.y;
             }
-            s_part[grp][jb][c] = v;
+        }
+        // ---- fixed-order sum of the block records of each (job, image b) pair -------------------------
+        float fv[PLB_MAX_JOBS][PF_FIRST];
+        int ids[PLB_MAX_JOBS];
+        const int lane = tid & 31;
+#pragma unroll
+        for (int jb = 0; jb < PLB_MAX_JOBS; ++jb) {
+            // pair ids of this group's records: lane m loads the id of record m, shared by shuffle below
+            const float* r = rp[jb] + min(lane, PF_FIRST - 1) * (PF_GROUPS * PH_REC_STRIDE) + PH_REC_ID;
+            ids[jb] = (lane < rcnt_all[jb]) ? __float_as_int(__ldcg(r)) : -2;
+#pragma unroll
+            for (int m = 0; m < PF_FIRST; ++m) {
+                fv[jb][m] = 0.0f;
+                if (m < rcnt[jb]) fv[jb][m] = __ldcg(rp[jb] + m * (PF_GROUPS * PH_REC_STRIDE) + c);   // one aligned line per warp
+            }
+        }
+        DBG_STAMP(b == 0 && tid == 0, 16);
+#pragma unroll
+        for (int jb = 0; jb < PLB_MAX_JOBS; ++jb) {
+            float v = 0.0f;
+#pragma unroll
+            for (int m = 0; m < PF_FIRST; ++m) {
+                const int id = __shfl_sync(0xffffffffu, ids[jb], m);
+                v += (id == rpair[jb]) ? fv[jb][m] : 0.0f;
+            }
+            if (jb < a.n_jobs) {
+                for (int m = PF_FIRST; m < rcnt[jb]; ++m) {       // grids with more than 8 * PF_FIRST / 2 blocks per pair
+                    const float* r = rp[jb] + (size_t)m * (PF_GROUPS * PH_REC_STRIDE);
+                    const int id = __float_as_int(__ldcg(r + PH_REC_ID));
+                    const float val = __ldcg(r + c);
+                    v += (id == rpair[jb]) ? val : 0.0f;
+                }
+                s_part[grp][jb][c] = v;
+            }
         }
         if (b == 0) {
             double part = 0.0;
@@ -723,10 +783,10 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
             }
             // grids beyond LQ * PF_THREADS / 2 blocks (never launched today: <= 148 x 8)
             for (int q = tid + LQ * PF_THREADS; q < p.grid * 2; q += PF_THREADS) {
-                const float* r = records + (size_t)q * PH_REC_STRIDE;
-                const int id = __float_as_int(__ldcg(r));
+                const float2 r = __ldcg(lp + (q - tid));
+                const int id = __float_as_int(r.x);
                 const float w = (id >= a.B) ? p.w_e[1] : p.w_e[0];
-                part += (id >= 0) ? (double)__ldcg(r + 1 + PLB_MAX_SRC * 12) * (double)w : 0.0;
+                part += (id >= 0) ? (double)r.y * (double)w : 0.0;
             }
             s_lpart[tid] = part;
         }

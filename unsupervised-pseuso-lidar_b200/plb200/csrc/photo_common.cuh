@@ -19,8 +19,8 @@ __host__ __device__ constexpr int photo_threads(int maxsrc, bool multi) {
 }
 constexpr int PH_MAX_WARPS = 8;
 constexpr int PH_NREC = PLB_MAX_SRC * 12 + 1;  // per (job,image) record: dP[src][12], sum|diff|
-constexpr int PH_REC_STRIDE = 56;
-                                  // floats per (block, set) record: [0]=pair, [1..] values
+constexpr int PH_REC_STRIDE = 64;  // floats per (block, set) record = two 128-byte lines: [0..PH_NREC) values, [PH_REC_ID] pair id
+constexpr int PH_REC_ID = 63;
 #ifndef PH_USE_PDL
 #define PH_USE_PDL 1               // finalize kernel launched as a programmatic dependent of the main kernel
 #endif
@@ -47,6 +47,8 @@ constexpr int PH_REC_STRIDE = 56;
 struct PhotoLayout {
     size_t tickets;   // int32 [n_pairs + 1]
     size_t records;   // float [grid][2][PH_REC_STRIDE]
+    size_t lossrec;   // float2 [grid][2]: (pair id bits, sum |diff|) of every record again, compact: block 0 of the
+                      // finalize kernel reads ALL of them, and a 224-byte stride costs it 32 L1 wavefronts per load
     size_t ws_pose;   // float [n_pairs][MAX_SRC][6] (photo_min.cu)
     size_t ws_loss;   // double [n_pairs]
     size_t gup;       // float [n_jobs][MAX_SCALES][B*H*W]  (only when a low scale carries a gradient)
@@ -103,6 +105,7 @@ static inline PhotoLayout photo_layout(const plb_photo_args& a) {
         if (tiles * a.B > n_rec) n_rec = tiles * a.B;
     }
     L.records = off; off = align_up(off + sizeof(float) * n_rec * PH_REC_STRIDE, 256);
+    L.lossrec = off; off = align_up(off + sizeof(float) * 2 * n_rec, 256);
     L.ws_pose = off; off = align_up(off + sizeof(float) * n_pairs * PLB_MAX_SRC * 6, 256);
     L.ws_loss = off; off = align_up(off + sizeof(double) * n_pairs, 256);
     L.gup = off;
