@@ -12,6 +12,18 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "headline"
 cfg = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
 sets = [synth.to_device(s, dev) for s in bench.make_sets(cfg, 4, 1234, dev)]
+if os.environ.get("DBG_SAME_IMAGES"):
+    # every image of the batch identical (frames, disparity, pose, intrinsics): any remaining spread between the
+    # blocks' finishing times is scheduling, not content
+    def same(t):
+        t[:] = t[:1]
+    for s_ in sets:
+        same(s_["tgt"]); same(s_["poses"]); same(s_["intrinsics"])
+        for r in s_["ref_imgs"]:
+            same(r)
+        for fr in s_["disparity"]:
+            for d in fr:
+                same(d)
 from losses import Losses
 for rep in range(3):
     ms = bench.time_photo_kernel(Losses(), sets, cfg, dev, 64)

@@ -23,7 +23,8 @@ for r in rows:
         hdr = r
         iE, iSm = hdr.index("Instructions Executed"), hdr.index("# Samples")
     elif hdr is not None and r[0].isdigit() and len(r) > iE:
-        lines.append((cur_file, int(r[0]), r[1].strip(), int(r[iE] or 0), int(r[iSm] or 0)))
+        num = lambda v: int(v) if v.strip().lstrip("-").isdigit() else 0
+        lines.append((cur_file, int(r[0]), r[1].strip(), num(r[iE]), num(r[iSm])))
 tot = sum(l[3] for l in lines)
 ts = sum(l[4] for l in lines)
 print("instructions executed %d, samples %d" % (tot, ts))

@@ -6,13 +6,12 @@
 // runs for the [N,4]x[4,4] product - so x,y,z and the validity mask
 // (cloud_x >= 0 & cloud_z < 1) are bit-identical to the reference's.
 //
-// Order-preserving compaction in three launches with no inter-block waiting:
-//   (1) per-tile valid counts.  Validity (cloud_x >= 0 & cloud_z < 1) is decided from a division-free
-//       fp64 evaluation whenever the value is further than 1e-9 from its threshold (the two
-//       evaluations differ by < 1e-12 for |x|, |y|, d below 1e4); only the rare borderline pixel runs
-//       the exact chain - so the mask stays bit-identical to the reference's at a third of the work;
-//   (2) exclusive scan of the tile counts of each image (one warp per image);
-//   (3) every tile computes its points exactly once, and writes them at their final row-major rank;
+// Order-preserving compaction in two launches with no inter-block waiting:
+//   (1) per-tile valid counts.  cloud_x and cloud_z are affine in the depth, so validity (cloud_x >= 0 & cloud_z < 1)
+//       costs two fp64 FMAs per coordinate whenever the value is further than 1e-8 from its threshold; only the rare
+//       borderline pixel runs the exact chain - the mask stays bit-identical to the reference's;
+//   (2) every tile sums the counts of the tiles before it, compacts (pixel, depth) of its valid pixels in shared
+//       memory and evaluates the kept points densely, one per thread, at their final row-major rank;
 //       [0::sparsity] keeps ranks divisible by `sparsity`.  Integer prefix sums: bitwise repeatable.
 #include "common.cuh"
 
@@ -53,18 +52,28 @@ __device__ __forceinline__ void cloud_point(const CloudConst& cc, int col, int r
     }
 }
 
-// One pixel: the point (reference operation order) and its validity (cloud_x >= 0 & cloud_z < 1).
-// The mask must be bit-identical to the reference's and identical in the count and the write launch:
-// a value closer than 1e-9 to its threshold (or a huge / non-finite input) is re-evaluated with IEEE
-// divisions, so the cheap division can never flip a decision.
-__device__ __forceinline__ bool cloud_eval(const CloudConst& cc, int col, int row, float depth, double (&o)[4]) {
-    cloud_point<false>(cc, col, row, depth, o);
-    const bool safe = fabs(o[0]) > 1e-9 && fabs(o[2] - 1.0) > 1e-9 && fabs(o[0]) < 1e12 && fabs(o[2]) < 1e12;
-    if (!safe) cloud_point<true>(cc, col, row, depth, o);
+// Validity of one pixel (cloud_x >= 0 & cloud_z < 1), bit-identical to the reference's and identical in the
+// count and the write launch.  cloud_x and cloud_z are affine in the depth, cloud_k = d * A_k(col, row) + C_k, with
+// A_k affine in (col, row): the host folds the calibration into eight doubles (CloudHost) and a pixel costs two FMAs
+// per tested coordinate.  This re-associated value differs from the reference's chain by < 1e-10 for |d| < 1e5, so it
+// decides whenever it is further than 1e-8 from its threshold; the rare borderline (or huge / non-finite) pixel runs
+// the exact chain with IEEE divisions.
+struct CloudHost {
+    double rf_u, rf_v, b_x, b_y;
+    double a0x, a0y, a0c, c0;          // cloud_x = d * (col * a0x + row * a0y + a0c) + c0
+    double a2x, a2y, a2c, c2;          // cloud_z likewise
+};
+
+__device__ __forceinline__ bool cloud_valid(const CloudConst& cc, const CloudHost& h, int col, int row, double A0, double A2,
+                                            float depth) {
+    const double d = (double)depth;
+    const double v0 = __fma_rn(d, A0, h.c0), v2 = __fma_rn(d, A2, h.c2);
+    const bool safe = fabs(v0) > 1e-8 && fabs(v2 - 1.0) > 1e-8 && fabs(d) < 1e5;      // NaN fails every test
+    if (safe) return v0 >= 0.0 && v2 < 1.0;
+    double o[4];
+    cloud_point<true>(cc, col, row, depth, o);
     return o[0] >= 0.0 && o[2] < 1.0;
 }
-
-struct CloudHost { double rf_u, rf_v, b_x, b_y; };
 
 __device__ __forceinline__ CloudConst cloud_const(const plb_cloud_args& a, const CloudHost& h) {
     CloudConst cc;
@@ -85,6 +94,25 @@ __device__ __forceinline__ void cloud_load(const float* depth, size_t img_off, i
     }
 }
 
+// validity bits of this thread's CL_ITEMS consecutive pixels
+__device__ __forceinline__ unsigned cloud_mask(const CloudConst& cc, const CloudHost& h, int W, int p0, int npx,
+                                               int row, int col, const float (&dv)[CL_ITEMS]) {
+    double A0 = __fma_rn((double)col, h.a0x, __fma_rn((double)row, h.a0y, h.a0c));
+    double A2 = __fma_rn((double)col, h.a2x, __fma_rn((double)row, h.a2y, h.a2c));
+    unsigned vmask = 0;
+#pragma unroll
+    for (int k = 0; k < CL_ITEMS; ++k) {
+        if (p0 + k < npx && cloud_valid(cc, h, col, row, A0, A2, dv[k])) vmask |= 1u << k;
+        if (++col == W) {
+            col = 0; ++row;
+            A0 = __fma_rn((double)row, h.a0y, h.a0c); A2 = __fma_rn((double)row, h.a2y, h.a2c);
+        } else {
+            A0 += h.a0x; A2 += h.a2x;
+        }
+    }
+    return vmask;
+}
+
 // launch 1: valid points per tile
 __global__ void __launch_bounds__(CL_THREADS)
 cloud_count_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) {
@@ -97,14 +125,8 @@ cloud_count_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     const int p0 = blk * CL_TILE + tid * CL_ITEMS;
     float dv[CL_ITEMS];
     cloud_load(depth, (size_t)b * npx, p0, npx, dv);
-    int row = p0 / a.W, col = p0 - row * a.W;
-    int mine = 0;
-#pragma unroll
-    for (int k = 0; k < CL_ITEMS; ++k) {
-        double o[4];
-        if (p0 + k < npx && cloud_eval(cc, col, row, dv[k], o)) ++mine;
-        if (++col == a.W) { col = 0; ++row; }
-    }
+    const int row0 = p0 / a.W;
+    int mine = __popc(cloud_mask(cc, h, a.W, p0, npx, row0, p0 - row0 * a.W, dv));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
     if (lane == 0) s_warp[warp] = mine;
@@ -117,31 +139,11 @@ cloud_count_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     }
 }
 
-// launch 2: counts -> exclusive prefix per image (in place), one warp per image; also the image's point count
-__global__ void __launch_bounds__(32)
-cloud_scan_kernel(const __grid_constant__ plb_cloud_args a, int tiles) {
-    const int b = blockIdx.x, lane = threadIdx.x;
-    int32_t* counts = (int32_t*)a.workspace + (size_t)b * tiles;
-    int carry = 0;
-    for (int base = 0; base < tiles; base += 32) {
-        const int k = base + lane;
-        const int c = k < tiles ? counts[k] : 0;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (k < tiles) counts[k] = carry + incl - c;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0 && a.count != nullptr) {
-        const int sp = a.sparsity > 0 ? a.sparsity : 1;
-        a.count[b] = (carry + sp - 1) / sp;
-    }
-}
-
-// launch 3: points at their final rank
+// launch 2: every tile sums the counts of the tiles before it (a few hundred L2-resident integers: cheaper than a
+// scan launch), compacts the (pixel, depth) pairs of its valid pixels in shared memory in rank order - validity
+// from the same cheap test as launch 1 - and only then evaluates the points, one KEPT point per thread: the exact
+// fp64 chain runs on the ~60 % of the pixels that survive (and, with [0::sparsity], on the kept ranks only),
+// without divergence, and thread j writes output row j.
 __global__ void __launch_bounds__(CL_THREADS)
 cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) {
     const int b = blockIdx.y, blk = blockIdx.x, tiles = gridDim.x;
@@ -149,24 +151,24 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     const int npx = a.H * a.W;
     const CloudConst cc = cloud_const(a, h);
     const float* depth = a.depth + (size_t)b * npx;
-    __shared__ int s_warp[CL_THREADS / 32];
-    const int base = __ldg((const int32_t*)a.workspace + (size_t)b * tiles + blk);
+    __shared__ int s_warp[CL_THREADS / 32], s_pre[CL_THREADS / 32];
+    __shared__ int s_pix[CL_TILE], s_row[CL_TILE];
+    __shared__ float s_dep[CL_TILE];
 
     const int p0 = blk * CL_TILE + tid * CL_ITEMS;
-    double pts[CL_ITEMS][4];
-    unsigned vmask = 0;
+    float dv[CL_ITEMS];
+    cloud_load(depth, (size_t)b * npx, p0, npx, dv);
+    // exclusive prefix of this tile: counts of tiles [0, blk) of image b, fixed order (integers)
     {
-        float dv[CL_ITEMS];
-        cloud_load(depth, (size_t)b * npx, p0, npx, dv);
-        int row = p0 / a.W, col = p0 - row * a.W;
+        const int32_t* counts = (const int32_t*)a.workspace + (size_t)b * tiles;
+        int part = 0;
+        for (int k = tid; k < blk; k += CL_THREADS) part += __ldg(counts + k);
 #pragma unroll
-        for (int k = 0; k < CL_ITEMS; ++k) {
-            if (p0 + k < npx) {
-                if (cloud_eval(cc, col, row, dv[k], pts[k])) vmask |= 1u << k;
-            }
-            if (++col == a.W) { col = 0; ++row; }
-        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_pre[warp] = part;
     }
+    const int row0 = p0 / a.W, col0 = p0 - row0 * a.W;
+    const unsigned vmask = cloud_mask(cc, h, a.W, p0, npx, row0, col0, dv);
     const int mine = __popc(vmask);
     // inclusive scan of `mine` across the warp, then across warps
     int incl = mine;
@@ -177,37 +179,58 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    int warp_off = 0;
+    int warp_off = 0, base = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < CL_THREADS / 32; ++w) {
         const int c = s_warp[w];
         if (w < warp) warp_off += c;
+        total += c;
+        base += s_pre[w];
     }
-    const int lrank0 = warp_off + incl - mine;     // rank of this thread's first valid point inside the tile
     const int sp = a.sparsity > 0 ? a.sparsity : 1;
+    if (blk == tiles - 1 && tid == 0 && a.count != nullptr) a.count[b] = (base + total + sp - 1) / sp;
     if (a.valid != nullptr) {
 #pragma unroll
         for (int k = 0; k < CL_ITEMS; ++k)
             if (p0 + k < npx) a.valid[(size_t)b * npx + p0 + k] = (vmask >> k) & 1u;
     }
-    int rank = base + lrank0;
+    // kept points of this tile: local ranks r with (base + r) % sp == 0, i.e. r = r_first + j * sp
+    int r_first = 0, n_keep = total;
+    if (sp != 1) {
+        r_first = (sp - base % sp) % sp;
+        n_keep = total > r_first ? (total - r_first + sp - 1) / sp : 0;
+    }
+    if (n_keep == 0) return;
+    {
+        int row = row0, col = col0;
+        int r = warp_off + incl - mine;     // local rank of this thread's first valid point
 #pragma unroll
-    for (int k = 0; k < CL_ITEMS; ++k) {
-        if ((vmask >> k) & 1u) {
-            if (rank % sp == 0) {
-                const size_t pos = (size_t)b * npx + rank / sp;
-                if (a.cloud_f64 != nullptr) {
-                    double2* o = reinterpret_cast<double2*>(a.cloud_f64 + pos * 4);
-                    __stcs(o, make_double2(pts[k][0], pts[k][1]));
-                    __stcs(o + 1, make_double2(pts[k][2], pts[k][3]));
-                }
-                if (a.cloud_f32 != nullptr)
-                    __stcs(reinterpret_cast<float4*>(a.cloud_f32) + pos,
-                           make_float4((float)pts[k][0], (float)pts[k][1], (float)pts[k][2], (float)pts[k][3]));
-                if (a.index != nullptr) a.index[pos] = p0 + k;
-            }
-            ++rank;
+        for (int k = 0; k < CL_ITEMS; ++k) {
+            if ((vmask >> k) & 1u) { s_pix[r] = p0 + k; s_row[r] = row; s_dep[r] = dv[k]; ++r; }
+            if (++col == a.W) { col = 0; ++row; }
         }
+    }
+    __syncthreads();
+    const size_t out0 = (size_t)b * npx + (sp == 1 ? (size_t)base : (size_t)(base + r_first) / sp);   // first output row of the tile
+    for (int j = tid; j < n_keep; j += CL_THREADS) {
+        const int r = r_first + j * sp;
+        const int pix = s_pix[r], row = s_row[r], col = pix - row * a.W;
+        const float d = s_dep[r];
+        double o[4];
+        // the reference's operation order with constant-divisor divisions; a coordinate within 1e-9 of its
+        // threshold (or huge) is re-evaluated with IEEE divisions, as the values always were
+        cloud_point<false>(cc, col, row, d, o);
+        const bool safe = fabs(o[0]) > 1e-9 && fabs(o[2] - 1.0) > 1e-9 && fabs(o[0]) < 1e12 && fabs(o[2]) < 1e12;
+        if (!safe) cloud_point<true>(cc, col, row, d, o);
+        const size_t pos = out0 + j;
+        if (a.cloud_f64 != nullptr) {
+            double2* q = reinterpret_cast<double2*>(a.cloud_f64 + pos * 4);
+            __stcs(q, make_double2(o[0], o[1]));
+            __stcs(q + 1, make_double2(o[2], o[3]));
+        }
+        if (a.cloud_f32 != nullptr)
+            __stcs(reinterpret_cast<float4*>(a.cloud_f32) + pos, make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]));
+        if (a.index != nullptr) a.index[pos] = pix;
     }
 }
 
@@ -229,10 +252,16 @@ int cloud_launch(const plb_cloud_args* a, cudaStream_t st) {
     CloudHost h;                                    // IEEE double divisions, as numpy does them (PseudoLiDAR.py:84-85)
     h.rf_u = 1.0 / a->P[0]; h.rf_v = 1.0 / a->P[5];
     h.b_x = a->P[3] / (-a->P[0]); h.b_y = a->P[7] / (-a->P[5]);
+    {
+        // cloud_k = x T[k][0] + y T[k][1] + d T[k][2] + T[k][3],  x = (col - c_u) d / f_u + b_x,  y = (row - c_v) d / f_v + b_y
+        const double c_u = a->P[2], c_v = a->P[6], f_u = a->P[0], f_v = a->P[5];
+        const double* T0 = a->Tinv; const double* T2 = a->Tinv + 8;
+        h.a0x = T0[0] / f_u; h.a0y = T0[1] / f_v; h.a0c = T0[2] - c_u * h.a0x - c_v * h.a0y;
+        h.c0 = h.b_x * T0[0] + h.b_y * T0[1] + T0[3];
+        h.a2x = T2[0] / f_u; h.a2y = T2[1] / f_v; h.a2c = T2[2] - c_u * h.a2x - c_v * h.a2y;
+        h.c2 = h.b_x * T2[0] + h.b_y * T2[1] + T2[3];
+    }
     cloud_count_kernel<<<grid, CL_THREADS, 0, st>>>(*a, h);
-    ++g_launches;
-    PLB_CHECK_LAUNCH();
-    cloud_scan_kernel<<<a->B, 32, 0, st>>>(*a, tiles);
     ++g_launches;
     PLB_CHECK_LAUNCH();
     cloud_write_kernel<<<grid, CL_THREADS, 0, st>>>(*a, h);
