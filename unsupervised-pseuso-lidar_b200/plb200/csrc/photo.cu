@@ -402,8 +402,8 @@ __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairCons
                 }
 #pragma unroll
                 for (int g = 0; g < NP; ++g)
-                    group_pixel<GRAD, IMG_GRAD, 2>(pc, 2 * g, plane, H, W, xf, yf, D, t, w_e, valid, pf, accp[g], l1acc, gp, gt);
-                if (ODD) group_pixel<GRAD, IMG_GRAD, 1>(pc, NSRC - 1, plane, H, W, xf, yf, D, t, w_e, valid, pf, accs, l1acc, gp, gt);
+                    group_pixel<GRAD, IMG_GRAD, 2>(pc, 2 * g, plane, H, W, xf, yf, D, t, w_e, valid, pf && s == 0, accp[g], l1acc, gp, gt);
+                if (ODD) group_pixel<GRAD, IMG_GRAD, 1>(pc, NSRC - 1, plane, H, W, xf, yf, D, t, w_e, valid, pf && s == 0, accs, l1acc, gp, gt);
                 if (GRAD) {
                     float* g = pc.g_disp[s];
                     if (valid && g != nullptr)
