@@ -225,15 +225,21 @@ class FusedLossFn(torch.autograd.Function):
                 g_refs = [torch.zeros_like(r) for r in refs]
         scratch = torch.empty(2, dtype=torch.float32, device=dev)
         _launch_loss(cfg, tgt, refs, poses, K, pyr, True, g_pyr, g_poses, g_tgt, g_refs, scratch, up, skip)
+        # the gradient buffers leave with autograd: holding on to them would make AccumulateGrad CLONE every one of
+        # them into .grad (a device copy per tensor) instead of adopting the buffer
+        ctx.tensors = (tgt, refs, poses, K, pyr, None, None)
         need = ctx.needs_input_grad
         grads = [None, g_tgt if need[1] else None, g_poses if need[2] else None, None]
         for i in range(cfg.n_src):
             grads.append(g_refs[i] if (need[4 + i] and g_refs is not None) else None)
         k = 4 + cfg.n_src
-        for j, p in enumerate(g_pyr):
-            for s, g in enumerate(p):
+        for p in g_pyr:
+            while p:
+                g = p.pop(0)
                 grads.append(g if need[k] else None)
                 k += 1
+            del g
+        del g_pyr, g_poses, g_tgt, g_refs
         return tuple(grads)
 
 
