@@ -1,198 +1,201 @@
 // Second-order depth smoothness (losses.py:242-260), all scales of the pyramid,
 // loss and gradient in one launch.  disp -> depth is folded in.
 //
-// One block = one 64x16 tile of one scale of one image.  The depth tile plus a
-// 2-pixel halo is staged in shared memory once; every pixel then evaluates the
-// four second differences anchored on it (forward sums) and gathers the signs
-// of the <= 14 second differences it takes part in (gradient) - no atomics, no
-// scatter, bitwise repeatable.
+// Streaming stencil, no shared-memory tiles and no block barriers in the loop.  One warp owns a strip of 28
+// columns (lanes 2..29; lanes 0, 1, 30, 31 are the halo) and a chunk of SW_ROWS rows, and walks DOWN it with the
+// depth rows y, y+1, y+2 in registers (one new row per step, loaded two steps ahead).  Per step every lane
+// evaluates the four second differences ANCHORED on its pixel of row y once (neighbours by shuffle): |.| goes to
+// the forward sums of the owned anchors, the signs stay in registers.  The gradient of pixel (x, y) is the signed
+// stencil over the anchors that contain it - columns x, x-1, x-2 of this row (shuffles) and rows y-1, y-2 (the
+// signs kept from the previous two steps) - so it is complete the moment row y has been processed; a chunk starts
+// two rows early to have those signs.  No atomics, fixed-order reductions: bitwise repeatable.
 #include "common.cuh"
 
 namespace plb {
 
-constexpr int SM_TW = 64, SM_TH = 16, SM_HALO = 2, SM_THREADS = 256, SM_ROWS = 4;
-constexpr int SM_SW = SM_TW + 2 * SM_HALO;  // 68
-constexpr int SM_SH = SM_TH + 2 * SM_HALO;  // 20
+constexpr int SW_THREADS = 256, SW_WARPS = SW_THREADS / 32;
+constexpr int SW_OWN = 28;                 // owned columns per warp (lanes 2..29)
+#ifndef SW_AHEAD
+#define SW_AHEAD 2                         // rows in flight beyond the three in use
+#endif
+#ifndef SW_ROWS
+#define SW_ROWS 16                         // owned rows per warp
+#endif
 
-struct SmoothLayout {
-    size_t ticket;    // int32[1]
-    size_t partials;  // float [blocks][4]
-    size_t total;
-    int tiles_x[PLB_MAX_SCALES], tiles[PLB_MAX_SCALES], first_block[PLB_MAX_SCALES + 1];
+struct SmoothLaunch {
+    int n_units, grid;
+    int first_unit[PLB_MAX_SCALES + 1];
+    int strips[PLB_MAX_SCALES], chunks[PLB_MAX_SCALES];
+    float c1[PLB_MAX_SCALES], c2[PLB_MAX_SCALES], c3[PLB_MAX_SCALES];   // weight_s / element count of each difference map
 };
 
-__host__ __device__ inline SmoothLayout smooth_layout(const plb_smooth_args& a) {
-    SmoothLayout L;
-    int nb = 0;
+static SmoothLaunch smooth_plan(const plb_smooth_args& a) {
+    SmoothLaunch L;
+    int n = 0;
+    float wscale = 1.0f;
     for (int s = 0; s < PLB_MAX_SCALES; ++s) {
-        L.first_block[s] = nb;
+        L.first_unit[s] = n;
+        L.strips[s] = L.chunks[s] = 0;
+        L.c1[s] = L.c2[s] = L.c3[s] = 0.0f;
         if (s < a.n_scales) {
-            L.tiles_x[s] = (a.dw[s] + SM_TW - 1) / SM_TW;
-            L.tiles[s] = L.tiles_x[s] * ((a.dh[s] + SM_TH - 1) / SM_TH);
-            nb += L.tiles[s] * a.B;
-        } else {
-            L.tiles_x[s] = L.tiles[s] = 0;
+            const int h = a.dh[s], w = a.dw[s];
+            L.strips[s] = (w + SW_OWN - 1) / SW_OWN;
+            L.chunks[s] = (h + SW_ROWS - 1) / SW_ROWS;
+            n += L.strips[s] * L.chunks[s] * a.B;
+            L.c1[s] = wscale / ((float)a.B * (float)h * (float)(w - 2));
+            L.c2[s] = wscale / ((float)a.B * (float)(h - 1) * (float)(w - 1));
+            L.c3[s] = wscale / ((float)a.B * (float)(h - 2) * (float)w);
+            wscale /= a.scale_decay;
         }
     }
-    L.first_block[PLB_MAX_SCALES] = nb;
-    L.ticket = 0;
-    L.partials = 256;
-    L.total = 256 + ((size_t)nb * 4 * sizeof(float) + 255) / 256 * 256;
+    L.first_unit[PLB_MAX_SCALES] = n;
+    L.n_units = n;
+    L.grid = (n + SW_WARPS - 1) / SW_WARPS;
     return L;
 }
 
-__device__ __forceinline__ float sgnf(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+// workspace: int32 ticket | double partials[grid]
+static size_t smooth_ws_bytes(const SmoothLaunch& L) { return 256 + ((size_t)L.grid * sizeof(double) + 255) / 256 * 256; }
 
-// sign codes of the four second differences anchored on one pixel, 2 bits each (0:-1, 1:0, 2:+1)
-__device__ __forceinline__ unsigned sgn2(float v) { return v > 0.0f ? 2u : (v < 0.0f ? 0u : 1u); }
-__device__ __forceinline__ float unsgn(unsigned code, int shift) { return (float)(int)((code >> shift) & 3u) - 1.0f; }
+// sign(v) with sign(0) = 0 (and sign(NaN) = +-1, as any non-zero): one compare, one select, one bit merge
+__device__ __forceinline__ float sgnf(float v) {
+    return __int_as_float((__float_as_int(v) & 0x80000000) | (v != 0.0f ? 0x3f800000 : 0));
+}
 
-__global__ void __launch_bounds__(SM_THREADS)
-smooth_kernel(const __grid_constant__ plb_smooth_args a, int n_tiles) {
+__global__ void __launch_bounds__(SW_THREADS)
+smooth_kernel(const __grid_constant__ plb_smooth_args a, const __grid_constant__ SmoothLaunch L) {
     if (skip_launch(a.skip_if_unit)) return;
-    const SmoothLayout L = smooth_layout(a);
-    int32_t* ticket = (int32_t*)((char*)a.workspace + L.ticket);
-    float* partials = (float*)((char*)a.workspace + L.partials);
+    int32_t* ticket = (int32_t*)a.workspace;
+    double* partials = (double*)((char*)a.workspace + 256);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    __shared__ float sD[SM_SH][SM_SW];                       // depth, tile + 2-pixel halo
-    // signs of the second differences anchored at (x-2.., y-2..): d2/dx2, d2/dy2, dxdy + dydx
-    __shared__ signed char sS1[SM_TH + SM_HALO][SM_TW + SM_HALO + 2], sS3[SM_TH + SM_HALO][SM_TW + SM_HALO + 2],
-        sSm[SM_TH + SM_HALO][SM_TW + SM_HALO + 2];
-    __shared__ double s_fin[SM_THREADS];
+    __shared__ double s_fin[SW_THREADS];
     __shared__ int s_flag;
 
-    const float up = a.upstream ? __ldg(a.upstream) : 1.0f;
-    double total = 0.0;   // this thread's share of the (weight/count-scaled) forward sums
-
-    // persistent: block k takes tiles k, k + grid, ... (a tile = 64x16 pixels of one scale of one image)
-#pragma unroll 1
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    double total = 0.0;   // this lane's share of the (weight / count-scaled) forward sums
+    const int u = blockIdx.x * SW_WARPS + warp;
+    if (u < L.n_units) {
         int s = 0;
-        while (s + 1 < a.n_scales && t >= L.first_block[s + 1]) ++s;
-        const int local = t - L.first_block[s];
-        const int b = local / L.tiles[s], tile = local % L.tiles[s];
+        while (s + 1 < a.n_scales && u >= L.first_unit[s + 1]) ++s;
+        const int local = u - L.first_unit[s];
+        const int strips = L.strips[s], per_img = strips * L.chunks[s];
+        const int b = local / per_img, rem = local - b * per_img;
+        const int chunk = rem / strips, strip = rem - chunk * strips;      // consecutive warps: adjacent strips of the same rows
         const int h = a.dh[s], w = a.dw[s];
-        const int tx0 = (tile % L.tiles_x[s]) * SM_TW, ty0 = (tile / L.tiles_x[s]) * SM_TH;
-        const float* disp = a.disp[s] + (size_t)b * h * w;   // (image planes stay below 2^31 elements: checked at launch)
-        const bool want = a.want_grad && a.g_disp[s] != nullptr;
+        const int x = strip * SW_OWN - 2 + lane;
+        const int y0 = chunk * SW_ROWS, y1 = min(y0 + SW_ROWS, h);
+        const int ystart = max(y0 - 2, 0);
+        const bool colin = x >= 0 && x < w;
+        const int ylast = min(y1 + 1, h - 1);
+        const bool own_lane = lane >= 2 && lane < 2 + SW_OWN && colin;
+        const float* disp = a.disp[s] + (size_t)b * h * w + (colin ? x : 0);
+        float* gout = (a.want_grad && a.g_disp[s] != nullptr) ? a.g_disp[s] + (size_t)b * h * w + (colin ? x : 0) : nullptr;
+        const bool is_depth = a.input_is_depth != 0;
+        const float da = a.disp_a, db = a.disp_b;
+        const float up = a.upstream ? __ldg(a.upstream) : 1.0f;
+        const float c1 = L.c1[s], c2 = L.c2[s], c3 = L.c3[s];
+        const float g1 = c1 * up, g2 = c2 * up, g3 = c3 * up;
+        const bool rmw = own_lane && gout != nullptr && a.accumulate != 0;
 
-        // issue every global read of the tile up front: the depth tile and (accumulate mode) the
-        // gradient values this thread will add to - one memory round trip per tile instead of two
-        const int px = tx0 + (warp & 1) * 32 + lane;
-        float old[SM_ROWS];
+        // register queue: rows y, y+1, y+2 in use, SW_AHEAD more in flight; the loop is unrolled by the queue length so
+        // that the rotation costs nothing, and the row pointers advance by w per step (no per-step multiplications)
+        constexpr int NQ = 3 + SW_AHEAD;
+        float q[NQ], oq[NQ];
+        const float* prow = disp + (size_t)ystart * w;       // next depth row to load
+        int yload = ystart;
+        auto loadrow = [&]() -> float {                       // rows the chunk needs: [ystart, y1 + 1] inside the image
+            float v = 0.0f;
+            if (yload <= ylast) {                             // warp-uniform
+                if (colin) v = __ldg(prow);                   // RAW value: converted when it enters the window, not here -
+                                                              // a use right behind the load would stall the warp on it
+            }
+            prow += w; ++yload;
+            return v;
+        };
+        const float* pold = gout != nullptr ? gout + (size_t)ystart * w : nullptr;   // next gradient row to pre-load (accumulate mode)
+        int yold = ystart;
+        auto loadold = [&]() -> float {
+            float v = 0.0f;
+            if (yold >= y0 && yold < y1) {                    // warp-uniform
+                if (rmw) v = __ldcg(pold);
+            }
+            pold += w; ++yold;
+            return v;
+        };
 #pragma unroll
-        for (int j = 0; j < SM_ROWS; ++j) {
-            const int y = ty0 + (warp >> 1) * SM_ROWS + j;
-            old[j] = (want && a.accumulate && px < w && y < h)
-                         ? __ldcg(a.g_disp[s] + (b * h * w + y * w + px)) : 0.0f;
-        }
-        // tile + halo: warp w takes rows w, w+8, w+16; lanes take columns lane, lane+32, lane+64
-        for (int ly = warp; ly < SM_SH; ly += SM_THREADS / 32) {
-            const int gy = ty0 + ly - SM_HALO;
-            const bool rowin = gy >= 0 && gy < h;
-            const float* drow = disp + gy * w;
+        for (int k = 0; k < NQ; ++k) { q[k] = loadrow(); oq[k] = loadold(); }
+        float s3_m1 = 0.0f, s3_m2 = 0.0f, sm_m1 = 0.0f;      // signs of the anchors one / two rows up
+        float sum1 = 0.0f, summ = 0.0f, sum3 = 0.0f;
+        const bool x1ok = colin && x <= w - 3, xmok = colin && x <= w - 2;
+        float* pout = gout != nullptr ? gout + (size_t)ystart * w : nullptr;
+        auto conv = [&](float v, int y) -> float {            // disparity -> depth; 0 outside the image, as the loads give
+            return (is_depth || !colin || y > ylast) ? v : rcp_nr(fmaf(da, v, db));
+        };
+        float r0 = conv(q[0], ystart), r1 = conv(q[1], ystart + 1);      // rows y, y + 1 of the window (converted)
+        auto step = [&](int y, float raw2, float old) {
+            const float r2 = conv(raw2, y + 2);
+            const bool owned = own_lane && y >= y0;
+            const float d01 = __shfl_down_sync(0xffffffffu, r0, 1), d02 = __shfl_down_sync(0xffffffffu, r0, 2);
+            const float d11 = __shfl_down_sync(0xffffffffu, r1, 1);
+            const float e0 = d01 - r0, e1 = r1 - r0;          // first differences anchored on (x, y)
+            const float v1 = x1ok ? (d02 - d01) - e0 : 0.0f;
+            const float v3 = (colin && y <= h - 3) ? (r2 - r1) - e1 : 0.0f;
+            const bool mixed = xmok && y <= h - 2;
+            const float vm1 = mixed ? (d11 - r1) - e0 : 0.0f;
+            const float vm2 = mixed ? (d11 - d01) - e1 : 0.0f;
+            const float s1 = sgnf(v1), s3 = sgnf(v3), sm = sgnf(vm1) + sgnf(vm2);
+            if (owned) {
+                sum1 += fabsf(v1); sum3 += fabsf(v3); summ += fabsf(vm1) + fabsf(vm2);
+            }
+            const float s1_l1 = __shfl_up_sync(0xffffffffu, s1, 1), s1_l2 = __shfl_up_sync(0xffffffffu, s1, 2);
+            const float sm_l1 = __shfl_up_sync(0xffffffffu, sm, 1), smp_l1 = __shfl_up_sync(0xffffffffu, sm_m1, 1);
+            if (owned && pout != nullptr) {
+                const float t1 = s1 - 2.0f * s1_l1 + s1_l2;
+                const float t3 = s3 - 2.0f * s3_m1 + s3_m2;
+                const float tm = (sm - sm_l1) - (sm_m1 - smp_l1);
+                float g = fmaf(g1, t1, fmaf(g3, t3, g2 * tm));
+                if (!is_depth) g *= -da * r0 * r0;
+                *pout = old + g;
+            }
+            if (pout != nullptr) pout += w;
+            s3_m2 = s3_m1; s3_m1 = s3; sm_m1 = sm;
+            r0 = r1; r1 = r2;
+        };
+        int y = ystart;
+#pragma unroll 1
+        while (y < y1) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int lx = lane + 32 * c;
-                if (lx < SM_SW) {
-                    const int gx = tx0 + lx - SM_HALO;
-                    float v = 0.0f;
-                    if (rowin && gx >= 0 && gx < w) {
-                        v = __ldg(drow + gx);
-                        if (!a.input_is_depth) v = rcp_nr(fmaf(a.disp_a, v, a.disp_b));
-                    }
-                    sD[ly][lx] = v;
+            for (int k = 0; k < NQ; ++k) {
+                if (y < y1) {                                 // warp-uniform
+                    step(y, q[(k + 2) % NQ], oq[k]);
+                    q[k] = loadrow(); oq[k] = loadold();      // slot k now holds row y + NQ
+                    ++y;
                 }
             }
         }
-        __syncthreads();
-
-        // weights of the four terms: weight_s / element count of each difference map
-        float wscale = 1.0f;
-        for (int k = 0; k < s; ++k) wscale /= a.scale_decay;
-        const float n1 = (float)a.B * (float)h * (float)(w - 2);
-        const float n2 = (float)a.B * (float)(h - 1) * (float)(w - 1);
-        const float n3 = (float)a.B * (float)(h - 2) * (float)w;
-        const float c1 = wscale / n1, c2 = wscale / n2, c3 = wscale / n3;
-
-        // ---- pass 1: every anchor (tile + the 2 columns / rows before it) evaluates its four
-        // second differences once: |.| -> forward sums (anchors inside the tile), signs -> sS planes
-        float sum_dx2 = 0.0f, sum_mixed = 0.0f, sum_dy2 = 0.0f;
-        for (int ay = warp; ay < SM_TH + SM_HALO; ay += SM_THREADS / 32) {
-            const int gy = ty0 + ay - SM_HALO;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int ax = lane + 32 * c;
-                if (ax < SM_TW + SM_HALO) {
-                    const int gx = tx0 + ax - SM_HALO;
-                    int s1 = 0, s3 = 0, sm = 0;
-                    if (gx >= 0 && gy >= 0 && gx < w && gy < h) {
-                        const float d00 = sD[ay][ax], d01 = sD[ay][ax + 1], d02 = sD[ay][ax + 2];
-                        const float d10 = sD[ay + 1][ax], d11 = sD[ay + 1][ax + 1], d20 = sD[ay + 2][ax];
-                        const bool own = ax >= SM_HALO && ay >= SM_HALO;
-                        const float o1 = own ? 1.0f : 0.0f;
-                        float v;
-                        v = (gx <= w - 3) ? (d02 - d01) - (d01 - d00) : 0.0f;
-                        s1 = (v > 0.0f) - (v < 0.0f); sum_dx2 = fmaf(o1, fabsf(v), sum_dx2);
-                        v = (gy <= h - 3) ? (d20 - d10) - (d10 - d00) : 0.0f;
-                        s3 = (v > 0.0f) - (v < 0.0f); sum_dy2 = fmaf(o1, fabsf(v), sum_dy2);
-                        const bool mixed = gx <= w - 2 && gy <= h - 2;
-                        v = mixed ? (d11 - d10) - (d01 - d00) : 0.0f;
-                        sm = (v > 0.0f) - (v < 0.0f); sum_mixed = fmaf(o1, fabsf(v), sum_mixed);
-                        v = mixed ? (d11 - d01) - (d10 - d00) : 0.0f;
-                        sm += (v > 0.0f) - (v < 0.0f); sum_mixed = fmaf(o1, fabsf(v), sum_mixed);
-                    }
-                    sS1[ay][ax] = (signed char)s1; sS3[ay][ax] = (signed char)s3; sSm[ay][ax] = (signed char)sm;
-                }
-            }
-        }
-        total += (double)(sum_dx2 * c1) + (double)(sum_mixed * c2) + (double)(sum_dy2 * c3);
-        __syncthreads();
-
-        // ---- pass 2: gradient of every tile pixel = signed stencil over the anchors containing it
-        if (want) {
-            const int lx = (warp & 1) * 32 + lane + SM_HALO;
-            const float g1 = c1 * up, g2 = c2 * up, g3 = c3 * up;
-#pragma unroll
-            for (int j = 0; j < SM_ROWS; ++j) {
-                const int ly = (warp >> 1) * SM_ROWS + j + SM_HALO;
-                const int y = ty0 + (warp >> 1) * SM_ROWS + j;
-                if (px >= w || y >= h) continue;
-                const int t1 = (int)sS1[ly][lx] - 2 * (int)sS1[ly][lx - 1] + (int)sS1[ly][lx - 2];
-                const int t3 = (int)sS3[ly][lx] - 2 * (int)sS3[ly - 1][lx] + (int)sS3[ly - 2][lx];
-                const int tm = (int)sSm[ly][lx] - (int)sSm[ly][lx - 1] - (int)sSm[ly - 1][lx] + (int)sSm[ly - 1][lx - 1];
-                float g = fmaf(g1, (float)t1, fmaf(g3, (float)t3, g2 * (float)tm));
-                if (!a.input_is_depth) { const float D = sD[ly][lx]; g *= -a.disp_a * D * D; }
-                a.g_disp[s][b * h * w + y * w + px] = old[j] + g;
-            }
-        }
-        __syncthreads();   // sD / sS are rewritten by the next tile
+        total = (double)(sum1 * c1) + (double)(summ * c2) + (double)(sum3 * c3);
     }
 
     // ---- block partial (fixed order), then the last block sums all partials in double ----------
-    s_fin[tid] = total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) s_fin[warp] = total;
     __syncthreads();
-    for (int st = SM_THREADS / 2; st > 0; st >>= 1) {
-        if (tid < st) s_fin[tid] += s_fin[tid + st];
-        __syncthreads();
-    }
     if (tid == 0) {
-        __stcg((double*)partials + blockIdx.x, s_fin[0]);
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < SW_WARPS; ++k) t += s_fin[k];
+        __stcg(partials + blockIdx.x, t);
         __threadfence();
         s_flag = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
     }
     __syncthreads();
     if (!s_flag) return;
     __threadfence();
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int k = tid; k < (int)gridDim.x; k += 2 * SM_THREADS) {
-        acc0 += __ldcg((const double*)partials + k);
-        if (k + SM_THREADS < (int)gridDim.x) acc1 += __ldcg((const double*)partials + k + SM_THREADS);
-    }
-    s_fin[tid] = acc0 + acc1;
+    double acc = 0.0;
+    for (int k = tid; k < (int)gridDim.x; k += SW_THREADS) acc += __ldcg(partials + k);
+    s_fin[tid] = acc;
     __syncthreads();
-    for (int st = SM_THREADS / 2; st > 0; st >>= 1) {
+    for (int st = SW_THREADS / 2; st > 0; st >>= 1) {
         if (tid < st) s_fin[tid] += s_fin[tid + st];
         __syncthreads();
     }
@@ -211,16 +214,14 @@ int smooth_launch(const plb_smooth_args* a, cudaStream_t st) {
         if ((long long)a->B * a->dh[s] * a->dw[s] >= (1LL << 31)) return PLB_EINVAL;
     }
     if (a->loss == nullptr) return PLB_ENULL;
-    const SmoothLayout L = smooth_layout(*a);
-    if (a->workspace == nullptr || a->workspace_bytes < L.total) return PLB_EWORKSPACE;
-    const int n_tiles = L.first_block[PLB_MAX_SCALES];
-    const int grid = n_tiles < 148 * 4 ? n_tiles : 148 * 4;   // persistent: at most 4 blocks per SM
-    smooth_kernel<<<grid, SM_THREADS, 0, st>>>(*a, n_tiles);
+    const SmoothLaunch L = smooth_plan(*a);
+    if (a->workspace == nullptr || a->workspace_bytes < smooth_ws_bytes(L)) return PLB_EWORKSPACE;
+    smooth_kernel<<<L.grid, SW_THREADS, 0, st>>>(*a, L);
     ++g_launches;
     PLB_CHECK_LAUNCH();
     return PLB_OK;
 }
 
-size_t smooth_workspace_bytes(const plb_smooth_args* a) { return smooth_layout(*a).total; }
+size_t smooth_workspace_bytes(const plb_smooth_args* a) { return smooth_ws_bytes(smooth_plan(*a)); }
 
 }  // namespace plb
