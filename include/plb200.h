@@ -35,6 +35,9 @@ extern "C" {
 /* rotation_mode */
 #define PLB_ROT_AXISANGLE 0 /* live: transformation_from_parameters, geometry/pose_geometry.py:124-199 */
 #define PLB_ROT_EULER 1     /* dormant: pose_vec2mat / euler2mat, geometry/pose_geometry.py:38-108 */
+#define PLB_INPUT_DISP 0
+#define PLB_INPUT_DEPTH 1
+#define PLB_INPUT_LOGIT 2
 
 /* plb_photo_job.mode */
 #define PLB_PHOTO_L1_MEAN 0 /* live: nn.L1Loss per (scale, source), mean over sources: losses.py:223-228 */
@@ -83,8 +86,12 @@ typedef struct plb_photo_args {
     int32_t n_pose;            /* poses is [B,n_pose,6] (rot3 | trans3)                           */
     int32_t rotation_mode;     /* PLB_ROT_*                                                        */
     int32_t k_is_f64;          /* intrinsics dtype                                                 */
-    int32_t input_is_depth;    /* 0: depth = 1/(disp_a*disp+disp_b); 1: `disp` already holds depth */
+    int32_t input_is_depth;    /* PLB_INPUT_DISP 0: depth = 1/(disp_a*disp+disp_b); PLB_INPUT_DEPTH 1: `disp` already holds
+                                  depth; PLB_INPUT_LOGIT 2: `disp` holds the disparity head's pre-activation x and
+                                  disp = head_alpha*sigmoid(x)+head_beta is folded in too (models/depth/disp_net.py:121-139;
+                                  gradients are then with respect to x)                             */
     float disp_a, disp_b;      /* 10, 0.01 in the reference                                        */
+    float head_alpha, head_beta; /* 10, 0.01 in the reference's DispNet (PLB_INPUT_LOGIT only)      */
     int32_t want_grad;         /* 0: loss only (no_grad / eval)                                    */
     int32_t deterministic;     /* reserved (loss, pose and disparity gradients are always
                                   bitwise repeatable; image gradients use float atomics)            */
@@ -118,8 +125,9 @@ typedef struct plb_smooth_args {
     int32_t dw[PLB_MAX_SCALES];
     float* g_disp[PLB_MAX_SCALES];      /* out; NULL = not wanted                                  */
     int32_t accumulate;                 /* 1: g_disp += grad, 0: g_disp = grad                      */
-    int32_t input_is_depth;
+    int32_t input_is_depth;             /* PLB_INPUT_* as in plb_photo_args                         */
     float disp_a, disp_b;
+    float head_alpha, head_beta;
     float scale_decay;                  /* 2.3 in the reference (losses.py:259)                     */
     int32_t want_grad;
     float* loss;                        /* out (written) [1]                                        */

@@ -401,3 +401,14 @@ def project_velo_to_img(point_cloud, T, P, width, height):
     has = winner >= 0
     depth[has] = xyz[winner[has], 2]
     return np.transpose(depth.reshape(width, height)), winner.reshape(width, height).T
+
+
+# --------------------------------------------------------------------------
+# models/depth/disp_net.py:121-139  (the disparity head in front of the loss)
+# --------------------------------------------------------------------------
+
+def disp_head(x, alpha=10.0, beta=0.01):
+    """`models/depth/disp_net.py:121,127,133,139`: `disp = self.alpha * predict_disp(out) + self.beta`, where
+    `predict_disp` ends in `nn.Sigmoid()` (`:24-28`) and `alpha = 10`, `beta = 0.01` (`:53-57`).  `x` is the
+    convolution output in front of the sigmoid."""
+    return alpha * torch.sigmoid(x) + beta

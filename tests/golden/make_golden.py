@@ -211,6 +211,26 @@ def velo_case(ref_unused, name):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+def head_case(name):
+    """The disparity head `alpha * sigmoid(conv) + beta` of the UNMODIFIED `models/depth/disp_net.py::DispNetS`
+    (`:121-139`): the pre-activation of two scales (forward hooks on the convolution in front of the sigmoid) and
+    the disparities the network returns for them."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_disp_net", os.path.join(reference_shim.REFERENCE_ROOT, "models", "depth", "disp_net.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(3)
+    net = mod.DispNetS().train()
+    cap = {}
+    net.predict_disp1[0].register_forward_hook(lambda m, i, o: cap.__setitem__("x1", o.detach().clone()))
+    net.predict_disp3[0].register_forward_hook(lambda m, i, o: cap.__setitem__("x3", o.detach().clone()))
+    with torch.no_grad():
+        out = net(torch.randn(2, 3, 64, 128))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x1=cap["x1"].numpy(), disp1=out[0].numpy(),
+                        x3=cap["x3"].numpy(), disp3=out[2].numpy())
+    print(name, [tuple(o.shape) for o in out])
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)  # fixed reduction order for the committed vectors
@@ -222,6 +242,7 @@ def main():
     dormant_case(ref, "dormant_b4_s2_32x48", 4, 32, 48, 2, seed=31)
     cloud_case(ref, "cloud_kitti")
     velo_case(ref, "velo_kitti")
+    head_case("head_dispnet")
     ref = reference_shim.load(patch_batch=True)
     live_case(ref, "live_b2_s2_32x48_patched", 2, 32, 48, 2, seed=14, regime="trained")
     live_case(ref, "live_b3_s1_24x40_patched", 3, 24, 40, 1, seed=15, regime="trained")

@@ -1,0 +1,107 @@
+"""GPU parity of the disparity head folded into the loss: the kernels take the
+depth network's pre-activation maps x, evaluate disp = alpha * sigmoid(x) + beta (models/depth/disp_net.py:121-139)
+themselves and return d loss / d x.  Checked against the oracle composition `disp_head -> losses_forward` under
+torch autograd (fp32 and, for the tolerance, fp64)."""
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _logits(inp, seed):
+    """Pre-activations whose head output IS the synthetic (smooth, road-scene-like) disparity of the other parity
+    tests, clamped into the head's range (beta, alpha + beta): x = logit((d - beta) / alpha)."""
+    out = []
+    for fr in inp["disparity"]:
+        out.append([torch.logit((d.clamp(0.012, 0.1) - 0.01) / 10.0) for d in fr])
+    return out
+
+
+@pytest.mark.parametrize("B,H,W,S", [(2, 32, 48, 1), (3, 48, 96, 3), (2, 192, 640, 4)])
+def test_live_loss_with_head_vs_oracle(B, H, W, S):
+    from losses import Losses
+    from plb200 import synth
+    from oracle import restated as O
+    inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=S, seed=500 + H, n_depth_frames=2)
+    x = _logits(inp, 7 + S)
+
+    def oracle(dtype):
+        c = lambda t: t.to(dtype)
+        rx = [[c(t).clone().requires_grad_(True) for t in fr] for fr in x]
+        rp = c(inp["poses"]).clone().requires_grad_(True)
+        disp = [[O.disp_head(t) for t in fr] for fr in rx]
+        loss = O.losses_forward(c(inp["tgt"]), [c(r) for r in inp["ref_imgs"]], disp, rp, inp["intrinsics"])
+        sum(loss).backward()
+        return loss, rp, rx
+    l32, p32, x32 = oracle(torch.float32)
+    _, p64, x64 = oracle(torch.float64)
+    dev = torch.device("cuda:0")
+    gx = [[t.to(dev).requires_grad_(True) for t in fr] for fr in x]
+    gp = inp["poses"].to(dev).requires_grad_(True)
+    loss = Losses(disp_head=(10.0, 0.01)).forward(inp["tgt"].to(dev), [r.to(dev) for r in inp["ref_imgs"]], gx, gp,
+                                                  inp["intrinsics"].to(dev), None)
+    sum(loss).backward()
+    for k in range(2):
+        assert abs(float(loss[k]) - float(l32[k])) <= LOSS_TOL * abs(float(l32[k])), k
+    e32 = rel_err(p32.grad, p64.grad)
+    assert rel_err(gp.grad.cpu(), p64.grad) < max(GRAD_TOL, 3 * e32), e32
+    for f, fr in enumerate(gx):
+        for s, t in enumerate(fr):
+            e = rel_err(x32[f][s].grad, x64[f][s].grad)
+            assert rel_err(t.grad.cpu(), x64[f][s].grad) < max(GRAD_TOL, 3 * e), (f, s, e)
+
+
+def test_head_equals_explicit_disparity():
+    """Fused head == the same kernels fed alpha * sigmoid(x) + beta computed by torch, gradient chained by autograd."""
+    from losses import Losses
+    from plb200 import synth
+    dev = torch.device("cuda:0")
+    inp = synth.to_device(synth.make_photo_inputs(2, 64, 128, n_src=2, n_scales=2, seed=9, n_depth_frames=2), dev)
+    x = [[(torch.randn_like(d) - 3.0) for d in fr] for fr in inp["disparity"]]
+    outs = []
+    for fused in (True, False):
+        xs = [[t.clone().requires_grad_(True) for t in fr] for fr in x]
+        p = inp["poses"].clone().requires_grad_(True)
+        if fused:
+            loss = Losses(disp_head=(10.0, 0.01)).forward(inp["tgt"], inp["ref_imgs"], xs, p, inp["intrinsics"], None)
+        else:
+            disp = [[10.0 * torch.sigmoid(t) + 0.01 for t in fr] for fr in xs]
+            loss = Losses().forward(inp["tgt"], inp["ref_imgs"], disp, p, inp["intrinsics"], None)
+        sum(loss).backward()
+        outs.append((loss, p.grad, [t.grad for fr in xs for t in fr]))
+    (la, pa, ga), (lb, pb, gb) = outs
+    for k in range(2):
+        assert abs(float(la[k]) - float(lb[k])) <= 2e-6 * abs(float(lb[k]))
+    assert rel_err(pa, pb) < 2e-5
+    for a, b in zip(ga, gb):
+        assert rel_err(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_head_in_min_reprojection_mode(S):
+    """The SSIM / min-reprojection / automask kernel with the head folded in == the same kernel fed the disparity
+    torch computed (selections are identical: both see the same depth up to rounding of the sigmoid)."""
+    from plb200 import ops, synth, _lib
+    dev = torch.device("cuda:0")
+    inp = synth.to_device(synth.make_photo_inputs(2, 48, 96, n_src=2, n_scales=S, seed=21, n_depth_frames=1), dev)
+    x = [torch.logit((d.clamp(0.012, 0.1) - 0.01) / 10.0) for d in inp["disparity"][0]]
+    outs = []
+    for fused in (True, False):
+        xs = [t.clone().requires_grad_(True) for t in x]
+        p = inp["poses"].clone().requires_grad_(True)
+        pyr = [xs] if fused else [[10.0 * torch.sigmoid(t) + 0.01 for t in xs]]
+        loss, _ = ops.fused_losses(inp["tgt"], inp["ref_imgs"], pyr, p, inp["intrinsics"], do_smooth=False,
+                                   mode=_lib.PHOTO_MIN_REPROJ, disp_head=(10.0, 0.01) if fused else None)
+        loss.backward()
+        outs.append((loss, p.grad, [t.grad for t in xs]))
+    (la, pa, ga), (lb, pb, gb) = outs
+    assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
+    assert rel_err(pa, pb) < 1e-3          # a flipped min / mask selection moves the pose gradient (see test_gpu_dormant)
+    for a, b in zip(ga, gb):
+        bad = int(((a - b).abs() > 1e-4 * float(b.abs().max())).sum())
+        assert bad <= max(16, int(5e-4 * b.numel())), bad

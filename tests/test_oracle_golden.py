@@ -119,6 +119,15 @@ def test_velo_projection_bit_exact():
     assert np.array_equal(nz, g["full_nz_index"]) and np.array_equal(depth.reshape(-1)[nz], g["full_nz_value"])
 
 
+def test_disp_head_golden():
+    """`alpha * sigmoid(x) + beta` against the disparities the unmodified DispNetS returned for the captured
+    pre-activations (models/depth/disp_net.py:121-139)."""
+    g = load_golden("head_dispnet")
+    for k in ("1", "3"):
+        out = O.disp_head(torch.from_numpy(g["x" + k]))
+        assert torch.equal(out, torch.from_numpy(g["disp" + k]))
+
+
 def test_live_reference_if_present():
     """When the reference tree is mounted (build container), run it live against
     the oracle at B=4 once more - guards against a stale fixture."""

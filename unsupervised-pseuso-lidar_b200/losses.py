@@ -32,18 +32,23 @@ class Losses:
     """`losses.py:56-271`.  Constructor takes no arguments in the reference
     (trainer.py:79); the keyword options only select implementation variants."""
 
-    def __init__(self, rotation_mode="axisangle", fused_backward=True):
+    def __init__(self, rotation_mode="axisangle", fused_backward=True, disp_head=None):
         self.SSIM = SSIM()
         self.clip_loss = 0.5
         self.rotation_mode = rotation_mode
         self.fused_backward = fused_backward
+        # disp_head=(alpha, beta): `forward` then takes the depth network's PRE-ACTIVATION maps and evaluates the
+        # head `alpha * sigmoid(x) + beta` (models/depth/disp_net.py:121-139: alpha=10, beta=0.01) inside the
+        # kernels, returning gradients with respect to x (SURVEY.md section 8(f) rank 1)
+        self.disp_head = disp_head
 
     # ---- live path -------------------------------------------------------
     def forward(self, tgt_img, ref_imgs, disparity, poses, intrinsics, gt=None):
         """`losses.py:262-271` -> [loss_mam, loss_smooth] (0-d CUDA tensors)."""
         pyr = [list(frame) if isinstance(frame, (list, tuple)) else [frame] for frame in disparity]
         mam, smooth = ops.fused_losses(tgt_img, list(ref_imgs), pyr, poses, intrinsics, input_is_depth=False,
-                                       rotation_mode=self.rotation_mode, fused_backward=self.fused_backward)
+                                       rotation_mode=self.rotation_mode, fused_backward=self.fused_backward,
+                                       disp_head=self.disp_head)
         return [mam, smooth]
 
     __call__ = forward

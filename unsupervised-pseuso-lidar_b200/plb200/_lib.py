@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libplb200.so")
 MAX_SRC, MAX_SCALES, MAX_JOBS = 4, 4, 2
 ROT_AXISANGLE, ROT_EULER = 0, 1
 PHOTO_L1_MEAN, PHOTO_MIN_REPROJ = 0, 1
+INPUT_DISP, INPUT_DEPTH, INPUT_LOGIT = 0, 1, 2
 PHOTO_NO_SSIM, PHOTO_NO_AUTOMASK = 1, 2
 
 _fp = C.c_void_p  # device pointers are passed as integers
@@ -48,6 +49,7 @@ class PhotoArgs(C.Structure):
         ("k_is_f64", C.c_int32),
         ("input_is_depth", C.c_int32),
         ("disp_a", C.c_float), ("disp_b", C.c_float),
+        ("head_alpha", C.c_float), ("head_beta", C.c_float),
         ("want_grad", C.c_int32),
         ("deterministic", C.c_int32),
         ("poses", _fp),
@@ -73,6 +75,7 @@ class SmoothArgs(C.Structure):
         ("accumulate", C.c_int32),
         ("input_is_depth", C.c_int32),
         ("disp_a", C.c_float), ("disp_b", C.c_float),
+        ("head_alpha", C.c_float), ("head_beta", C.c_float),
         ("scale_decay", C.c_float),
         ("want_grad", C.c_int32),
         ("loss", _fp),

@@ -259,6 +259,16 @@ __device__ __forceinline__ float rcp_nr(float z) {
     return r * fmaf(-z, r, 2.0f);
 }
 
+// Disparity head folded into the loss (PLB_INPUT_LOGIT): disp = alpha * sigmoid(x) + beta (models/depth/disp_net.py:121).
+__device__ __forceinline__ float head_disp(float x, float alpha, float beta) {
+    return fmaf(alpha, rcp_nr(1.0f + expf(-x)), beta);
+}
+// d disp / d x = alpha * s * (1 - s), from the DEPTH the kernels keep: disp = (1/D - b) / a, s = (disp - beta) / alpha
+__device__ __forceinline__ float head_chain_from_depth(float D, float a, float b, float alpha, float beta) {
+    const float d = (rcp_nr(D) - b) / a;
+    return (d - beta) * (alpha + beta - d) / alpha;
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

@@ -325,7 +325,7 @@ __device__ __forceinline__ void flush_group(const V (&acc)[9], int i0, float l1,
 }
 
 // One run: consecutive rows [y, y + rows) of one 32-px strip of one (job, image) pair, NSRC sources.
-template <bool GRAD, bool IMG_GRAD, int NSRC, bool MULTI>
+template <bool GRAD, bool IMG_GRAD, int NSRC, bool MULTI, bool HEAD>
 __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairConst& pc, int strip, int y, int rows,
                                          int lane, float* rec) {
     constexpr int NP = NSRC / 2, ODD = NSRC & 1;
@@ -365,8 +365,8 @@ __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairCons
         }
         const float yf = (float)y;
         if (!MULTI) {
-            const float d0 = d_cur;
-            const float D = a.input_is_depth ? d0 : rcp_nr(fmaf(a.disp_a, d0, a.disp_b));
+            const float d0 = HEAD ? head_disp(d_cur, a.head_alpha, a.head_beta) : d_cur;
+            const float D = a.input_is_depth == PLB_INPUT_DEPTH ? d0 : rcp_nr(fmaf(a.disp_a, d0, a.disp_b));
             float gp = 0.0f;
 #pragma unroll
             for (int g = 0; g < NP; ++g)
@@ -375,7 +375,11 @@ __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairCons
             if (GRAD) {
                 float* g = pc.g_disp[0];
                 // d loss / d D = -gp / D;  d D / d disp = -disp_a * D^2
-                if (valid && g != nullptr) g[o] = a.input_is_depth ? -gp * rcp_nr(D) : a.disp_a * D * gp;
+                if (valid && g != nullptr) {
+                    float gv = a.input_is_depth == PLB_INPUT_DEPTH ? -gp * rcp_nr(D) : a.disp_a * D * gp;
+                    if (HEAD) gv *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
+                    g[o] = gv;
+                }
             }
         } else {
             const int n_scales = pc.n_scales, lowres = pc.lowres;
@@ -385,8 +389,9 @@ __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairCons
                 const bool full = !((lowres >> s) & 1);
                 float D, gp = 0.0f;
                 if (full) {
-                    const float d = __ldg(disp_b + o);
-                    D = a.input_is_depth ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
+                    float d = __ldg(disp_b + o);
+                    if (HEAD) d = head_disp(d, a.head_alpha, a.head_beta);
+                    D = a.input_is_depth == PLB_INPUT_DEPTH ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
                 } else {
                     const int dh = pc.dh[s], dw = pc.dw[s];
                     int x0, x1, y0, y1; float lx0, lx1, ly0, ly1;
@@ -394,7 +399,11 @@ __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairCons
                     up_coord(y, pc.sy[s], dh, y0, y1, ly0, ly1);
                     float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
                     float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
-                    if (!a.input_is_depth) {
+                    if (HEAD) {
+                        v00 = head_disp(v00, a.head_alpha, a.head_beta); v01 = head_disp(v01, a.head_alpha, a.head_beta);
+                        v10 = head_disp(v10, a.head_alpha, a.head_beta); v11 = head_disp(v11, a.head_alpha, a.head_beta);
+                    }
+                    if (a.input_is_depth != PLB_INPUT_DEPTH) {
                         v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
                         v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
                     }
@@ -407,7 +416,11 @@ __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairCons
                 if (GRAD) {
                     float* g = pc.g_disp[s];
                     if (valid && g != nullptr)
-                        g[o] = (full && !a.input_is_depth) ? a.disp_a * D * gp : -gp * rcp_nr(D);
+                    {
+                        float gv = (full && a.input_is_depth != PLB_INPUT_DEPTH) ? a.disp_a * D * gp : -gp * rcp_nr(D);
+                        if (full && HEAD) gv *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
+                        g[o] = gv;
+                    }
                 }
             }
         }
@@ -453,7 +466,7 @@ __device__ inline void photo_pose_jacobian(const plb_photo_args& a, const plb_ph
     for (int m = 0; m < 6; ++m) J[k * 6 + m] = g6[m];
 }
 
-template <bool GRAD, bool IMG_GRAD, int MAXSRC, bool MULTI>
+template <bool GRAD, bool IMG_GRAD, int MAXSRC, bool MULTI, bool HEAD>
 __global__ void __launch_bounds__(photo_threads(MAXSRC, MULTI), (MAXSRC <= 2) ? PH_MIN_BLOCKS : 2)
 photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
     constexpr int PH_THREADS = photo_threads(MAXSRC, MULTI), PH_WARPS = PH_THREADS / 32;
@@ -612,13 +625,13 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         float* rec = s_rec[set][warp];
         const int n_src = pc.n_src;
         if (MAXSRC <= 2) {
-            if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI>(a, pc, strip, y, rows, lane, rec);
-            else run_rows<GRAD, IMG_GRAD, 1, MULTI>(a, pc, strip, y, rows, lane, rec);
+            if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
+            else run_rows<GRAD, IMG_GRAD, 1, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
         } else {
-            if (n_src == 4) run_rows<GRAD, IMG_GRAD, 4, MULTI>(a, pc, strip, y, rows, lane, rec);
-            else if (n_src == 3) run_rows<GRAD, IMG_GRAD, 3, MULTI>(a, pc, strip, y, rows, lane, rec);
-            else if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI>(a, pc, strip, y, rows, lane, rec);
-            else run_rows<GRAD, IMG_GRAD, 1, MULTI>(a, pc, strip, y, rows, lane, rec);
+            if (n_src == 4) run_rows<GRAD, IMG_GRAD, 4, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
+            else if (n_src == 3) run_rows<GRAD, IMG_GRAD, 3, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
+            else if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
+            else run_rows<GRAD, IMG_GRAD, 1, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
         }
         u += rows;
     }
@@ -1016,9 +1029,15 @@ photo_upsample_T_kernel(const __grid_constant__ PhotoLaunch p, const __grid_cons
             if (r < nr) {
                 float chain = 1.0f;
                 const size_t o = (size_t)b * dh * dw + (size_t)(j0 + r) * dw + i;
-                if (!a.input_is_depth) {
-                    const float D = 1.0f / (a.disp_a * __ldg(job.disp[s] + o) + a.disp_b);
-                    chain = -a.disp_a * D * D;
+                if (a.input_is_depth != PLB_INPUT_DEPTH) {
+                    float d = __ldg(job.disp[s] + o), hc = 1.0f;
+                    if (a.input_is_depth == PLB_INPUT_LOGIT) {
+                        const float sg = 1.0f / (1.0f + expf(-d));
+                        d = fmaf(a.head_alpha, sg, a.head_beta);
+                        hc = a.head_alpha * sg * (1.0f - sg);
+                    }
+                    const float D = 1.0f / (a.disp_a * d + a.disp_b);
+                    chain = -a.disp_a * D * D * hc;
                 }
                 job.g_disp[s][o] = acc[r] * chain;
             }
@@ -1054,12 +1073,12 @@ int validate_photo(const plb_photo_args* a) {
     return PLB_OK;
 }
 
-template <bool GRAD, bool IMG, int MS, bool MULTI>
+template <bool GRAD, bool IMG, int MS, bool MULTI, bool HEAD>
 static int blocks_per_sm() {
     static int cached = 0;
     if (cached == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, MS, MULTI>, photo_threads(MS, MULTI), 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, MS, MULTI, HEAD>, photo_threads(MS, MULTI), 0) != cudaSuccess ||
             n < 1) {
             (void)cudaGetLastError();
             n = 2;
@@ -1141,6 +1160,10 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
         if (a->jobs[j].n_src > maxsrc) maxsrc = a->jobs[j].n_src;
     }
     const bool lowres_grad = photo_has_lowres_grad(*a);
+    // the disparity head folded in (PLB_INPUT_LOGIT) is its own set of kernel variants: the default variants keep
+    // their register budget (the single-scale one has none to spare)
+    const bool head = a->input_is_depth == PLB_INPUT_LOGIT;
+    if (head && img_grad) return PLB_EINVAL;       // image gradients: disparity / depth inputs only
     p.strips = (a->W + 31) / 32;
     p.units_per_pair = p.strips * a->H;
     p.n_pairs = a->n_jobs * a->B;
@@ -1174,7 +1197,8 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     for (int j = 0; j < a->n_jobs; ++j)
         if (a->jobs[j].n_scales != 1 || p.lowres[j] != 0) multi = true;
     int bps;
-#define PLB_BPS(G, I, M) (multi ? blocks_per_sm<G, I, M, true>() : blocks_per_sm<G, I, M, false>())
+#define PLB_BPS(G, I, M) (head ? (multi ? blocks_per_sm<G, false, M, true, true>() : blocks_per_sm<G, false, M, false, true>()) \
+                               : (multi ? blocks_per_sm<G, I, M, true, false>() : blocks_per_sm<G, I, M, false, false>()))
     if (!a->want_grad) bps = maxsrc <= 2 ? PLB_BPS(false, false, 2) : PLB_BPS(false, false, 4);
     else if (img_grad) bps = maxsrc <= 2 ? PLB_BPS(true, true, 2) : PLB_BPS(true, true, 4);
     else bps = maxsrc <= 2 ? PLB_BPS(true, false, 2) : PLB_BPS(true, false, 4);
@@ -1196,8 +1220,11 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     dim3 g(p.grid), block(photo_threads(maxsrc <= 2 ? 2 : 4, multi));
 #define PLB_LAUNCH(G, I, M)                                           \
     do {                                                              \
-        if (multi) photo_l1_kernel<G, I, M, true><<<g, block, 0, st>>>(p); \
-        else photo_l1_kernel<G, I, M, false><<<g, block, 0, st>>>(p);     \
+        if (head) {                                                   \
+            if (multi) photo_l1_kernel<G, false, M, true, true><<<g, block, 0, st>>>(p); \
+            else photo_l1_kernel<G, false, M, false, true><<<g, block, 0, st>>>(p);      \
+        } else if (multi) photo_l1_kernel<G, I, M, true, false><<<g, block, 0, st>>>(p); \
+        else photo_l1_kernel<G, I, M, false, false><<<g, block, 0, st>>>(p);             \
     } while (0)
     if (!a->want_grad) { if (maxsrc <= 2) PLB_LAUNCH(false, false, 2); else PLB_LAUNCH(false, false, 4); }
     else if (img_grad) { if (maxsrc <= 2) PLB_LAUNCH(true, true, 2); else PLB_LAUNCH(true, true, 4); }

@@ -79,11 +79,13 @@ __device__ __forceinline__ void pm_taps(const float* __restrict__ cb, int plane,
 }
 
 // depth at full-resolution pixel (x, y) of scale s (direct, or align_corners=False upsample of depth)
+template <bool HEAD>
 __device__ __forceinline__ float pm_depth(const plb_photo_args& a, const PairConst& pc, int s, bool full, int x, int y,
                                           int W) {
     if (full) {
-        const float d = __ldg(pc.disp[s] + (y * W + x));
-        return a.input_is_depth ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
+        float d = __ldg(pc.disp[s] + (y * W + x));
+        if (HEAD) d = head_disp(d, a.head_alpha, a.head_beta);
+        return a.input_is_depth == PLB_INPUT_DEPTH ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
     }
     const float* disp_b = pc.disp[s];
     const int dh = pc.dh[s], dw = pc.dw[s];
@@ -92,7 +94,11 @@ __device__ __forceinline__ float pm_depth(const plb_photo_args& a, const PairCon
     up_coord(y, pc.sy[s], dh, y0, y1, ly0, ly1);
     float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
     float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
-    if (!a.input_is_depth) {
+    if (HEAD) {
+        v00 = head_disp(v00, a.head_alpha, a.head_beta); v01 = head_disp(v01, a.head_alpha, a.head_beta);
+        v10 = head_disp(v10, a.head_alpha, a.head_beta); v11 = head_disp(v11, a.head_alpha, a.head_beta);
+    }
+    if (a.input_is_depth != PLB_INPUT_DEPTH) {
         v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
         v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
     }
@@ -228,7 +234,7 @@ __device__ __forceinline__ void pm_stage2_all(PminSmem& S, int n_src, int tid, i
     }
 }
 
-template <bool GRAD, int NSMAX>
+template <bool GRAD, int NSMAX, bool HEAD>
 __global__ void __launch_bounds__(PM_THREADS, 3)
 photo_min_kernel(const __grid_constant__ PminLaunch p) {
     const plb_photo_args& a = p.a;
@@ -325,7 +331,7 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
         for (int k = tid; k < PM_N2; k += PM_THREADS) {
             const int ly = k / PM_W2, lx = k - ly * PM_W2;
             const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
-            const float D = pm_depth(a, pc, s, full, gx, gy, W);
+            const float D = pm_depth<HEAD>(a, pc, s, full, gx, gy, W);
             const float xf = (float)gx, yf = (float)gy;
             const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
             const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
@@ -402,7 +408,7 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) e[ii][cc] += (sel == cc + 4 * ii) ? g : 0.0f;
                     }
-                D = pm_depth(a, pc, s, full, qx, qy, W);
+                D = pm_depth<HEAD>(a, pc, s, full, qx, qy, W);
                 const float xf = (float)qx, yf = (float)qy;
                 const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
                 const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
@@ -435,7 +441,8 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
                 }
                 float* g = pc.g_disp[s];
                 if (g != nullptr) {
-                    const float chain = (full && !a.input_is_depth) ? -a.disp_a * D * D : 1.0f;
+                    float chain = (full && a.input_is_depth != PLB_INPUT_DEPTH) ? -a.disp_a * D * D : 1.0f;
+                    if (full && HEAD) chain *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
                     g[qy * W + qx] = gD * chain;
                 }
             }
@@ -521,16 +528,16 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     }
 }
 
-template <bool GRAD, int NSMAX>
+template <bool GRAD, int NSMAX, bool HEAD>
 static int pm_launch_variant(const PminLaunch& p, dim3 grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        const cudaError_t e = cudaFuncSetAttribute(photo_min_kernel<GRAD, NSMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(photo_min_kernel<GRAD, NSMAX, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)sizeof(PminSmem));
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    photo_min_kernel<GRAD, NSMAX><<<grid, PM_THREADS, sizeof(PminSmem), st>>>(p);
+    photo_min_kernel<GRAD, NSMAX, HEAD><<<grid, PM_THREADS, sizeof(PminSmem), st>>>(p);
     return PLB_OK;
 }
 
@@ -550,8 +557,11 @@ int photo_min_launch(const plb_photo_args* a, cudaStream_t st) {
     p.w_e = job.term_weight / ((float)a->B * (float)a->H * (float)a->W);
     p.C1 = 1e-4f; p.C2 = 9e-4f;
     dim3 grid(p.tiles, a->B);
-    if (a->want_grad) rc = job.n_src <= 2 ? pm_launch_variant<true, 2>(p, grid, st) : pm_launch_variant<true, PLB_MAX_SRC>(p, grid, st);
-    else rc = job.n_src <= 2 ? pm_launch_variant<false, 2>(p, grid, st) : pm_launch_variant<false, PLB_MAX_SRC>(p, grid, st);
+    const bool head = a->input_is_depth == PLB_INPUT_LOGIT;
+#define PM_GO(G, N) (head ? pm_launch_variant<G, N, true>(p, grid, st) : pm_launch_variant<G, N, false>(p, grid, st))
+    if (a->want_grad) rc = job.n_src <= 2 ? PM_GO(true, 2) : PM_GO(true, PLB_MAX_SRC);
+    else rc = job.n_src <= 2 ? PM_GO(false, 2) : PM_GO(false, PLB_MAX_SRC);
+#undef PM_GO
     if (rc != PLB_OK) return rc;
     ++g_launches;
     PLB_CHECK_LAUNCH();

@@ -89,7 +89,8 @@ smooth_kernel(const __grid_constant__ plb_smooth_args a, const __grid_constant__
         const bool own_lane = lane >= 2 && lane < 2 + SW_OWN && colin;
         const float* disp = a.disp[s] + (size_t)b * h * w + (colin ? x : 0);
         float* gout = (a.want_grad && a.g_disp[s] != nullptr) ? a.g_disp[s] + (size_t)b * h * w + (colin ? x : 0) : nullptr;
-        const bool is_depth = a.input_is_depth != 0;
+        const bool is_depth = a.input_is_depth == PLB_INPUT_DEPTH, is_logit = a.input_is_depth == PLB_INPUT_LOGIT;
+        const float ha = a.head_alpha, hb = a.head_beta;
         const float da = a.disp_a, db = a.disp_b;
         const float up = a.upstream ? __ldg(a.upstream) : 1.0f;
         const float c1 = L.c1[s], c2 = L.c2[s], c3 = L.c3[s];
@@ -128,7 +129,9 @@ smooth_kernel(const __grid_constant__ plb_smooth_args a, const __grid_constant__
         const bool x1ok = colin && x <= w - 3, xmok = colin && x <= w - 2;
         float* pout = gout != nullptr ? gout + (size_t)ystart * w : nullptr;
         auto conv = [&](float v, int y) -> float {            // disparity -> depth; 0 outside the image, as the loads give
-            return (is_depth || !colin || y > ylast) ? v : rcp_nr(fmaf(da, v, db));
+            if (is_depth || !colin || y > ylast) return v;
+            if (is_logit) v = head_disp(v, ha, hb);
+            return rcp_nr(fmaf(da, v, db));
         };
         float r0 = conv(q[0], ystart), r1 = conv(q[1], ystart + 1);      // rows y, y + 1 of the window (converted)
         auto step = [&](int y, float raw2, float old) {
@@ -154,6 +157,7 @@ smooth_kernel(const __grid_constant__ plb_smooth_args a, const __grid_constant__
                 const float tm = (sm - sm_l1) - (sm_m1 - smp_l1);
                 float g = fmaf(g1, t1, fmaf(g3, t3, g2 * tm));
                 if (!is_depth) g *= -da * r0 * r0;
+                if (is_logit) g *= head_chain_from_depth(r0, da, db, ha, hb);
                 *pout = old + g;
             }
             if (pout != nullptr) pout += w;

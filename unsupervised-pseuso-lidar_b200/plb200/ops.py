@@ -68,7 +68,7 @@ class LossConfig:
 
     def __init__(self, n_src, scales_per_frame, input_is_depth=False, do_photo=True, do_smooth=True,
                  rotation_mode="axisangle", fused_backward=True, disp_a=10.0, disp_b=0.01, scale_decay=2.3,
-                 mode=_lib.PHOTO_L1_MEAN, flags=0):
+                 mode=_lib.PHOTO_L1_MEAN, flags=0, disp_head=None):
         self.n_src = n_src
         self.scales_per_frame = list(scales_per_frame)  # e.g. [4, 4]: frames with a depth pyramid
         self.input_is_depth = bool(input_is_depth)
@@ -77,6 +77,12 @@ class LossConfig:
         self.fused_backward = fused_backward
         self.disp_a, self.disp_b, self.scale_decay = disp_a, disp_b, scale_decay
         self.mode, self.flags = mode, flags
+        # (alpha, beta): the pyramids hold the disparity head's PRE-ACTIVATION x and disp = alpha * sigmoid(x) + beta
+        # (models/depth/disp_net.py:121-139) is evaluated inside the kernels; gradients come back with respect to x
+        self.disp_head = None if disp_head is None else (float(disp_head[0]), float(disp_head[1]))
+        if self.disp_head is not None and self.input_is_depth:
+            raise ValueError("disp_head applies to disparity inputs, not to depth")
+        self.input_kind = _lib.INPUT_LOGIT if self.disp_head else (_lib.INPUT_DEPTH if self.input_is_depth else _lib.INPUT_DISP)
 
 
 def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt, g_refs, out, up, skip):
@@ -93,8 +99,10 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
         a.n_pose = poses.shape[1]
         a.rotation_mode = cfg.rotation_mode
         a.k_is_f64 = 1 if K.dtype == torch.float64 else 0
-        a.input_is_depth = int(cfg.input_is_depth)
+        a.input_is_depth = cfg.input_kind
         a.disp_a, a.disp_b = cfg.disp_a, cfg.disp_b
+        if cfg.disp_head:
+            a.head_alpha, a.head_beta = cfg.disp_head
         a.want_grad = int(want_grad)
         a.poses, a.K = poses.data_ptr(), K.data_ptr()
         a.g_poses = _ptr(g_poses) if want_grad else 0
@@ -145,8 +153,10 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
             s_.dh[s], s_.dw[s] = d.shape[-2], d.shape[-1]
             s_.g_disp[s] = _ptr(g_pyr[0][s]) if (want_grad and g_pyr is not None) else 0
         s_.accumulate = 1 if cfg.do_photo else 0
-        s_.input_is_depth = int(cfg.input_is_depth)
+        s_.input_is_depth = cfg.input_kind
         s_.disp_a, s_.disp_b, s_.scale_decay = cfg.disp_a, cfg.disp_b, cfg.scale_decay
+        if cfg.disp_head:
+            s_.head_alpha, s_.head_beta = cfg.disp_head
         s_.want_grad = int(want_grad)
         s_.loss = out.data_ptr() + 4
         s_.upstream = up_ptr[1]
