@@ -459,20 +459,21 @@ class EdgeSmoothFn(torch.autograd.Function):
         tgt = _f32c(tgt)
         disps = [_f32c(d) for d in disps]
         loss = torch.empty((), dtype=torch.float32, device=tgt.device)
-        EdgeSmoothFn._launch(tgt, disps, normalize, False, None, None, loss, None)
-        ctx.normalize = normalize
-        ctx.save_for_backward(tgt, *disps)
+        # single pass: when a disparity needs a gradient the forward launch writes d loss / d disp for a unit upstream
+        # (the loss is a scalar, its gradient is linear in the upstream value); backward only scales it
+        want = any(ctx.needs_input_grad[2:])
+        g_disp = [torch.empty_like(d) for d in disps] if want else None
+        g_scratch = [torch.empty_like(d) for d in disps] if (want and normalize) else None
+        EdgeSmoothFn._launch(tgt, disps, normalize, want, g_disp, g_scratch, loss, None)
+        ctx.g_disp = g_disp
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        tgt, *disps = ctx.saved_tensors
-        g = g.detach().to(torch.float32).reshape(()).contiguous()
-        g_disp = [torch.empty_like(d) for d in disps]
-        g_scratch = [torch.empty_like(d) for d in disps] if ctx.normalize else None
-        scratch_loss = torch.empty((), dtype=torch.float32, device=tgt.device)
-        EdgeSmoothFn._launch(tgt, disps, ctx.normalize, True, g_disp, g_scratch, scratch_loss, g)
-        return (None, None) + tuple(g_disp)
+        g_disp, ctx.g_disp = ctx.g_disp, None
+        g = g.detach().to(torch.float32)
+        need = ctx.needs_input_grad[2:]
+        return (None, None) + tuple((gd * g if n else None) for gd, n in zip(g_disp, need))
 
 
 def edge_aware_smooth(disps, tgt, normalize=True):
