@@ -25,7 +25,14 @@ _ws_lock = threading.Lock()
 _ws_cache = {}
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Raw handle of torch's current stream on the current device (the fast private accessor when this torch has
+    it: `torch.cuda.current_stream()` costs ~18 us of Python per call, and a loss step asks six times)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
