@@ -10,9 +10,9 @@
 // combined in block order by the last block to finish, which writes the threshold to a device
 // scalar; a second launch clamps in place.  No host synchronisation (the reference's float()
 // forces one).
-// Backward: one thread per input pixel q; it visits the <= 9 window centres p that contain q,
-// recomputes the statistics of p and adds d out(p) / d x(q) (reflection makes q appear up to
-// 4 times in a border window).  Gather form: no atomics, bitwise repeatable.
+// Backward: tiled; the derivative coefficients of every window centre are evaluated once per tile (+ 1 halo)
+// into shared memory, then every input pixel q gathers the <= 9 centres p that contain it (reflection makes
+// q appear up to 4 times in a border window).  Gather form: no atomics, bitwise repeatable.
 #include "common.cuh"
 
 namespace plb {
@@ -158,56 +158,79 @@ photomap_clip_kernel(float* out, long long n, const float* thr) {
     out[idx] = fminf(out[idx], t);
 }
 
+// Backward, tiled: one block = one 32 x 8 tile of one (image, channel) plane.  The derivative coefficients of
+// every window centre of tile + 1 halo are evaluated ONCE (scaled by the upstream gradient, clip applied) into
+// shared memory; then every tile pixel q gathers its <= 9 centres.  (One thread per pixel recomputing the
+// statistics of all nine centres did the 18-load window nine times over: 430 us for a 12 x 3 x 192 x 640 map.)
+constexpr int PB_TW = 32, PB_TH = 8;
+constexpr int PB_W1 = PB_TW + 2, PB_H1 = PB_TH + 2, PB_N1 = PB_W1 * PB_H1;   // centres: tile + 1
+
 __global__ void __launch_bounds__(PMAP_THREADS)
-photomap_bwd_kernel(const __grid_constant__ plb_photomap_args a) {
+photomap_bwd_kernel(const __grid_constant__ plb_photomap_args a, int tiles_x) {
     const int H = a.H, W = a.W, plane = H * W;
-    const long long n = (long long)a.B * a.C * plane;
-    const long long idx = (long long)blockIdx.x * PMAP_THREADS + threadIdx.x;
-    if (idx >= n) return;
-    const long long img = idx / plane;
-    const int o = (int)(idx - img * plane);
-    const int qy = o / W, qx = o - qy * W;
+    const int tile = blockIdx.x, tx0 = (tile % tiles_x) * PB_TW, ty0 = (tile / tiles_x) * PB_TH;
+    const long long img = blockIdx.y;
     const float* x = a.x + img * plane;
     const float* y = a.y + img * plane;
     const float* g = a.g_out + img * plane;
-    const float xq = __ldg(x + o), yq = __ldg(y + o);
+    const int tid = threadIdx.x;
     const bool clip = a.clip >= 0.0f;
     const float thr = clip ? __ldg(a.threshold) : 0.0f;
+    // per centre p: go * (ax, bx, cx) and go * (ay, by, cy); the centre-only terms go * lx, go * ly
+    __shared__ float4 sX[PB_N1], sY[PB_N1];      // .x = a, .y = b, .z = c, .w = l
+    for (int k = tid; k < PB_N1; k += PMAP_THREADS) {
+        const int ly = k / PB_W1, lx = k - ly * PB_W1;
+        const int px = tx0 + lx - 1, py = ty0 + ly - 1;
+        float4 cx4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), cy4 = cx4;
+        if (px >= 0 && px < W && py >= 0 && py < H) {
+            const int po = py * W + px;
+            const float go = __ldg(g + po);
+            if (go != 0.0f) {
+                const float xc = __ldg(x + po), yc = __ldg(y + po);
+                MapTerm t;
+                if (a.w_ssim != 0.0f) {
+                    t = map_term(window(x, y, px, py, H, W), xc, yc, a.C1, a.C2, a.w_ssim, a.w_l1, true);
+                } else {
+                    const float diff = yc - xc;
+                    const float sg = (diff > 0.0f ? 1.0f : 0.0f) - (diff < 0.0f ? 1.0f : 0.0f);
+                    t.v = a.w_l1 * fabsf(diff);
+                    t.ax = t.bx = t.cx = t.ay = t.by = t.cy = 0.0f;
+                    t.lx = -a.w_l1 * sg; t.ly = a.w_l1 * sg;
+                }
+                if (!clip || t.v <= thr) {            // torch.clamp passes the gradient where v <= max
+                    cx4 = make_float4(go * t.ax, go * t.bx, go * t.cx, go * t.lx);
+                    cy4 = make_float4(go * t.ay, go * t.by, go * t.cy, go * t.ly);
+                }
+            }
+        }
+        sX[k] = cx4; sY[k] = cy4;
+    }
+    __syncthreads();
+    const int qx = tx0 + (tid & 31), qy = ty0 + (tid >> 5);
+    if (qx >= W || qy >= H) return;
+    const int o = qy * W + qx;
+    const float xq = __ldg(x + o), yq = __ldg(y + o);
+    const int k0 = ((tid >> 5) + 1) * PB_W1 + (tid & 31) + 1;
     float gx = 0.0f, gy = 0.0f;
-#pragma unroll 1
+#pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
         const int py = qy + dy;
-        if (py < 0 || py >= H) continue;
         // multiplicity of row qy in the reflection-padded window of centre row py
         const float my = 1.0f + ((py == 0 && dy == -1) ? 1.0f : 0.0f) + ((py == H - 1 && dy == 1) ? 1.0f : 0.0f);
-#pragma unroll 1
+#pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
             const int px = qx + dx;
-            if (px < 0 || px >= W) continue;
             const float mx = 1.0f + ((px == 0 && dx == -1) ? 1.0f : 0.0f) + ((px == W - 1 && dx == 1) ? 1.0f : 0.0f);
-            const float go = __ldg(g + py * W + px);
-            if (go == 0.0f) continue;
-            const int po = py * W + px;
-            const float xc = __ldg(x + po), yc = __ldg(y + po);
-            MapTerm t;
-            if (a.w_ssim != 0.0f) {
-                t = map_term(window(x, y, px, py, H, W), xc, yc, a.C1, a.C2, a.w_ssim, a.w_l1, true);
-            } else {
-                const float diff = yc - xc;
-                const float sg = (diff > 0.0f ? 1.0f : 0.0f) - (diff < 0.0f ? 1.0f : 0.0f);
-                t.v = a.w_l1 * fabsf(diff);
-                t.ax = t.bx = t.cx = t.ay = t.by = t.cy = 0.0f;
-                t.lx = -a.w_l1 * sg; t.ly = a.w_l1 * sg;
-            }
-            if (clip && !(t.v <= thr)) continue;      // torch.clamp passes the gradient where v <= max
+            const float4 cx4 = sX[k0 + dy * PB_W1 + dx], cy4 = sY[k0 + dy * PB_W1 + dx];   // zero outside the image
             const float m = mx * my;
-            float dxq = m * fmaf(t.bx, xq, fmaf(t.cx, yq, t.ax));
-            float dyq = m * fmaf(t.by, yq, fmaf(t.cy, xq, t.ay));
-            if (dx == 0 && dy == 0) { dxq += t.lx; dyq += t.ly; }
-            gx = fmaf(go, dxq, gx);
-            gy = fmaf(go, dyq, gy);
+            float dxq = m * fmaf(cx4.y, xq, fmaf(cx4.z, yq, cx4.x));
+            float dyq = m * fmaf(cy4.y, yq, fmaf(cy4.z, xq, cy4.x));
+            if (dx == 0 && dy == 0) { dxq += cx4.w; dyq += cy4.w; }
+            gx += dxq;
+            gy += dyq;
         }
     }
+    const long long idx = img * plane + o;
     if (a.g_x != nullptr) a.g_x[idx] = gx;
     if (a.g_y != nullptr) a.g_y[idx] = gy;
 }
@@ -244,8 +267,10 @@ int photomap_launch(const plb_photomap_args* a, cudaStream_t st) {
 int photomap_bwd_launch(const plb_photomap_args* a, cudaStream_t st) {
     const int rc = validate_pmap(a, true);
     if (rc != PLB_OK) return rc;
-    const PmapLayout L = pmap_layout(*a);
-    photomap_bwd_kernel<<<L.blocks, PMAP_THREADS, 0, st>>>(*a);
+    const int tiles_x = (a->W + PB_TW - 1) / PB_TW, tiles_y = (a->H + PB_TH - 1) / PB_TH;
+    if ((long long)a->B * a->C > 65535) return PLB_EINVAL;
+    dim3 grid(tiles_x * tiles_y, a->B * a->C);
+    photomap_bwd_kernel<<<grid, PMAP_THREADS, 0, st>>>(*a, tiles_x);
     ++g_launches;
     PLB_CHECK_LAUNCH();
     return PLB_OK;
