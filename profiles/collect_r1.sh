@@ -16,4 +16,6 @@ $NCU -k regex:upsample\|smooth -s 4 -c 2 -o $O/r1_aux_c2 python profiles/prof_ph
 $NCU -k regex:photo_min -s 2 -c 1 -o $O/r1_photo_min_c2min python profiles/prof_photo.py c2min 4 > $O/r1_ncu_d.log 2>&1
 $NCU -k regex:cloud_ -s 4 -c 2 -o $O/r1_cloud python profiles/prof_cloud.py > $O/r1_ncu_e.log 2>&1
 python profiles/kbench.py headline headline64 c1 c2 c3 c5 c2min > $O/r1_kbench.txt 2>&1
-tail -2 $O/r1_ncu_?.log | grep -c Report
+grep -c Report $O/r1_ncu_?.log
+python profiles/edge_bench.py > $O/r1_edge_bench.txt 2>&1
+python profiles/aux_bench.py > $O/r1_aux_bench.txt 2>&1

@@ -16,3 +16,5 @@ python profiles/ncu_hot.py $O/r1_photo_l1_c2.ncu-rep > $R/r1_photo_l1_c2.opcodes
 python profiles/ncu_hot.py $O/r1_photo_l1_headline.ncu-rep > $R/r1_photo_l1_headline.opcodes.txt
 python profiles/ncu_lines.py $O/r1_photo_l1_c2.ncu-rep "" 40 > $R/r1_photo_l1_c2.lines.txt
 python profiles/ncu_lines.py $O/r1_photo_min_c2min.ncu-rep "" 40 > $R/r1_photo_min_c2min.lines.txt
+grep -v "^/\|_warn_once\|Warning" $O/r1_edge_bench.txt > $R/edge_bench.txt
+grep -v "^/\|_warn_once\|Warning" $O/r1_aux_bench.txt > $R/aux_bench.txt
