@@ -9,7 +9,7 @@
 //       P . xyz in fp64 with the rounding order of the per-point np.matmul (rounded products, then
 //       (p0 + p2) + (p1 + p3)), IEEE divisions, the reference's six tests, atomicMax(index + 1) into a
 //       zero-filled int32 cell map;
-//   (2) velo_resolve_kernel: one thread per cell: depth = xyz[2] of the winner (recomputed from the
+//   (2) velo_resolve_kernel: one thread per PAIR of cells: depth = xyz[2] of the winner (recomputed from the
 //       point: 16 B of L2-resident read instead of an 8 B/point scratch array), winner index out, and
 //       the cell map is zeroed again (self-cleaning workspace).
 #include "common.cuh"
@@ -58,22 +58,48 @@ velo_scatter_kernel(const __grid_constant__ plb_velo_args a) {
     }
 }
 
+// depth (xyz[2]) of the point that owns a cell, recomputed from the point
+__device__ __forceinline__ double velo_cell_depth(const plb_velo_args& a, const float* pts, int w) {
+    float x, y, z;
+    velo_load(pts, a.point_stride, (size_t)(w - 1), x, y, z);
+    return dot4_np(a.T + 8, (double)x, (double)y, (double)z, 1.0);
+}
+
+// Two cells per thread: one 8-byte load of the cell map, one 16-byte store of the fp64 image (most cells are empty;
+// the kernel is a 12-byte-per-cell stream with a rare side trip to the owning point).
 __global__ void __launch_bounds__(VL_THREADS)
 velo_resolve_kernel(const __grid_constant__ plb_velo_args a) {
     const int b = blockIdx.y;
     const int ncell = a.H * a.W;
     const float* pts = a.points + (size_t)b * a.N * a.point_stride;
     int32_t* cells = (int32_t*)a.workspace + (size_t)b * ncell;
-    for (int q = blockIdx.x * VL_THREADS + threadIdx.x; q < ncell; q += gridDim.x * VL_THREADS) {
+    const size_t base = (size_t)b * ncell;
+    // pairs are aligned when the image's first cell is: (b * ncell) even -> 8-byte cell pairs, 16-byte fp64 pairs
+    const bool paired = ((base & 1) == 0);
+    const int npair = paired ? ncell / 2 : 0;
+    for (int q2 = blockIdx.x * VL_THREADS + threadIdx.x; q2 < npair; q2 += gridDim.x * VL_THREADS) {
+        const int q = 2 * q2;
+        const int2 w = *reinterpret_cast<const int2*>(cells + q);
+        double d0 = 0.0, d1 = 0.0;
+        if (w.x > 0 || w.y > 0) {
+            if (w.x > 0) d0 = velo_cell_depth(a, pts, w.x);
+            if (w.y > 0) d1 = velo_cell_depth(a, pts, w.y);
+            *reinterpret_cast<int2*>(cells + q) = make_int2(0, 0);
+        }
+        const size_t o = base + q;
+        if (a.depth_f64 != nullptr) __stcs(reinterpret_cast<double2*>(a.depth_f64 + o), make_double2(d0, d1));
+        if (a.depth_f32 != nullptr) __stcs(reinterpret_cast<float2*>(a.depth_f32 + o), make_float2((float)d0, (float)d1));
+        if (a.winner != nullptr) __stcs(reinterpret_cast<int2*>(a.winner + o), make_int2(w.x - 1, w.y - 1));
+    }
+    // the cells the pairs do not cover: the odd last one, or the whole image when it starts on an odd cell
+    for (int q = 2 * npair + blockIdx.x * VL_THREADS + threadIdx.x; q < ncell; q += gridDim.x * VL_THREADS) {
         const int w = cells[q];
         double depth = 0.0;
         if (w > 0) {
-            float x, y, z;
-            velo_load(pts, a.point_stride, (size_t)(w - 1), x, y, z);
-            depth = dot4_np(a.T + 8, (double)x, (double)y, (double)z, 1.0);
+            depth = velo_cell_depth(a, pts, w);
             cells[q] = 0;
         }
-        const size_t o = (size_t)b * ncell + q;
+        const size_t o = base + q;
         if (a.depth_f64 != nullptr) __stcs(a.depth_f64 + o, depth);
         if (a.depth_f32 != nullptr) __stcs(a.depth_f32 + o, (float)depth);
         if (a.winner != nullptr) __stcs(a.winner + o, w - 1);
@@ -91,6 +117,8 @@ int velo_launch(const plb_velo_args* a, cudaStream_t st) {
     if ((int64_t)a->H * a->W > (int64_t)1 << 30 || a->N > (1 << 30)) return PLB_EINVAL;
     if ((a->N > 0 && !a->points) || (!a->depth_f64 && !a->depth_f32)) return PLB_ENULL;
     if (a->point_stride == 4 && ((uintptr_t)a->points & 15)) return PLB_EINVAL;
+    if (((uintptr_t)a->depth_f64 & 15) || ((uintptr_t)a->depth_f32 & 7) || ((uintptr_t)a->winner & 7) ||
+        ((uintptr_t)a->workspace & 7)) return PLB_EINVAL;      // two cells per thread: paired stores
     if (!a->workspace || a->workspace_bytes < velo_workspace_bytes(a)) return PLB_EWORKSPACE;
     if (a->N > 0) {
         dim3 grid(min((a->N + VL_THREADS - 1) / VL_THREADS, 148 * 8), a->B);
@@ -98,7 +126,7 @@ int velo_launch(const plb_velo_args* a, cudaStream_t st) {
         ++g_launches;
         PLB_CHECK_LAUNCH();
     }
-    dim3 grid2(min((a->H * a->W + VL_THREADS - 1) / VL_THREADS, 148 * 8), a->B);
+    dim3 grid2(min((a->H * a->W / 2 + VL_THREADS - 1) / VL_THREADS + 1, 148 * 8), a->B);
     velo_resolve_kernel<<<grid2, VL_THREADS, 0, st>>>(*a);
     ++g_launches;
     PLB_CHECK_LAUNCH();
