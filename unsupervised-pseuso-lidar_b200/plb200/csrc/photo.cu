@@ -324,6 +324,247 @@ __device__ __forceinline__ void flush_group(const V (&acc)[9], int i0, float l1,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-source directions (3-4-source kernel variants only: the <= 2-source variants have no registers to spare,
+// measured 196 vs 183 us on c2): TWO ROWS of the strip ride the packed pipe (low half = row y, high half = row
+// y + 1 of the same source) instead of two sources of one row - the scalar path costs 250 warp instructions
+// per row segment against 165 for half of a packed pair.  Same stages as above; the projection constants are
+// broadcast, the target pixel / depth / row coordinate differ per half, and the depth-gradient numerator is
+// kept per half (each row writes its own gradient).  `vk[k]`: half k is a real pixel (x < W and, for the odd
+// last row of a run, k == 0).
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD>
+__device__ __forceinline__ void rowpair_pixel(const PairConst& pc, int i0, int plane, int H, int W, float xf, float2 yv,
+                                              float2 Dv, const float (&t)[2][3], float w_e, const bool (&vk)[2], bool pf,
+                                              float2 (&acc)[9], float& l1acc, float2& gpv) {
+    typedef float2 V;
+    V xv, eps, neg1, two;
+    v_bc(xv, xf); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f); v_bc(two, 2.0f);
+    // ---- stage A: project both rows ----------------------------------------------------------------
+    V cam[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float4 q = pc.Q[i0][r];
+        V qx, qy, qz, p3;
+        v_bc(qx, q.x); v_bc(qy, q.y); v_bc(qz, q.z); v_bc(p3, q.w);
+        cam[r] = v_fma(Dv, v_fma(qx, xv, v_fma(qy, yv, qz)), p3);
+    }
+    const V ze = v_add(cam[2], eps);
+    const V nze = v_mul(ze, neg1);
+    V inv;
+    {
+        float r0, r1;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(ze.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(ze.y));
+        inv = make_float2(r0, r1);
+    }
+    inv = v_mul(inv, v_fma(nze, inv, two));                  // Newton step
+    V px = v_mul(cam[0], inv), py = v_mul(cam[1], inv);
+    px = v_fma(v_fma(px, nze, cam[0]), inv, px);             // residual correction: IEEE-accurate quotient
+    py = v_fma(v_fma(py, nze, cam[1]), inv, py);
+    int x0[2], y0[2];
+    V fx, fy;
+    bool all_in = true;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float ixc = fminf(fmaxf(v_get(px, k), -2.0f), (float)(W + 1));
+        const float iyc = fminf(fmaxf(v_get(py, k), -2.0f), (float)(H + 1));
+        const float xfl = floorf(ixc), yfl = floorf(iyc);
+        x0[k] = (int)xfl; y0[k] = (int)yfl;
+        v_set(fx, k, ixc - xfl); v_set(fy, k, iyc - yfl);
+        all_in = all_in && (!vk[k] || (((unsigned)x0[k] < (unsigned)(W - 1)) && ((unsigned)y0[k] < (unsigned)(H - 1))));
+    }
+    // ---- stage B: 24 tap loads ----------------------------------------------------------------------
+    V v[3][4];
+    unsigned msk[2];
+    const float* __restrict__ cb = pc.src[i0];
+    if (__all_sync(0xffffffffu, all_in)) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int o00 = vk[k] ? y0[k] * W + x0[k] : 0;
+            const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
+            v_set(v[0][0], k, __ldg(cb + o00)); v_set(v[0][1], k, __ldg(cb + o00 + 1));
+            v_set(v[0][2], k, __ldg(cb + o01)); v_set(v[0][3], k, __ldg(cb + o01 + 1));
+            v_set(v[1][0], k, __ldg(cb + o10)); v_set(v[1][1], k, __ldg(cb + o10 + 1));
+            v_set(v[1][2], k, __ldg(cb + o11)); v_set(v[1][3], k, __ldg(cb + o11 + 1));
+            v_set(v[2][0], k, __ldg(cb + o20)); v_set(v[2][1], k, __ldg(cb + o20 + 1));
+            v_set(v[2][2], k, __ldg(cb + o21)); v_set(v[2][3], k, __ldg(cb + o21 + 1));
+            if (PH_PF_SRC > 0 && pf && k == 1) {
+                // the next pair of rows touches two new source rows below the lower footprint
+                const int opf = o01 + PH_PF_SRC * W;
+                prefetch_l1(cb + opf); prefetch_l1(cb + (opf + plane)); prefetch_l1(cb + (opf + 2 * plane));
+                prefetch_l1(cb + (opf + W)); prefetch_l1(cb + (opf + W + plane)); prefetch_l1(cb + (opf + W + 2 * plane));
+            }
+            msk[k] = vk[k] ? 15u : 0u;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const bool vx0 = (unsigned)x0[k] < (unsigned)W, vx1 = (unsigned)(x0[k] + 1) < (unsigned)W;
+            const bool vy0 = (unsigned)y0[k] < (unsigned)H, vy1 = (unsigned)(y0[k] + 1) < (unsigned)H;
+            const bool mnw = vk[k] && vx0 && vy0, mne = vk[k] && vx1 && vy0;
+            const bool msw = vk[k] && vx0 && vy1, mse = vk[k] && vx1 && vy1;
+            const int o00 = y0[k] * W + x0[k];
+            const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
+            v_set(v[0][0], k, ldg_pred(cb + o00, mnw)); v_set(v[0][1], k, ldg_pred(cb + o00 + 1, mne));
+            v_set(v[0][2], k, ldg_pred(cb + o01, msw)); v_set(v[0][3], k, ldg_pred(cb + o01 + 1, mse));
+            v_set(v[1][0], k, ldg_pred(cb + o10, mnw)); v_set(v[1][1], k, ldg_pred(cb + o10 + 1, mne));
+            v_set(v[1][2], k, ldg_pred(cb + o11, msw)); v_set(v[1][3], k, ldg_pred(cb + o11 + 1, mse));
+            v_set(v[2][0], k, ldg_pred(cb + o20, mnw)); v_set(v[2][1], k, ldg_pred(cb + o20 + 1, mne));
+            v_set(v[2][2], k, ldg_pred(cb + o21, msw)); v_set(v[2][3], k, ldg_pred(cb + o21 + 1, mse));
+            msk[k] = (mnw ? 1u : 0u) | (mne ? 2u : 0u) | (msw ? 4u : 0u) | (mse ? 8u : 0u);
+        }
+    }
+    // ---- stage C: blend, L1, gradient terms ----------------------------------------------------------
+    V Gx, Gy;
+    v_bc(Gx, 0.0f); v_bc(Gy, 0.0f);
+    float l1[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const V dA = v_sub(v[c][1], v[c][0]), dB = v_sub(v[c][3], v[c][2]);
+        const V top = v_fma(fx, dA, v[c][0]), bot = v_fma(fx, dB, v[c][2]);
+        const V dV = v_sub(bot, top);
+        const V proj = v_fma(fy, dV, top);
+        V sg;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float d = v_get(proj, k) - t[k][c];
+            l1[k] += fabsf(d);
+            if (GRAD) {
+                const float ne = (d != 0.0f) ? 1.0f : 0.0f;
+                v_set(sg, k, __int_as_float(__float_as_int(ne) | (__float_as_int(d) & 0x80000000)));
+            }
+        }
+        if (GRAD) {
+            Gx = v_fma(sg, v_fma(fy, v_sub(dB, dA), dA), Gx);
+            Gy = v_fma(sg, dV, Gy);
+        }
+    }
+    l1acc += (vk[0] ? l1[0] : 0.0f) + (vk[1] ? l1[1] : 0.0f);
+    if (GRAD) {
+        V gi;
+        V s = v_fma(Gx, px, v_mul(Gy, py));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const bool use = msk[k] != 0u;
+            v_set(gi, k, use ? w_e * v_get(inv, k) : 0.0f);
+            v_set(s, k, use ? v_get(s, k) : 0.0f);
+        }
+        const V gcx = v_mul(Gx, gi), gcy = v_mul(Gy, gi);
+        const V gcz = v_mul(v_mul(s, gi), neg1);
+        {
+            V q3[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { float w3; load_p3(pc, i0, r, w3); v_bc(q3[r], w3); }
+            gpv = v_add(gpv, v_fma(gcx, q3[0], v_fma(gcy, q3[1], v_mul(gcz, v_add(q3[2], eps)))));
+        }
+        const V hx = v_mul(gcx, Dv), hy = v_mul(gcy, Dv), hz = v_mul(gcz, Dv);
+        acc[0] = v_add(acc[0], hx); acc[1] = v_add(acc[1], hy); acc[2] = v_add(acc[2], hz);
+        acc[3] = v_fma(hx, yv, acc[3]); acc[4] = v_fma(hy, yv, acc[4]); acc[5] = v_fma(hz, yv, acc[5]);
+        acc[6] = v_add(acc[6], gcx); acc[7] = v_add(acc[7], gcy); acc[8] = v_add(acc[8], gcz);
+    }
+}
+
+// One run of a SINGLE-source pair (no image gradients): rows two at a time on the packed pipe.
+template <bool GRAD, bool MULTI, bool HEAD>
+__device__ __forceinline__ void run_rows_single(const plb_photo_args& a, const PairConst& pc, int strip, int y, int rows,
+                                                int lane, float* rec) {
+    const int H = a.H, W = a.W, plane = H * W;
+    const float w_e = pc.w_e;
+    const int x = strip * 32 + lane;
+    const bool valid = x < W;
+    const float xf = (float)x;
+    const float* __restrict__ tgt_b = pc.tgt;
+    const int xc = min(x, W - 1);
+    float2 acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = make_float2(0.0f, 0.0f);
+    float l1acc = 0.0f;
+    const int y_end = y + rows;
+    // software pipeline over row pairs: the target pixels of the NEXT pair are loaded while this one is processed
+    auto row_of = [&](int yy) -> int { return min(yy, H - 1) * W + xc; };   // the odd last row of a run repeats itself (masked)
+    float tn[2][3];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int o = row_of(y + k);
+        tn[k][0] = __ldg(tgt_b + o); tn[k][1] = __ldg(tgt_b + (o + plane)); tn[k][2] = __ldg(tgt_b + (o + 2 * plane));
+    }
+#pragma unroll 1
+    for (; y < y_end; y += 2) {
+        float t[2][3];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { t[k][0] = tn[k][0]; t[k][1] = tn[k][1]; t[k][2] = tn[k][2]; }
+        const bool pf = y + 2 < y_end;
+        if (pf) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int o = row_of(y + 2 + k);
+                tn[k][0] = __ldg(tgt_b + o); tn[k][1] = __ldg(tgt_b + (o + plane)); tn[k][2] = __ldg(tgt_b + (o + 2 * plane));
+            }
+        }
+        const bool vk[2] = {valid, valid && (y + 1 < y_end)};
+        const int o0 = row_of(y), o1 = row_of(y + 1);
+        const float2 yv = make_float2((float)y, (float)(y + 1));
+        const int n_scales = MULTI ? pc.n_scales : 1, lowres = MULTI ? pc.lowres : 0;
+#pragma unroll 1
+        for (int s = 0; s < n_scales; ++s) {
+            const float* disp_b = pc.disp[s];
+            const bool full = !((lowres >> s) & 1);
+            float2 Dv;
+            if (full) {
+                float d0 = __ldg(disp_b + o0), d1 = __ldg(disp_b + o1);
+                if (HEAD) { d0 = head_disp(d0, a.head_alpha, a.head_beta); d1 = head_disp(d1, a.head_alpha, a.head_beta); }
+                Dv = a.input_is_depth == PLB_INPUT_DEPTH ? make_float2(d0, d1)
+                                                         : make_float2(rcp_nr(fmaf(a.disp_a, d0, a.disp_b)), rcp_nr(fmaf(a.disp_a, d1, a.disp_b)));
+            } else {
+                const int dh = pc.dh[s], dw = pc.dw[s];
+                int x0, x1; float lx0, lx1;
+                up_coord(xc, pc.sx[s], dw, x0, x1, lx0, lx1);
+                float Dk[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    int y0, y1; float ly0, ly1;
+                    up_coord(min(y + k, H - 1), pc.sy[s], dh, y0, y1, ly0, ly1);
+                    float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
+                    float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
+                    if (HEAD) {
+                        v00 = head_disp(v00, a.head_alpha, a.head_beta); v01 = head_disp(v01, a.head_alpha, a.head_beta);
+                        v10 = head_disp(v10, a.head_alpha, a.head_beta); v11 = head_disp(v11, a.head_alpha, a.head_beta);
+                    }
+                    if (a.input_is_depth != PLB_INPUT_DEPTH) {
+                        v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
+                        v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
+                    }
+                    Dk[k] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+                }
+                Dv = make_float2(Dk[0], Dk[1]);
+            }
+            float2 gpv = make_float2(0.0f, 0.0f);
+            rowpair_pixel<GRAD>(pc, 0, plane, H, W, xf, yv, Dv, t, w_e, vk, pf && s == 0, acc, l1acc, gpv);
+            if (GRAD) {
+                float* g = pc.g_disp[s];
+                if (g != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (vk[k]) {
+                            const float D = v_get(Dv, k), gp = v_get(gpv, k);
+                            float gv = (full && a.input_is_depth != PLB_INPUT_DEPTH) ? a.disp_a * D * gp : -gp * rcp_nr(D);
+                            if (full && HEAD) gv *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
+                            g[k == 0 ? o0 : o1] = gv;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // both halves belong to the one source: fold them, then the usual warp reduction into the record
+    float accs[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) accs[k] = acc[k].x + acc[k].y;
+    flush_group<float, 1>(accs, 0, l1acc, xf, rec, lane);
+    __syncwarp();
+}
+
 // One run: consecutive rows [y, y + rows) of one 32-px strip of one (job, image) pair, NSRC sources.
 template <bool GRAD, bool IMG_GRAD, int NSRC, bool MULTI, bool HEAD>
 __device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairConst& pc, int strip, int y, int rows,
@@ -626,11 +867,13 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         const int n_src = pc.n_src;
         if (MAXSRC <= 2) {
             if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
+            else if (PH_ROWPAIR && MAXSRC > 2 && !IMG_GRAD) run_rows_single<GRAD, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
             else run_rows<GRAD, IMG_GRAD, 1, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
         } else {
             if (n_src == 4) run_rows<GRAD, IMG_GRAD, 4, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
             else if (n_src == 3) run_rows<GRAD, IMG_GRAD, 3, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
             else if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
+            else if (PH_ROWPAIR && MAXSRC > 2 && !IMG_GRAD) run_rows_single<GRAD, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
             else run_rows<GRAD, IMG_GRAD, 1, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
         }
         u += rows;
@@ -1180,7 +1423,9 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
             // (scalar) sources; the ratio is tuned per kernel variant (profiles/README.md)
             {
                 const int wp = maxsrc <= 2 ? PH_W_PAIR : PH_W_PAIR4, wo = maxsrc <= 2 ? PH_W_ODD : PH_W_ODD4;
-                p.unit_weight[j] = a->jobs[j].n_scales * (wp * (a->jobs[j].n_src / 2) + wo * (a->jobs[j].n_src & 1));
+                const int ws = PH_W_SINGLE4;      // a single-source job beside a 3-4-source one: row pairs on the packed pipe
+                const int n = a->jobs[j].n_src;
+                p.unit_weight[j] = a->jobs[j].n_scales * ((n == 1 && PH_ROWPAIR && maxsrc > 2 && !img_grad) ? ws : wp * (n / 2) + wo * (n & 1));
             }
             if (p.unit_weight[j] < min_w) min_w = p.unit_weight[j];
             wsum += (long long)p.unit_weight[j] * p.units_per_pair * a->B;

@@ -27,6 +27,9 @@ constexpr int PH_REC_ID = 63;
 #ifndef PH_PF_SRC
 #define PH_PF_SRC 1               // L1 prefetch of the source row this many rows below the current footprint (0 = off)
 #endif
+#ifndef PH_ROWPAIR
+#define PH_ROWPAIR 1                // single-source directions of the 3-4-source kernels: two rows per iteration on the packed pipe
+#endif
 #ifndef PH_MIN_BLOCKS
 #define PH_MIN_BLOCKS 3           // resident blocks per SM the <= 2-source kernels are compiled for
 #endif
@@ -36,6 +39,9 @@ constexpr int PH_REC_ID = 63;
 #endif
 #ifndef PH_W_ODD
 #define PH_W_ODD 5                // ... and of a single source (scalar pipe) in the unit weights, <= 2-source kernels
+#endif
+#ifndef PH_W_SINGLE4
+#define PH_W_SINGLE4 4             // a single-source job in the 3-4-source kernels (two rows per iteration on the packed pipe)
 #endif
 #ifndef PH_W_PAIR4
 #define PH_W_PAIR4 4              // the same for the 3-4-source kernels (both <= 8)
