@@ -934,6 +934,9 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
     __shared__ float s_g6[PF_COMBOS][6];
     __shared__ int s_col[PF_COMBOS];                   // pose column of each (job, source), -1 = unused
     const bool grads = want_grad && a.g_poses != nullptr;
+    // guarded relaunch (backward with unit upstream): leave before the Jacobians, not after them.  The upstream scalars
+    // were written before the MAIN kernel was launched (an ordinary launch), so they are readable ahead of the wait.
+    if (skip_launch(a.skip_if_unit)) return;
     if (tid < PF_COMBOS) {
         const int jb = tid / PLB_MAX_SRC, i = tid - jb * PLB_MAX_SRC;
         s_col[tid] = (jb < a.n_jobs && i < a.jobs[jb].n_src) ? a.jobs[jb].pose_index[i] : -1;
