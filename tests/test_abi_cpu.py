@@ -78,3 +78,15 @@ def test_ops_refuse_cpu_tensors(L):
     from geometry.pose_geometry import inverse_warp
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         inverse_warp(inp["tgt"], inp["disparity"][0][0], inp["poses"][:, 0], inp["intrinsics"], False)
+
+
+def test_integration_stub_matches_the_abi(L):
+    """The ctypes stub printed in INTEGRATION.md (what a reference maintainer would paste) mirrors the real structs."""
+    import ctypes as C
+    src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = src[src.index("class Job(C.Structure):"):src.index("lib.plb_photo_workspace_bytes.restype")]
+    ns = {"C": C}
+    exec(code, ns)
+    assert C.sizeof(ns["Job"]) == C.sizeof(L.PhotoJob)
+    assert C.sizeof(ns["Args"]) == C.sizeof(L.PhotoArgs)
+    assert [f[0] for f in ns["Args"]._fields_] == [f[0] for f in L.PhotoArgs._fields_]
