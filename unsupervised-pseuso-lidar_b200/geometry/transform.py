@@ -2,7 +2,10 @@
 only; the fused loss does not go through these)."""
 import torch
 
-from plb200 import ops
+
+def _ops():
+    from plb200 import ops      # lazy: a CPU-only loader worker that star-imports geometry.pose_geometry needs no .so
+    return ops
 
 
 class Transform():
@@ -25,7 +28,7 @@ class Transform():
 
     def reconstruct(self, depth, K):
         """`geometry/transform.py:74-105`: depth [B,H,W] -> Xc [B,3,H,W]."""
-        return ops.reconstruct(depth, K)
+        return _ops().reconstruct(depth, K)
 
     def k_hom(self, K):
         """`geometry/transform.py:107-112`, batch-agnostic."""
@@ -35,4 +38,4 @@ class Transform():
 
     def project(self, X, K, Tcw):
         """`geometry/transform.py:114-150`: X [B,3,H,W], Tcw [B,4,4] -> grid [B,H,W,2]."""
-        return ops.project(X, K, Tcw)
+        return _ops().project(X, K, Tcw)

@@ -28,12 +28,14 @@ _ws_cache = {}
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
-def _stream():
-    """Raw handle of torch's current stream on the current device (the fast private accessor when this torch has
-    it: `torch.cuda.current_stream()` costs ~18 us of Python per call, and a loss step asks six times)."""
+def _stream(device=None):
+    """Raw handle of torch's current stream on `device` (default: the current device) - the fast private accessor
+    when this torch has it: `torch.cuda.current_stream()` costs ~18 us of Python per call, and a loss step asks
+    six times."""
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
     if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
-    return torch.cuda.current_stream().cuda_stream
+        return _raw_stream(idx)
+    return torch.cuda.current_stream(idx).cuda_stream
 
 
 def _workspace(tag, nbytes, device):
@@ -49,9 +51,19 @@ def _workspace(tag, nbytes, device):
 
 
 def _need_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: the kernels are launched on that device's stream, and a
+    launch with another device's pointers would fault (or, with peer access, silently run on the wrong GPU)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("plb200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device.type)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError("plb200 ops launch on the current device (cuda:%d) but got a tensor on %s; wrap the "
+                               "call in `with torch.cuda.device(t.device):`" % (cur, t.device))
 
 
 def _f32c(t):
@@ -148,8 +160,8 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
             job.term_weight = 1.0 if cfg.mode == _lib.PHOTO_MIN_REPROJ else 1.0 / (entries * job.n_src)
             job.mode, job.flags = cfg.mode, cfg.flags
         nbytes = lib.plb_photo_workspace_bytes(a)
-        ws = _workspace("photo", nbytes, dev)
-        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        ws_photo = _workspace("photo", nbytes, dev)
+        a.workspace, a.workspace_bytes = ws_photo.data_ptr(), ws_photo.numel()
         check(lib.plb_photo_loss(a, st), "plb_photo_loss")
     if cfg.do_smooth:
         s_ = _lib.SmoothArgs()
@@ -170,17 +182,20 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
         if skip:
             s_.skip_if_unit[0], s_.skip_if_unit[1] = up_ptr[0], up_ptr[1]
         nbytes = lib.plb_smooth_workspace_bytes(s_)
-        ws = _workspace("smooth", nbytes, dev)
-        s_.workspace, s_.workspace_bytes = ws.data_ptr(), ws.numel()
+        ws_smooth = _workspace("smooth", nbytes, dev)
+        s_.workspace, s_.workspace_bytes = ws_smooth.data_ptr(), ws_smooth.numel()
         check(lib.plb_smooth_loss(s_, st), "plb_smooth_loss")
-    return (a if cfg.do_photo else None), (s_ if cfg.do_smooth else None), st
+    # the workspace tensors travel with the argument structs: a later, larger call replaces the cached buffer, and
+    # the guarded relaunch of THIS call must keep writing into memory that is still its own
+    return ((a if cfg.do_photo else None), (s_ if cfg.do_smooth else None), st,
+            (ws_photo if cfg.do_photo else None, ws_smooth if cfg.do_smooth else None))
 
 
 def _relaunch_guarded(args, up, scratch):
     """The backward pass of a fused forward: the SAME launches again (same buffers, same stream) with the real
     upstream scalars behind the device-side "all upstream == 1" guard.  The argument structs of the forward call
     are reused; only the upstream / guard / loss pointers change - rebuilding them costs ~80 us of Python."""
-    a, s_, st0 = args
+    a, s_, st0, _keepalive = args
     st = _stream()
     if st != st0:
         return False                                   # another stream: other workspaces - take the general path
