@@ -163,52 +163,79 @@ def dist_env():
 # --------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port of the reference's torch path, host cores
 # --------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, steps, warmup, budget_s=25.0):
-    """Times oracle/restated.py (`losses_forward` + backward: the same torch op
-    sequence as the reference's `Losses.forward`) on all host cores, on a bounded
-    sample of the workload (batch 4 - the only batch the reference itself runs at,
-    geometry/transform.py:110 - same H, W, sources, scales)."""
+def oracle_step(cfg, inp):
+    """One fwd+bwd of the reference's torch op sequence (oracle/restated.py, the restatement pinned to the unmodified
+    reference by tests/golden) on whatever device `inp` lives on."""
     from oracle import restated as O
+    disp = [[d.detach().clone().requires_grad_(True) for d in fr] for fr in inp["disparity"]]
+    poses = inp["poses"].detach().clone().requires_grad_(True)
+    if cfg["variant"] == "live":
+        loss = O.losses_forward(inp["tgt"], inp["ref_imgs"], disp, poses, inp["intrinsics"])
+        sum(loss).backward()
+        return loss[0].detach() + loss[1].detach()
+    depths = O.disp_to_depth(disp)
+    if cfg["variant"] == "min":
+        loss = O.min_reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[0], poses, inp["intrinsics"])
+    else:
+        loss = O.reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[:1], poses, inp["intrinsics"])
+    loss.backward()
+    return loss.detach()
+
+
+CPU_ARM_MAX_BATCH = 16
+
+
+def cpu_reference_run(cfg, steps, warmup, budget_s=25.0):
+    """Times the oracle port of the reference's `Losses.forward` + backward (same torch op sequence) on all host
+    cores, at the WORKLOAD'S OWN batch (capped at 16 images per step so that a step stays within seconds - the cap
+    only bites on c5 / headline64 - and stated in `sample`); same H, W, sources, scales, same synthetic frames."""
     from plb200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = min(4, cfg["B"])
+    Bs = min(CPU_ARM_MAX_BATCH, cfg["B"])
     n_src = cfg["n_src"]
-    inp = synth.make_photo_inputs(Bs, cfg["H"], cfg["W"], n_src=n_src, n_scales=cfg["n_scales"], seed=1234)
-
-    def step():
-        disp = [[d.clone().requires_grad_(True) for d in fr] for fr in inp["disparity"]]
-        poses = inp["poses"].clone().requires_grad_(True)
-        if cfg["variant"] == "live":
-            loss = O.losses_forward(inp["tgt"], inp["ref_imgs"], disp, poses, inp["intrinsics"])
-            sum(loss).backward()
-        elif cfg["variant"] == "min":
-            depths = O.disp_to_depth(disp)
-            loss = O.min_reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[0], poses, inp["intrinsics"])
-            loss.backward()
-        else:
-            depths = O.disp_to_depth(disp)
-            loss = O.reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[:1], poses, inp["intrinsics"])
-            loss.backward()
-        return float(sum(loss)) if isinstance(loss, list) else float(loss)
-
+    inp = synth.make_photo_inputs(Bs, cfg["H"], cfg["W"], n_src=n_src, n_scales=cfg["n_scales"], seed=1234,
+                                  n_depth_frames=2 if cfg["variant"] == "live" else 1)
     t_start = time.perf_counter()
-    for _ in range(max(1, min(warmup, 2))):
-        step()
+    n_warm = max(1, min(warmup, 2))
+    for _ in range(n_warm):
+        float(oracle_step(cfg, inp))
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        step()
+        float(oracle_step(cfg, inp))
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_start > budget_s and len(times) >= 3:
             break
     mean = sum(times) / len(times)
     mpix = Bs * cfg["H"] * cfg["W"] / 1e6
     return {"value": mpix / mean, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "oracle port of Losses.forward+backward (torch CPU, %d threads), batch %d of the workload's "
-                      "%dx%d / %d sources / %d scales, mean of %d steps" % (
-                          cores, Bs, cfg["H"], cfg["W"], n_src, cfg["n_scales"], len(times)),
-            "ms_per_step": mean * 1e3, "steps": len(times)}
+            "sample": "oracle port of Losses.forward+backward (torch CPU, %d threads), batch %d (workload batch %d) of "
+                      "the workload's %dx%d / %d sources / %d scales, %d warm-up + mean of %d steps" % (
+                          cores, Bs, cfg["B"], cfg["H"], cfg["W"], n_src, cfg["n_scales"], n_warm, len(times)),
+            "ms_per_step": mean * 1e3, "steps": len(times), "warmup": n_warm, "batch": Bs}
+
+
+def gpu_eager_run(cfg, gpu_sets, dev, iters=10, warmup=3):
+    """The real incumbent: the reference's stock torch-eager op
+    sequence ON THE SAME B200, same config, same device-resident synthetic frames, CUDA-event timed.  A LIBRARY
+    baseline (ATen sm_100 kernels), not our code: `oracle/restated.py` on CUDA tensors is that op sequence, batch
+    agnostic where the reference hard-codes batch 4 (geometry/transform.py:110)."""
+    st = torch.cuda.current_stream()
+    for i in range(warmup):
+        oracle_step(cfg, gpu_sets[i % len(gpu_sets)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(iters):
+        oracle_step(cfg, gpu_sets[i % len(gpu_sets)])
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    px = cfg["B"] * cfg["H"] * cfg["W"]
+    return {"value": px / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": iters, "warmup": warmup,
+            "kind": "torch-eager CUDA (stock ATen kernels, the reference's op sequence) on the same GPU, same config "
+                    "and device-resident inputs; library baseline, timed with CUDA events"}
 
 
 def run_reference_arm(args, cfg):
@@ -217,9 +244,11 @@ def run_reference_arm(args, cfg):
         return
     r = cpu_reference_run(cfg, args.steps, args.warmup, budget_s=120.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": r["steps"], "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"],
+            "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, cfg)},
+            "config": {"workload": workload_name(args.workload, cfg), "cpu_arm_batch": r["batch"],
+                       "note": "CPU arm = oracle port of the reference's torch path (the Python reference cannot travel "
+                               "to the GPU box); per-pixel throughput at batch %d of the workload's %d" % (r["batch"], cfg["B"])},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -365,6 +394,9 @@ def run_ours(args, cfg):
             except ValueError:
                 pass
         cpu = cpu_reference_run(cfg, 6, 1) if (world == 1 and not args.no_cpu) else None
+        eager = gpu_eager_run(cfg, gpu_sets, dev) if (world == 1 and not args.no_eager) else None
+        if eager:
+            eager["ours_over_eager"] = value / eager["value"]
         others = None
         if world == 1 and not args.no_cloud:
             # the other photometric compositions on the same frames (kernel-only, same method as `roofline`)
@@ -379,6 +411,10 @@ def run_ours(args, cfg):
                 others[name] = {"workload": workload_name(name, ocfg), "kernel_ms": oms,
                                 "mpix_s": ocfg["B"] * ocfg["H"] * ocfg["W"] / 1e6 / (oms / 1e3),
                                 "achieved_gbs": ob / (oms / 1e3) / 1e9, "frac": ob / (oms / 1e3) / 1e9 / peak}
+                if not args.no_eager and name != "headline64":
+                    oe = gpu_eager_run(ocfg, osets, dev, iters=5, warmup=2)
+                    others[name]["gpu_eager_baseline"] = {"mpix_s": oe["value"], "ms_per_step": oe["ms_per_step"],
+                                                          "kernel_over_eager": others[name]["mpix_s"] / oe["value"]}
                 del osets
         cloud = velo = None
         if world == 1 and not args.no_cloud:
@@ -403,6 +439,7 @@ def run_ours(args, cfg):
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": abytes,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650"},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "gpu_eager_baseline": eager,
             "cloud": cloud,
             "velo": velo,
             "other_workloads": others,
@@ -600,6 +637,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cloud", action="store_true", help="skip the secondary pseudo-LiDAR (config C4) timing")
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-CUDA incumbent (gpu_eager_baseline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = WORKLOADS[args.workload]

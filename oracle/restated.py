@@ -3,7 +3,9 @@
 CPU restatement (torch, fp32 like the reference; fp64 numpy for the point
 cloud) of the reference's view-synthesis hot path.  Every function cites the
 reference file:line it follows.  It is batch-size agnostic (the reference only
-runs at B=4 on CUDA, `geometry/transform.py:110,134`) and differentiable
+runs at B=4 on CUDA, `geometry/transform.py:110,134`), device agnostic (every
+tensor it creates follows its inputs: on CUDA tensors it IS the reference's stock
+torch-eager op sequence, which `bench.py` times as `gpu_eager_baseline`) and differentiable
 through torch autograd, so it gives the gradients the CUDA backward is checked
 against.
 
@@ -59,7 +61,7 @@ def rot_from_axisangle(vec):
 def get_translation_matrix(t):
     """`geometry/pose_geometry.py:138-153`: [B,*,3] -> [B,4,4] identity with t in column 3."""
     B = t.shape[0]
-    T = torch.eye(4, dtype=t.dtype).repeat(B, 1, 1)
+    T = torch.eye(4, dtype=t.dtype, device=t.device).repeat(B, 1, 1)
     T = T.clone()
     T[:, :3, 3] = t.reshape(B, 3)
     return T
@@ -81,7 +83,7 @@ def invert_pose(T):
     Rt = T[:, :3, :3].transpose(-2, -1)
     tinv = torch.bmm(-1.0 * Rt, T[:, :3, 3:4])
     top = torch.cat([Rt, tinv], dim=2)
-    bottom = torch.tensor([0, 0, 0, 1], dtype=T.dtype).view(1, 1, 4).repeat(len(T), 1, 1)
+    bottom = torch.tensor([0, 0, 0, 1], dtype=T.dtype, device=T.device).view(1, 1, 4).repeat(len(T), 1, 1)
     return torch.cat([top, bottom], dim=1)
 
 
@@ -114,10 +116,10 @@ def pose_vec2mat(vec, mode="euler"):
 # geometry/transform.py
 # --------------------------------------------------------------------------
 
-def image_grid(B, H, W, dtype):
+def image_grid(B, H, W, dtype, device=None):
     """`geometry/transform.py:14-72`: [B,3,H,W] of (x=0..W-1, y=0..H-1, 1)."""
-    xs = torch.linspace(0, W - 1, W, dtype=dtype)
-    ys = torch.linspace(0, H - 1, H, dtype=dtype)
+    xs = torch.linspace(0, W - 1, W, dtype=dtype, device=device)
+    ys = torch.linspace(0, H - 1, H, dtype=dtype, device=device)
     ys, xs = torch.meshgrid([ys, xs], indexing="ij")
     xs, ys = xs.repeat([B, 1, 1]), ys.repeat([B, 1, 1])
     return torch.stack([xs, ys, torch.ones_like(xs)], dim=1)
@@ -128,14 +130,14 @@ def reconstruct(depth, K):
     depth = depth.unsqueeze(1)
     B, _, H, W = depth.shape
     Kinv = K.inverse().to(depth.dtype)   # `.float()` in the reference (depth is fp32 there)
-    grid = image_grid(B, H, W, depth.dtype).view(B, 3, -1)
+    grid = image_grid(B, H, W, depth.dtype, depth.device).view(B, 3, -1)
     return Kinv.bmm(grid).view(B, 3, H, W) * depth
 
 
 def k_hom(K, dtype=torch.float32):
     """`geometry/transform.py:107-112` with the hard-coded batch 4 replaced by K's
     (fp32 in the reference; `dtype` exists for the fp64 accuracy study in the tests)."""
-    Kh = torch.eye(4, dtype=dtype).reshape(1, 4, 4).repeat(K.shape[0], 1, 1)
+    Kh = torch.eye(4, dtype=dtype, device=K.device).reshape(1, 4, 4).repeat(K.shape[0], 1, 1)
     Kh[:, :3, :3] = K.clone()
     return Kh
 
@@ -144,7 +146,7 @@ def project(X, K, Tcw):
     """`geometry/transform.py:114-150`: pixel grid in [-1,1] for grid_sample."""
     B, _, H, W = X.shape
     Xc = X.view(B, 3, -1)
-    ones = torch.ones(1, Xc.shape[-1], dtype=X.dtype).repeat(B, 1, 1)
+    ones = torch.ones(1, Xc.shape[-1], dtype=X.dtype, device=X.device).repeat(B, 1, 1)
     Xh = torch.cat([Xc, ones], 1)
     Tx = (k_hom(K, X.dtype) @ Tcw)[:, :3, :]
     cam = Tx @ Xh
@@ -161,7 +163,7 @@ def pose_matrix(pose, pose_inv, rotation_mode="axisangle"):
     (`notes/toy_problem/geometry/pose_geometry.py:126`)."""
     if rotation_mode == "euler":
         M34 = pose_vec2mat(pose, "euler")
-        bottom = torch.tensor([0, 0, 0, 1], dtype=M34.dtype).view(1, 1, 4).repeat(len(M34), 1, 1)
+        bottom = torch.tensor([0, 0, 0, 1], dtype=M34.dtype, device=M34.device).view(1, 1, 4).repeat(len(M34), 1, 1)
         Tcw = torch.cat([M34, bottom], dim=1)
     else:
         trans, rot = pose[:, 3:].unsqueeze(1), pose[:, :3].unsqueeze(1)
