@@ -12,6 +12,10 @@ from losses import Losses  # noqa: E402
 
 bench.WORKLOADS["headline64"] = dict(B=64, H=192, W=640, n_src=2, n_scales=1, variant="dir0")
 bench.WORKLOADS["headline4"] = dict(B=4, H=192, W=640, n_src=2, n_scales=1, variant="dir0")
+# single-direction pieces of the live composition (tuning the cost model of the unit list): d<n_src>s<n_scales>
+for _ns in (1, 2, 3):
+    for _sc in (1, 2, 3, 4):
+        bench.WORKLOADS["d%ds%d" % (_ns, _sc)] = dict(B=12, H=192, W=640, n_src=_ns, n_scales=_sc, variant="dir0")
 dev = torch.device("cuda:0")
 for wl in (sys.argv[1:] or ["headline", "c2", "headline64"]):
     cfg = bench.WORKLOADS[wl]

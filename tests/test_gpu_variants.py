@@ -47,15 +47,25 @@ def _check(inp, n_frames, **kw):
     # reference's - moves them by ~1/n_samples, i.e. several 1e-4; the per-pixel maps below pin the number
     # of such samples to a handful, and the full-size tests (test_gpu_live.py) hold the 1e-4 bar.
     e32 = rel_err(rp.grad, xp.grad)
+    print("loss rel err %.2e; pose-gradient rel err vs fp64: ours %.2e, fp32 reference %.2e" % (
+        abs(float(loss) - float(rl)) / abs(float(rl)), rel_err(p.grad.cpu(), xp.grad), e32))
     n_samples = inp["tgt"].shape[0] * inp["tgt"].shape[2] * inp["tgt"].shape[3] * len(inp["ref_imgs"])
     assert rel_err(p.grad.cpu(), xp.grad) < max(GRAD_TOL, 3 * e32, 8.0 / n_samples), (e32, n_samples)
+    full = inp["tgt"].shape[0] * inp["tgt"].shape[2] * inp["tgt"].shape[3]
     for f in range(n_frames):
-        for a, b32, b64 in zip(disp[f], rd[f], xd[f]):
+        # every (full-resolution pixel, source) sample whose footprint a rounding difference moves across a cell
+        # boundary changes the gradient of the map element it feeds: the budget counts SAMPLES (a low-resolution
+        # element collects 4^s pixels x n_src sources), not elements of the map
+        n_src_f = len(inp["ref_imgs"]) if f == 0 else 1
+        for si, (a, b32, b64) in enumerate(zip(disp[f], rd[f], xd[f])):
             x = b64.grad
             scale = float(x.abs().max())
             bad = int(((a.grad.cpu().double() - x).abs() > GRAD_TOL * scale).sum())
             bad_ref = int(((b32.grad.double() - x).abs() > GRAD_TOL * scale).sum())
-            assert bad <= max(4, int(5e-4 * x.numel())) + 4 * bad_ref, (f, bad, bad_ref)
+            budget = max(4, int(5e-4 * full * n_src_f)) + 4 * bad_ref
+            print("frame %d scale %d: %d of %d elements beyond %.0e (fp32 reference: %d, budget %d)" % (
+                f, si, bad, x.numel(), GRAD_TOL, bad_ref, budget))
+            assert bad <= budget, (f, si, bad, bad_ref)
 
 
 @pytest.mark.parametrize("n_src,S,n_frames", [(1, 1, 1), (3, 1, 1), (4, 2, 1), (3, 4, 2), (2, 3, 2)])

@@ -9,6 +9,14 @@ namespace plb {
 
 extern unsigned long long g_launches;  // host-side counter (api.cu)
 
+// per-device host-side caches (function attributes, occupancy, SM count): a process may drive several GPUs
+constexpr int PLB_MAX_DEVICES = 64;
+static inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { (void)cudaGetLastError(); d = 0; }
+    return (d >= 0 && d < PLB_MAX_DEVICES) ? d : 0;
+}
+
 #define PLB_CHECK_LAUNCH()                            \
     do {                                              \
         cudaError_t e__ = cudaGetLastError();         \

@@ -1,25 +1,31 @@
 // Fused photometric reprojection loss (live mode: warp + L1 mean), forward and
 // gradients in one pass.  See DESIGN.md "photo_l1_kernel".
 //
-// Work decomposition.  The unit of work is one ROW SEGMENT: 32 consecutive
-// pixels of one row of one target image of one job (direction), processed by
-// one warp: every global access of the warp - target pixels, disparity, the
-// 2x2x3 bilinear taps of each source - is a (nearly) contiguous 128-byte piece
-// of a planar NCHW row.  Units are ordered (job, image, 32-px column strip, row),
-// so a warp that walks its units moves DOWN a strip and re-uses the source rows
-// it has just pulled into L1.
+// Work decomposition.  What one warp evaluates per target pixel is a COMBO: two (source, scale) samples riding the
+// two halves of Blackwell's packed fp32 pipe - two sources at one scale, or ONE source at TWO scales (same pixel
+// ray, two depths) - or a single sample on the scalar pipe when a job has an odd number of them.  The unit of work
+// is one ROW SEGMENT of one combo: 32 consecutive pixels of one row of one target image of one job (direction),
+// processed by one warp: every global access of the warp - target pixels, disparity, the 2x2x3 bilinear taps of
+// each sample - is a (nearly) contiguous 128-byte piece of a planar NCHW row.  Units are ordered (job, image,
+// 32-px column strip, combo, row), so a warp that walks its units moves DOWN a strip and re-uses the source rows it
+// has just pulled into L1.
 //
-// The grid is persistent: 148 x (resident blocks per SM) blocks, and the weighted
-// unit list (a unit costs n_scales x n_src warps) is cut into equal contiguous
-// ranges, one per warp, so the tail is one row segment long instead of one tile.
-// A block's range touches at most two (job, image) pairs; K^-1 and P = K.[R|t]
-// for both are built once in the block prologue and kept in shared memory.
+// The grid is persistent: SMs x (resident blocks per SM) blocks, and the weighted unit list is cut into equal
+// contiguous ranges, one per warp, so the tail is a few row segments long instead of one tile.  A block's range
+// touches at most two (job, image) pairs; K^-1 and P = K.[R|t] for both are built once in the block prologue and
+// kept in shared memory.
 //
-// Reductions (loss, 3x4 projection-matrix gradient per source) are kept in
-// registers across a warp's run of rows, reduced warp -> block record in a fixed
-// order; a small finalize kernel (one block per image) sums the records of each
-// (job, image) pair, runs the pose chain and adds the loss: no atomics on the
-// results, bitwise repeatable, and no fence / ticket traffic in the main kernel.
+// Low-resolution scales (F.interpolate of the DEPTH, losses.py:214-215): the warp walks down rows, so the two
+// low-resolution depth rows it interpolates between live in registers and are replaced as the window advances
+// (streaming upsample: two FMAs per pixel instead of four loads and four reciprocals); the TRANSPOSED upsample of
+// the gradient runs the same way in the other direction - every lane accumulates its column's contribution to the
+// two low-resolution rows in registers and leaves one value per low-resolution row; photo_lowres_merge_kernel then
+// gathers the columns.  No full-resolution scratch plane is written or read for these scales.
+//
+// Reductions (loss, 3x4 projection-matrix gradient per source) are kept in registers across a warp's run of rows,
+// reduced warp -> block record in a fixed order; a small finalize kernel (one block per image) sums the records of
+// each (job, image) pair, runs the pose chain and adds the loss: no atomics on the results, bitwise repeatable, and
+// no fence / ticket traffic in the main kernel.
 #include "photo_common.cuh"
 
 namespace plb {
@@ -39,25 +45,22 @@ __device__ __forceinline__ void dbg_stamp(int slot) {
 #endif
 
 // ---------------------------------------------------------------------------------------------
-// Per-pixel stages.  A "group" is one or two sources handled together.  For a pair of sources all
-// floating-point work runs on Blackwell's packed fp32 pipe (FFMA2 / FADD2 / FMUL2: source 0 in the
-// low half, source 1 in the high half of a 64-bit register pair), which halves the issue slots of
-// the arithmetic; the coordinates of every source of the group are computed first, ONE warp vote
-// decides between the unpredicated and the predicated tap loads, all 12 x NS loads are issued back
-// to back, and only then is anything blended.
+// Per-pixel stages.  The two halves of a combo ride the packed fp32 pipe (FFMA2 / FADD2 / FMUL2: half 0 in the
+// low, half 1 in the high half of a 64-bit register pair), which halves the issue slots of the arithmetic; the
+// coordinates of both halves are computed first, ONE warp vote decides between the unpredicated and the
+// predicated tap loads, all 12 x NS loads are issued back to back, and only then is anything blended.
 //
-// Projection: cam = D * A + p3 with A = Q . (x, y, 1), Q = P[:, :3] . K^-1 (composed in fp64 in
-// the block prologue, rounded once): the ray is never formed.  The perspective divide is one
-// MUFU.RCP + one Newton step + a residual correction (as accurate as an IEEE divide: the sample
-// position is the difference of two ~W-sized numbers, every ulp of px is 6e-5 px of bilinear
-// weight); the normalise / un-normalise chain of the reference (transform.py:143-148 +
-// grid_sample) is the identity and is dropped; the bilinear blend is written as nested lerps
-// whose intermediates ARE the coordinate derivatives (d proj / d iy = bot - top).
+// Projection: cam = D * A + p3 with A = Q . (x, y, 1), Q = P[:, :3] . K^-1 (composed in fp64 in the block
+// prologue, rounded once): the ray is never formed, and the x part of A (the lane's column is fixed for a whole
+// run) is hoisted out of the row loop.  The perspective divide is one MUFU.RCP + one Newton step + a residual
+// correction (as accurate as an IEEE divide: the sample position is the difference of two ~W-sized numbers, every
+// ulp of px is 6e-5 px of bilinear weight); the normalise / un-normalise chain of the reference
+// (transform.py:143-148 + grid_sample) is the identity and is dropped; the bilinear blend is written as nested
+// lerps whose intermediates ARE the coordinate derivatives (d proj / d iy = bot - top).
 //
-// Depth gradient: d loss / d D = g_cam . A.  Because g_cam . (cx, cy, ze) = 0 identically (the
-// perspective divide is scale invariant) and (cx, cy, ze) = D * A + p3', this equals
-// -(g_cam . p3') / D - the analytically cancelled form, free of the ~W-sized cancellation the
-// chain-rule form carries, and A need not stay live across the loads.
+// Depth gradient: d loss / d D = g_cam . A.  Because g_cam . (cx, cy, ze) = 0 identically (the perspective divide
+// is scale invariant) and (cx, cy, ze) = D * A + p3', this equals -(g_cam . p3') / D - the analytically cancelled
+// form, free of the ~W-sized cancellation the chain-rule form carries, and A need not stay live across the loads.
 // ---------------------------------------------------------------------------------------------
 template <int NS> struct Vec;
 template <> struct Vec<1> { typedef float T; };
@@ -80,27 +83,42 @@ __device__ __forceinline__ void v_set(float2& v, int k, float s) { if (k == 0) v
 __device__ __forceinline__ float v_hsum(float v) { return v; }
 __device__ __forceinline__ float v_hsum(float2 v) { return v.x + v.y; }
 
-// row r of [Q | p3] for the group starting at source i0: x / y / constant coefficient and p3
-__device__ __forceinline__ void load_q(const PairConst& pc, int i0, int r, float& qx, float& qy, float& qz, float& qw) {
-    const float4 q = pc.Q[i0][r];
-    qx = q.x; qy = q.y; qz = q.z; qw = q.w;
-}
-__device__ __forceinline__ void load_q(const PairConst& pc, int i0, int r, float2& qx, float2& qy, float2& qz, float2& qw) {
-    const float4 a = pc.Q2[i0 >> 1][r][0], b = pc.Q2[i0 >> 1][r][1];
-    qx = make_float2(a.x, a.y); qy = make_float2(a.z, a.w); qz = make_float2(b.x, b.y); qw = make_float2(b.z, b.w);
-}
+// where the constants of a combo live: T2 table `tab` for a packed combo, Q[k0] for a single sample
+struct ComboRef { int tab, k0; };
 
+// hoisted x part of A: Ax[r] = qx * x + qz
+__device__ __forceinline__ void load_ax(const PairConst& pc, ComboRef c, float xf, float (&Ax)[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { const float4 q = pc.Q[c.k0][r]; Ax[r] = fmaf(q.x, xf, q.z); }
+}
+__device__ __forceinline__ void load_ax(const PairConst& pc, ComboRef c, float xf, float2 (&Ax)[3]) {
+    const float2 xv = make_float2(xf, xf);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float4 t = pc.T2[c.tab][r][0];
+        Ax[r] = __ffma2_rn(make_float2(t.x, t.y), xv, make_float2(t.z, t.w));
+    }
+}
+// per row: y coefficient and p3 of cam row r
+__device__ __forceinline__ void load_qy(const PairConst& pc, ComboRef c, int r, float& qy, float& p3) {
+    const float4 q = pc.Q[c.k0][r];
+    qy = q.y; p3 = q.w;
+}
+__device__ __forceinline__ void load_qy(const PairConst& pc, ComboRef c, int r, float2& qy, float2& p3) {
+    const float4 t = pc.T2[c.tab][r][1];
+    qy = make_float2(t.x, t.y); p3 = make_float2(t.z, t.w);
+}
 // p3 re-read from shared memory (asm volatile: a fresh load, not a value held in registers across the taps)
-__device__ __forceinline__ void load_p3(const PairConst& pc, int i0, int r, float& w) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(&pc.Q[i0][r].w);
+__device__ __forceinline__ void load_p3(const PairConst& pc, ComboRef c, int r, float& w) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(&pc.Q[c.k0][r].w);
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(a));
 }
-__device__ __forceinline__ void load_p3(const PairConst& pc, int i0, int r, float2& w) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(&pc.Q2[i0 >> 1][r][1].z);
+__device__ __forceinline__ void load_p3(const PairConst& pc, ComboRef c, int r, float2& w) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(&pc.T2[c.tab][r][1].z);
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w.x), "=f"(w.y) : "r"(a));
 }
 
-// coordinates of one group of sources at one depth (stage A output)
+// coordinates of the samples of one combo at one pixel (stage A output)
 template <int NS>
 struct GState {
     typename Vec<NS>::T inv, px, py, fx, fy;
@@ -108,20 +126,20 @@ struct GState {
     bool all_in;
 };
 
-// stage A: project the pixel into every source of the group
+// stage A: project the pixel into the source of every half
 template <int NS>
-__device__ __forceinline__ void group_project(const PairConst& pc, int i0, int H, int W, float xf, float yf, float D,
+__device__ __forceinline__ void group_project(const PairConst& pc, ComboRef c, int H, int W,
+                                              const typename Vec<NS>::T (&Ax)[3], float yf, typename Vec<NS>::T Dv,
                                               GState<NS>& g) {
     typedef typename Vec<NS>::T V;
-    V xv, yv, Dv, eps, neg1, two;
-    v_bc(xv, xf); v_bc(yv, yf); v_bc(Dv, D); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f); v_bc(two, 2.0f);
+    V yv, eps, neg1, two;
+    v_bc(yv, yf); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f); v_bc(two, 2.0f);
     V cam[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        V qx, qy, qz;
-        V p3;
-        load_q(pc, i0, r, qx, qy, qz, p3);
-        cam[r] = v_fma(Dv, v_fma(qx, xv, v_fma(qy, yv, qz)), p3);
+        V qy, p3;
+        load_qy(pc, c, r, qy, p3);
+        cam[r] = v_fma(Dv, v_fma(qy, yv, Ax[r]), p3);
     }
     const V ze = v_add(cam[2], eps);
     const V nze = v_mul(ze, neg1);
@@ -150,35 +168,35 @@ __device__ __forceinline__ void group_project(const PairConst& pc, int i0, int H
     g.inv = inv; g.px = px; g.py = py; g.all_in = all_in;
 }
 
-// stage B: issue the 12 x NS tap loads (one warp vote picks unpredicated or predicated loads)
-template <int NS>
-__device__ __forceinline__ void group_load(const PairConst& pc, int i0, int plane, int H, int W, bool valid, bool pf,
+// stage B: issue the 12 x NS tap loads (one warp vote picks unpredicated or predicated loads).  With compile-time
+// image dimensions every tap of a sample is ONE 64-bit address plus an immediate offset.
+template <int NS, bool ALL_VALID>
+__device__ __forceinline__ void group_load(const float* const (&cbp)[NS], int plane, int H, int W, bool valid, bool pf,
                                            const GState<NS>& g, typename Vec<NS>::T (&v)[3][4], unsigned (&msk)[NS]) {
-    typedef typename Vec<NS>::T V;
     const bool all_in = g.all_in;
     if (__all_sync(0xffffffffu, all_in || !valid)) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            const float* __restrict__ cb = pc.src[i0 + k];
-            const int o00 = (all_in && valid) ? g.y0[k] * W + g.x0[k] : 0;
-            const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
-            v_set(v[0][0], k, __ldg(cb + o00)); v_set(v[0][1], k, __ldg(cb + o00 + 1));
-            v_set(v[0][2], k, __ldg(cb + o01)); v_set(v[0][3], k, __ldg(cb + o01 + 1));
-            v_set(v[1][0], k, __ldg(cb + o10)); v_set(v[1][1], k, __ldg(cb + o10 + 1));
-            v_set(v[1][2], k, __ldg(cb + o11)); v_set(v[1][3], k, __ldg(cb + o11 + 1));
-            v_set(v[2][0], k, __ldg(cb + o20)); v_set(v[2][1], k, __ldg(cb + o20 + 1));
-            v_set(v[2][2], k, __ldg(cb + o21)); v_set(v[2][3], k, __ldg(cb + o21 + 1));
-            if (PH_PF_SRC > 0 && pf) {
+            // (when every lane is a pixel the vote already says that every footprint is interior)
+            const int o00 = (ALL_VALID || (all_in && valid)) ? g.y0[k] * W + g.x0[k] : 0;
+            const float* __restrict__ q = cbp[k] + o00;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                v_set(v[c][0], k, __ldg(q + c * plane)); v_set(v[c][1], k, __ldg(q + (c * plane + 1)));
+                v_set(v[c][2], k, __ldg(q + (c * plane + W))); v_set(v[c][3], k, __ldg(q + (c * plane + W + 1)));
+            }
+            if (PH_PF_SRC > 0 && pf && (NS == 1 || k == 0 || cbp[NS - 1] != cbp[0])) {
                 // the warp walks DOWN a strip: the source row the next unit(s) will newly touch, one line per channel
-                const int opf = o01 + PH_PF_SRC * W;
-                prefetch_l1(cb + opf); prefetch_l1(cb + (opf + plane)); prefetch_l1(cb + (opf + 2 * plane));
+                // (a scale pair samples ONE source twice, a few pixels apart: one prefetch serves both halves)
+                const int opf = W + PH_PF_SRC * W;
+                prefetch_l1(q + opf); prefetch_l1(q + (opf + plane)); prefetch_l1(q + (opf + 2 * plane));
             }
             msk[k] = valid ? 15u : 0u;
         }
     } else {
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            const float* __restrict__ cb = pc.src[i0 + k];
+            const float* __restrict__ cb = cbp[k];
             const bool vx0 = (unsigned)g.x0[k] < (unsigned)W, vx1 = (unsigned)(g.x0[k] + 1) < (unsigned)W;
             const bool vy0 = (unsigned)g.y0[k] < (unsigned)H, vy1 = (unsigned)(g.y0[k] + 1) < (unsigned)H;
             const bool mnw = valid && vx0 && vy0, mne = valid && vx1 && vy0;
@@ -196,15 +214,16 @@ __device__ __forceinline__ void group_load(const PairConst& pc, int i0, int plan
     }
 }
 
-// stage C: blend, L1, gradient terms
+// stage C: blend, L1, gradient terms.  `gpv`: per half, g_cam . p3' (the depth-gradient numerator).
 template <bool GRAD, bool IMG_GRAD, int NS>
-__device__ __forceinline__ void group_blend(const PairConst& pc, int i0, int plane, int W, float yf, float D,
-                                            const float (&t)[3], float w_e, bool valid, const GState<NS>& g,
-                                            const typename Vec<NS>::T (&v)[3][4], const unsigned (&msk)[NS],
-                                            typename Vec<NS>::T (&acc)[9], float& l1acc, float& gp, float (&gt)[3]) {
+__device__ __forceinline__ void group_blend(const PairConst& pc, ComboRef cr, float* const (&gsp)[NS], int plane, int W,
+                                            float yf, typename Vec<NS>::T Dv, const float (&t)[3], float w_e, bool valid,
+                                            const GState<NS>& g, const typename Vec<NS>::T (&v)[3][4],
+                                            const unsigned (&msk)[NS], typename Vec<NS>::T (&acc)[9], float& l1acc,
+                                            typename Vec<NS>::T& gpv, float (&gt)[3]) {
     typedef typename Vec<NS>::T V;
-    V yv, Dv, eps, neg1;
-    v_bc(yv, yf); v_bc(Dv, D); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f);
+    V yv, eps, neg1;
+    v_bc(yv, yf); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f);
     V Gx, Gy;
     v_bc(Gx, 0.0f); v_bc(Gy, 0.0f);
     float l1 = 0.0f;
@@ -249,8 +268,8 @@ __device__ __forceinline__ void group_blend(const PairConst& pc, int i0, int pla
         {
             V q3[3];   // p3 again (shared memory): cheaper than six registers held across the loads
 #pragma unroll
-            for (int r = 0; r < 3; ++r) load_p3(pc, i0, r, q3[r]);
-            gp += v_hsum(v_fma(gcx, q3[0], v_fma(gcy, q3[1], v_mul(gcz, v_add(q3[2], eps)))));
+            for (int r = 0; r < 3; ++r) load_p3(pc, cr, r, q3[r]);
+            gpv = v_fma(gcx, q3[0], v_fma(gcy, q3[1], v_mul(gcz, v_add(q3[2], eps))));
         }
         // d loss / d P[r][:] = sum g_cam[r] * (D * ray, 1), ray = K^-1 (x, y, 1): accumulated in pixel
         // coordinates - sum h_r, sum h_r * y (and x * sum h_r at the flush, x being fixed per lane) - and
@@ -265,7 +284,7 @@ __device__ __forceinline__ void group_blend(const PairConst& pc, int i0, int pla
             for (int k = 0; k < NS; ++k) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) gt[c] -= m * e[k][c];
-                float* gbase = pc.g_src[i0 + k];
+                float* gbase = gsp[k];
                 if (gbase != nullptr) {
                     const float fxk = v_get(g.fx, k), fyk = v_get(g.fy, k);
                     const float wnw = (1.0f - fxk) * (1.0f - fyk), wne = fxk * (1.0f - fyk);
@@ -286,394 +305,369 @@ __device__ __forceinline__ void group_blend(const PairConst& pc, int i0, int pla
     }
 }
 
-
-template <bool GRAD, bool IMG_GRAD, int NS>
-__device__ __forceinline__ void group_pixel(const PairConst& pc, int i0, int plane, int H, int W, float xf, float yf,
-                                            float D, const float (&t)[3], float w_e, bool valid, bool pf,
-                                            typename Vec<NS>::T (&acc)[9], float& l1acc, float& gp, float (&gt)[3]) {
-    GState<NS> g;
-    typename Vec<NS>::T v[3][4];
-    unsigned msk[NS];
-    group_project<NS>(pc, i0, H, W, xf, yf, D, g);
-    group_load<NS>(pc, i0, plane, H, W, valid, pf, g, v, msk);
-    group_blend<GRAD, IMG_GRAD, NS>(pc, i0, plane, W, yf, D, t, w_e, valid, g, v, msk, acc, l1acc, gp, gt);
+// Per-lane accumulators of one source -> this warp's shared record (ACCUMULATED in place).
+// Record of source i: [0..2] sum h_r, [3..5] sum h_r * x, [6..8] sum h_r * y, [9..11] sum g_cam[r];
+// value PLB_MAX_SRC*12: sum |diff| (added once per run: `l1` is zero in every other call).
+__device__ __forceinline__ void flush_source(const float (&a9)[9], int i, float l1, float xlane, float* rec, int lane) {
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        v[q] = a9[q]; v[3 + q] = a9[q] * xlane;
+        v[6 + q] = a9[3 + q]; v[9 + q] = a9[6 + q];
+    }
+    v[12] = l1;
+    v[13] = v[14] = v[15] = 0.0f;
+    int which;
+    const float r = warp_reduce16(v, lane, which);
+    if ((lane & 1) == 0) {
+        if (which < 12) rec[i * 12 + which] += r;
+        else if (which == 12) rec[PLB_MAX_SRC * 12] += r;
+    }
 }
 
-// Per-lane accumulators of one group -> this warp's shared record (ACCUMULATED in place).
-// Record of source i: [0..2] sum h_r, [3..5] sum h_r * x, [6..8] sum h_r * y, [9..11] sum g_cam[r];
-// value PLB_MAX_SRC*12: sum |diff|.
-template <typename V, int NS>
-__device__ __forceinline__ void flush_group(const V (&acc)[9], int i0, float l1, float xlane, float* rec, int lane) {
+// ---------------------------------------------------------------------------------------------
+// Depth streams.  A combo reads one depth per pixel (two for a scale pair).
+//   FULL scale: the disparity of the next row is loaded one iteration ahead (software pipeline).
+//   Low-resolution scale: F.interpolate(depth, [H, W], bilinear, align_corners=False) (losses.py:214-215; the
+//   reference interpolates DEPTH, not disparity).  A run is walked in CHUNKS of at most PH_CHUNK rows that never
+//   cross a multiple of PH_CHUNK.  Before the rows of a chunk a short pre-pass walks down the chunk once with a
+//   two-row window of x-interpolated low-res depths (the window advances by exactly one row at a time because the
+//   factor is >= 1) and leaves the upsampled depth of every pixel of the lane's column in a per-lane slot of shared
+//   memory - D = ly0 * r0 + ly1 * r1 with the same association as the 4-tap form ly0 * (lx0 v00 + lx1 v01) +
+//   ly1 * (lx0 v10 + lx1 v11).  The row loop then costs one shared load per pixel and holds NO low-resolution
+//   state in registers; it puts the gradient with respect to the upsampled depth back into the same slot, and a
+//   post-pass runs the TRANSPOSED upsample over the chunk: a_lo / a_hi collect ly0 * g and ly1 * g of the rows and
+//   are emitted - one value per low-res row and lane - when the window advances.
+// ---------------------------------------------------------------------------------------------
+constexpr int PH_CHUNK = PH_ROW_ALIGN;
+
+template <bool HEAD>
+__device__ __forceinline__ float to_depth(const plb_photo_args& a, float raw) {
+    if (HEAD) raw = head_disp(raw, a.head_alpha, a.head_beta);
+    return a.input_is_depth == PLB_INPUT_DEPTH ? raw : rcp_nr(fmaf(a.disp_a, raw, a.disp_b));
+}
+
+// x-interpolated depth of low-res row j of scale s at column xc
+template <bool HEAD>
+__device__ __forceinline__ float low_row(const plb_photo_args& a, const PairConst& pc, int s, int j, int xc) {
+    int x0, x1; float lx0, lx1;
+    const int dw = pc.dw[s];
+    up_coord(xc, pc.sx[s], dw, x0, x1, lx0, lx1);
+    const float* row = pc.disp[s] + j * dw;
+    const float v0 = to_depth<HEAD>(a, __ldg(row + x0)), v1 = to_depth<HEAD>(a, __ldg(row + x1));
+    return lx0 * v0 + lx1 * v1;
+}
+
+// pre-pass, any ratio (up_coord per row): upsampled depth of rows [yc, yc + nr) of the lane's column -> slot[r * 32]
+template <bool HEAD>
+__device__ __forceinline__ void low_prepass(const plb_photo_args& a, const PairConst& pc, int s, int xc, int yc, int nr,
+                                            float* slot) {
+    const int dh = pc.dh[s];
+    const float sy = pc.sy[s];
+    int y0, y1; float l0, l1;
+    up_coord(yc, sy, dh, y0, y1, l0, l1);
+    int jc = y0;
+    float r0 = low_row<HEAD>(a, pc, s, y0, xc), r1 = low_row<HEAD>(a, pc, s, y1, xc);
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r) {
+        up_coord(yc + r, sy, dh, y0, y1, l0, l1);
+        if (y0 != jc) {                                // the window advances by one low-res row (warp-uniform)
+            jc = y0;
+            r0 = r1;
+            r1 = low_row<HEAD>(a, pc, s, y1, xc);
+        }
+        slot[r * 32] = l0 * r0 + l1 * r1;
+    }
+}
+
+// One partial row of the transposed upsample leaves the warp.  The chunk [ya, yb) holds either all of the
+// full-resolution rows that feed low-res row j or a part of them; chunks end on multiples of PH_CHUNK >= 2 * factor
+// rows, so at most ONE chunk boundary crosses the (at most 2.5 * factor rows long) footprint of a low-res row and the
+// row has at most two contributors: slot 0 takes the part that starts the footprint, slot 1 the part that ends it,
+// and a chunk that holds the whole footprint zeroes slot 1.  Every (row, column) of both slots is written exactly
+// once per launch, in no particular order, and summed in a fixed order by the merge kernel: the result does not
+// depend on how the unit list was cut.
+__device__ __forceinline__ void low_emit(float* g, int dh, int f, int H, int W, int j, float val, int x, bool valid, int ya, int yb) {
+    if (j >= dh || !valid) return;
+    const int hf = f >> 1;
+    const int first = (j <= 1) ? 0 : (j - 1) * f + hf;                 // first row with y0 == j - 1 (or the image top)
+    const int last = (j == dh - 1) ? H - 1 : (j + 1) * f + hf - 1;     // last row with y0 == j
+    const bool before = first >= ya, after = last < yb;
+    float* row0 = g + ((size_t)j * W + x);
+    float* row1 = row0 + (size_t)dh * W;
+    if (before) {
+        *row0 = val;
+        if (after) *row1 = 0.0f;
+    } else {
+        *row1 = val;
+    }
+}
+
+// ---- chunk passes of the staged (LOW) kernels.  `slot` = this lane's column of the stream's [PH_CHUNK][32] staging
+//      area; row r of the chunk lives at slot[r * 32].  Before the rows of a chunk a pre-pass leaves the DEPTH of every
+//      pixel there; the row loop replaces it by w = d loss / d depth; a post-pass turns w into the gradient the caller
+//      asked for. ------------------------------------------------------------------------------------------------------
+
+// FULL scale: the chunk's disparities in flight together instead of one software-pipelined load per row
+template <bool HEAD>
+__device__ __forceinline__ void pre_full(const plb_photo_args& a, const float* disp, int W, int nr, float* slot) {
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r) slot[r * 32] = to_depth<HEAD>(a, __ldg(disp + r * W));
+}
+
+// FULL scale: w -> d loss / d disparity (the map re-read from L1: D is not kept)
+template <bool HEAD>
+__device__ __forceinline__ void post_full(const plb_photo_args& a, const float* disp, float* g, bool shared, int W, int nr,
+                                          const float* slot) {
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r) {
+        float gv = slot[r * 32];
+        if (a.input_is_depth != PLB_INPUT_DEPTH) {
+            const float D = to_depth<HEAD>(a, __ldg(disp + r * W));
+            gv *= -a.disp_a * D * D;                       // d D / d disp = -disp_a * D^2
+            if (HEAD) gv *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
+        }
+        if (shared) atomicAdd(g + r * W, gv); else g[r * W] = gv;
+    }
+}
+
+// LOWSCRATCH scale: w into the full-resolution scratch plane (photo_upsample_T_kernel gathers it)
+__device__ __forceinline__ void post_scratch(float* g, bool shared, int W, int nr, const float* slot) {
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r) {
+        if (shared) atomicAdd(g + r * W, slot[r * 32]); else g[r * W] = slot[r * 32];
+    }
+}
+
+// Low-resolution scale with an integer power-of-two factor f: row y has y0 = (y - f/2) >> lg and
+// l1 = ((y - f/2) mod f + 0.5) / f - up_coord's values exactly (dyadic rationals) - so walking down the rows is a
+// phase counter: k counts the rows of a band (the f rows that share y0), and the two-row window of x-interpolated
+// depths advances when k wraps.  At the image top the first f/2 rows clamp to (row 0, l1 = 0): t < 0.  The raw taps
+// of the row the NEXT advance needs are loaded one band ahead.
+template <bool HEAD>
+__device__ __forceinline__ void pre_low_p2(const plb_photo_args& a, const PairConst& pc, int s, int f, int xc, int yc, int nr,
+                                           float* slot) {
+    const int dh = pc.dh[s], dw = pc.dw[s], lg = 31 - __clz(f);
+    const float inv_f = pc.sy[s];                          // 1 / f exactly
+    int x0, x1; float lx0, lx1;
+    up_coord(xc, pc.sx[s], dw, x0, x1, lx0, lx1);
+    const float* base = pc.disp[s];
+    int t = yc - (f >> 1);
+    int j = t >> lg, k = t & (f - 1);                      // (arithmetic shift: -1 above the first band)
+    auto raw = [&](int jj, float& u, float& v) {
+        jj = min(max(jj, 0), dh - 1);
+        u = __ldg(base + (jj * dw + x0)); v = __ldg(base + (jj * dw + x1));
+    };
+    float u0, v0, u1, v1, un, vn;
+    raw(j, u0, v0); raw(j + 1, u1, v1); raw(j + 2, un, vn);
+    float r0 = lx0 * to_depth<HEAD>(a, u0) + lx1 * to_depth<HEAD>(a, v0);
+    float r1 = lx0 * to_depth<HEAD>(a, u1) + lx1 * to_depth<HEAD>(a, v1);
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r) {
+        const float l1 = t < 0 ? 0.0f : ((float)k + 0.5f) * inv_f;
+        const float l0 = 1.0f - l1;
+        slot[r * 32] = l0 * r0 + l1 * r1;
+        ++t; ++k;
+        if (k == f) {                                      // the window advances by one low-res row (warp-uniform)
+            k = 0; ++j;
+            r0 = r1;
+            r1 = lx0 * to_depth<HEAD>(a, un) + lx1 * to_depth<HEAD>(a, vn);
+            raw(j + 2, un, vn);
+        }
+    }
+}
+
+// ... and its transpose: w of the chunk's rows -> partial low-res rows (see low_emit)
+__device__ __forceinline__ void post_low_p2(const PairConst& pc, int s, int f, float* g, int H, int W, int x, bool valid,
+                                            int yc, int nr, const float* slot) {
+    const int dh = pc.dh[s], lg = 31 - __clz(f);
+    const float inv_f = pc.sy[s];
+    int t = yc - (f >> 1);
+    int j = t >> lg, k = t & (f - 1);
+    float a_lo = 0.0f, a_hi = 0.0f;
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r) {
+        const float l1 = t < 0 ? 0.0f : ((float)k + 0.5f) * inv_f;
+        const float gz = slot[r * 32];
+        a_lo = fmaf(1.0f - l1, gz, a_lo);
+        // bottom border (y1 == y0 == dh - 1): both weights act on row j
+        if (j >= dh - 1) a_lo = fmaf(l1, gz, a_lo); else a_hi = fmaf(l1, gz, a_hi);
+        ++t; ++k;
+        if (k == f) {
+            k = 0;
+            if (j >= 0) { low_emit(g, dh, f, H, W, j, a_lo, x, valid, yc, yc + nr); a_lo = a_hi; }
+            else a_lo += a_hi;                             // the clamped rows of the image top belong to low-res row 0
+            a_hi = 0.0f; ++j;
+        }
+    }
+    if (j >= 0) {
+        low_emit(g, dh, f, H, W, j, a_lo, x, valid, yc, yc + nr);
+        low_emit(g, dh, f, H, W, j + 1, a_hi, x, valid, yc, yc + nr);
+    } else {
+        low_emit(g, dh, f, H, W, 0, a_lo + a_hi, x, valid, yc, yc + nr);
+    }
+}
+
+// One run: consecutive rows [y, y + rows) of one 32-px strip of one combo of one (job, image) pair.
+//   NS = 2, ND = 1: two sources (k0, k0 + 1) at scale s0;  NS = 2, ND = 2: source k0 at scales s0, s1;
+//   NS = 1, ND = 1: source k0 at scale s0 on the scalar pipe.
+// LOW = false (every scale of the launch is full resolution): the disparity of the next row is loaded one iteration
+// ahead and the gradient is written from the row loop.  LOW = true: the staged form described above - the row loop
+// is the same for every kind of scale.  `stage`: this warp's [2][PH_CHUNK][32] floats of shared memory (LOW only).
+template <bool GRAD, bool IMG_GRAD, int NS, int ND, bool HEAD, bool LOW, int CH, int CW>
+__device__ __forceinline__ void run_combo(const plb_photo_args& a, const PairConst& pc, const PhotoCombo cb, int strip,
+                                          int y, int rows, int lane, float* rec, float* stage) {
+    typedef typename Vec<NS>::T V;
+    const int H = CH > 0 ? CH : a.H, W = CW > 0 ? CW : a.W, plane = H * W;
+    constexpr bool ALL_VALID = CW > 0 && (CW % 32) == 0;
+    constexpr int SST = PH_CHUNK * 32;                     // floats per stream of the staging area
+    const float w_e = pc.w_e;
+    const int x = strip * 32 + lane;
+    const bool valid = ALL_VALID ? true : (x < W);
+    const int xc = min(x, W - 1);
+    const float xf = (float)x;
+    const float* __restrict__ tgt_b = pc.tgt;
+    const int yb = y + rows;
+
+    ComboRef cr;
+    cr.k0 = cb.k0;
+    cr.tab = (ND == 2) ? (PLB_MAX_SRC / 2 + cb.k0) : (cb.k0 >> 1);
+    const float* cbp[NS];
+    float* gsp[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        const int i = i0 + k;
-        float v[16];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            v[q] = v_get(acc[q], k); v[3 + q] = v_get(acc[q], k) * xlane;
-            v[6 + q] = v_get(acc[3 + q], k); v[9 + q] = v_get(acc[6 + q], k);
-        }
-        v[12] = (i == 0) ? l1 : 0.0f;
-        v[13] = v[14] = v[15] = 0.0f;
-        int which;
-        const float r = warp_reduce16(v, lane, which);
-        if ((lane & 1) == 0) {
-            if (which < 12) rec[i * 12 + which] += r;
-            else if (which == 12 && i == 0) rec[PLB_MAX_SRC * 12] += r;
-        }
+        const int ks = (ND == 2) ? cb.k0 : cb.k0 + k;
+        cbp[k] = pc.src[ks];
+        gsp[k] = IMG_GRAD ? pc.g_src[ks] : nullptr;
     }
-}
+    V Ax[3];
+    load_ax(pc, cr, xf, Ax);
 
-// ---------------------------------------------------------------------------------------------
-// Single-source directions (3-4-source kernel variants only: the <= 2-source variants have no registers to spare,
-// measured 196 vs 183 us on c2): TWO ROWS of the strip ride the packed pipe (low half = row y, high half = row
-// y + 1 of the same source) instead of two sources of one row - the scalar path costs 250 warp instructions
-// per row segment against 165 for half of a packed pair.  Same stages as above; the projection constants are
-// broadcast, the target pixel / depth / row coordinate differ per half, and the depth-gradient numerator is
-// kept per half (each row writes its own gradient).  `vk[k]`: half k is a real pixel (x < W and, for the odd
-// last row of a run, k == 0).
-// ---------------------------------------------------------------------------------------------
-template <bool GRAD>
-__device__ __forceinline__ void rowpair_pixel(const PairConst& pc, int i0, int plane, int H, int W, float xf, float2 yv,
-                                              float2 Dv, const float (&t)[2][3], float w_e, const bool (&vk)[2], bool pf,
-                                              float2 (&acc)[9], float& l1acc, float2& gpv) {
-    typedef float2 V;
-    V xv, eps, neg1, two;
-    v_bc(xv, xf); v_bc(eps, 1e-5f); v_bc(neg1, -1.0f); v_bc(two, 2.0f);
-    // ---- stage A: project both rows ----------------------------------------------------------------
-    V cam[3];
+    // per depth stream: scale index and PH_SM_* (| 4: a second combo adds into the same map)
+    int sc[ND], md[ND];
+    float u0[ND];                                      // !LOW: raw value of the NEXT row
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float4 q = pc.Q[i0][r];
-        V qx, qy, qz, p3;
-        v_bc(qx, q.x); v_bc(qy, q.y); v_bc(qz, q.z); v_bc(p3, q.w);
-        cam[r] = v_fma(Dv, v_fma(qx, xv, v_fma(qy, yv, qz)), p3);
+    for (int d = 0; d < ND; ++d) {
+        const int s = d == 0 ? cb.s0 : cb.s1;
+        sc[d] = s;
+        md[d] = pc.smode[s];
+        u0[d] = 0.0f;
+        if (!LOW) u0[d] = __ldg(pc.disp[s] + (y * W + xc));
     }
-    const V ze = v_add(cam[2], eps);
-    const V nze = v_mul(ze, neg1);
-    V inv;
-    {
-        float r0, r1;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(ze.x));
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(ze.y));
-        inv = make_float2(r0, r1);
-    }
-    inv = v_mul(inv, v_fma(nze, inv, two));                  // Newton step
-    V px = v_mul(cam[0], inv), py = v_mul(cam[1], inv);
-    px = v_fma(v_fma(px, nze, cam[0]), inv, px);             // residual correction: IEEE-accurate quotient
-    py = v_fma(v_fma(py, nze, cam[1]), inv, py);
-    int x0[2], y0[2];
-    V fx, fy;
-    bool all_in = true;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const float ixc = fminf(fmaxf(v_get(px, k), -2.0f), (float)(W + 1));
-        const float iyc = fminf(fmaxf(v_get(py, k), -2.0f), (float)(H + 1));
-        const float xfl = floorf(ixc), yfl = floorf(iyc);
-        x0[k] = (int)xfl; y0[k] = (int)yfl;
-        v_set(fx, k, ixc - xfl); v_set(fy, k, iyc - yfl);
-        all_in = all_in && (!vk[k] || (((unsigned)x0[k] < (unsigned)(W - 1)) && ((unsigned)y0[k] < (unsigned)(H - 1))));
-    }
-    // ---- stage B: 24 tap loads ----------------------------------------------------------------------
-    V v[3][4];
-    unsigned msk[2];
-    const float* __restrict__ cb = pc.src[i0];
-    if (__all_sync(0xffffffffu, all_in)) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int o00 = vk[k] ? y0[k] * W + x0[k] : 0;
-            const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
-            v_set(v[0][0], k, __ldg(cb + o00)); v_set(v[0][1], k, __ldg(cb + o00 + 1));
-            v_set(v[0][2], k, __ldg(cb + o01)); v_set(v[0][3], k, __ldg(cb + o01 + 1));
-            v_set(v[1][0], k, __ldg(cb + o10)); v_set(v[1][1], k, __ldg(cb + o10 + 1));
-            v_set(v[1][2], k, __ldg(cb + o11)); v_set(v[1][3], k, __ldg(cb + o11 + 1));
-            v_set(v[2][0], k, __ldg(cb + o20)); v_set(v[2][1], k, __ldg(cb + o20 + 1));
-            v_set(v[2][2], k, __ldg(cb + o21)); v_set(v[2][3], k, __ldg(cb + o21 + 1));
-            if (PH_PF_SRC > 0 && pf && k == 1) {
-                // the next pair of rows touches two new source rows below the lower footprint
-                const int opf = o01 + PH_PF_SRC * W;
-                prefetch_l1(cb + opf); prefetch_l1(cb + (opf + plane)); prefetch_l1(cb + (opf + 2 * plane));
-                prefetch_l1(cb + (opf + W)); prefetch_l1(cb + (opf + W + plane)); prefetch_l1(cb + (opf + W + 2 * plane));
-            }
-            msk[k] = vk[k] ? 15u : 0u;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const bool vx0 = (unsigned)x0[k] < (unsigned)W, vx1 = (unsigned)(x0[k] + 1) < (unsigned)W;
-            const bool vy0 = (unsigned)y0[k] < (unsigned)H, vy1 = (unsigned)(y0[k] + 1) < (unsigned)H;
-            const bool mnw = vk[k] && vx0 && vy0, mne = vk[k] && vx1 && vy0;
-            const bool msw = vk[k] && vx0 && vy1, mse = vk[k] && vx1 && vy1;
-            const int o00 = y0[k] * W + x0[k];
-            const int o01 = o00 + W, o10 = o00 + plane, o11 = o10 + W, o20 = o10 + plane, o21 = o20 + W;
-            v_set(v[0][0], k, ldg_pred(cb + o00, mnw)); v_set(v[0][1], k, ldg_pred(cb + o00 + 1, mne));
-            v_set(v[0][2], k, ldg_pred(cb + o01, msw)); v_set(v[0][3], k, ldg_pred(cb + o01 + 1, mse));
-            v_set(v[1][0], k, ldg_pred(cb + o10, mnw)); v_set(v[1][1], k, ldg_pred(cb + o10 + 1, mne));
-            v_set(v[1][2], k, ldg_pred(cb + o11, msw)); v_set(v[1][3], k, ldg_pred(cb + o11 + 1, mse));
-            v_set(v[2][0], k, ldg_pred(cb + o20, mnw)); v_set(v[2][1], k, ldg_pred(cb + o20 + 1, mne));
-            v_set(v[2][2], k, ldg_pred(cb + o21, msw)); v_set(v[2][3], k, ldg_pred(cb + o21 + 1, mse));
-            msk[k] = (mnw ? 1u : 0u) | (mne ? 2u : 0u) | (msw ? 4u : 0u) | (mse ? 8u : 0u);
-        }
-    }
-    // ---- stage C: blend, L1, gradient terms ----------------------------------------------------------
-    V Gx, Gy;
-    v_bc(Gx, 0.0f); v_bc(Gy, 0.0f);
-    float l1[2] = {0.0f, 0.0f};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const V dA = v_sub(v[c][1], v[c][0]), dB = v_sub(v[c][3], v[c][2]);
-        const V top = v_fma(fx, dA, v[c][0]), bot = v_fma(fx, dB, v[c][2]);
-        const V dV = v_sub(bot, top);
-        const V proj = v_fma(fy, dV, top);
-        V sg;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float d = v_get(proj, k) - t[k][c];
-            l1[k] += fabsf(d);
-            if (GRAD) {
-                const float ne = (d != 0.0f) ? 1.0f : 0.0f;
-                v_set(sg, k, __int_as_float(__float_as_int(ne) | (__float_as_int(d) & 0x80000000)));
-            }
-        }
-        if (GRAD) {
-            Gx = v_fma(sg, v_fma(fy, v_sub(dB, dA), dA), Gx);
-            Gy = v_fma(sg, dV, Gy);
-        }
-    }
-    l1acc += (vk[0] ? l1[0] : 0.0f) + (vk[1] ? l1[1] : 0.0f);
-    if (GRAD) {
-        V gi;
-        V s = v_fma(Gx, px, v_mul(Gy, py));
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const bool use = msk[k] != 0u;
-            v_set(gi, k, use ? w_e * v_get(inv, k) : 0.0f);
-            v_set(s, k, use ? v_get(s, k) : 0.0f);
-        }
-        const V gcx = v_mul(Gx, gi), gcy = v_mul(Gy, gi);
-        const V gcz = v_mul(v_mul(s, gi), neg1);
-        {
-            V q3[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) { float w3; load_p3(pc, i0, r, w3); v_bc(q3[r], w3); }
-            gpv = v_add(gpv, v_fma(gcx, q3[0], v_fma(gcy, q3[1], v_mul(gcz, v_add(q3[2], eps)))));
-        }
-        const V hx = v_mul(gcx, Dv), hy = v_mul(gcy, Dv), hz = v_mul(gcz, Dv);
-        acc[0] = v_add(acc[0], hx); acc[1] = v_add(acc[1], hy); acc[2] = v_add(acc[2], hz);
-        acc[3] = v_fma(hx, yv, acc[3]); acc[4] = v_fma(hy, yv, acc[4]); acc[5] = v_fma(hz, yv, acc[5]);
-        acc[6] = v_add(acc[6], gcx); acc[7] = v_add(acc[7], gcy); acc[8] = v_add(acc[8], gcz);
-    }
-}
 
-// One run of a SINGLE-source pair (no image gradients): rows two at a time on the packed pipe.
-template <bool GRAD, bool MULTI, bool HEAD>
-__device__ __forceinline__ void run_rows_single(const plb_photo_args& a, const PairConst& pc, int strip, int y, int rows,
-                                                int lane, float* rec) {
-    const int H = a.H, W = a.W, plane = H * W;
-    const float w_e = pc.w_e;
-    const int x = strip * 32 + lane;
-    const bool valid = x < W;
-    const float xf = (float)x;
-    const float* __restrict__ tgt_b = pc.tgt;
-    const int xc = min(x, W - 1);
-    float2 acc[9];
+    V acc[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = make_float2(0.0f, 0.0f);
+    for (int k = 0; k < 9; ++k) v_bc(acc[k], 0.0f);
     float l1acc = 0.0f;
-    const int y_end = y + rows;
-    // software pipeline over row pairs: the target pixels of the NEXT pair are loaded while this one is processed
-    auto row_of = [&](int yy) -> int { return min(yy, H - 1) * W + xc; };   // the odd last row of a run repeats itself (masked)
-    float tn[2][3];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int o = row_of(y + k);
-        tn[k][0] = __ldg(tgt_b + o); tn[k][1] = __ldg(tgt_b + (o + plane)); tn[k][2] = __ldg(tgt_b + (o + 2 * plane));
-    }
-#pragma unroll 1
-    for (; y < y_end; y += 2) {
-        float t[2][3];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) { t[k][0] = tn[k][0]; t[k][1] = tn[k][1]; t[k][2] = tn[k][2]; }
-        const bool pf = y + 2 < y_end;
-        if (pf) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int o = row_of(y + 2 + k);
-                tn[k][0] = __ldg(tgt_b + o); tn[k][1] = __ldg(tgt_b + (o + plane)); tn[k][2] = __ldg(tgt_b + (o + 2 * plane));
-            }
-        }
-        const bool vk[2] = {valid, valid && (y + 1 < y_end)};
-        const int o0 = row_of(y), o1 = row_of(y + 1);
-        const float2 yv = make_float2((float)y, (float)(y + 1));
-        const int n_scales = MULTI ? pc.n_scales : 1, lowres = MULTI ? pc.lowres : 0;
-#pragma unroll 1
-        for (int s = 0; s < n_scales; ++s) {
-            const float* disp_b = pc.disp[s];
-            const bool full = !((lowres >> s) & 1);
-            float2 Dv;
-            if (full) {
-                float d0 = __ldg(disp_b + o0), d1 = __ldg(disp_b + o1);
-                if (HEAD) { d0 = head_disp(d0, a.head_alpha, a.head_beta); d1 = head_disp(d1, a.head_alpha, a.head_beta); }
-                Dv = a.input_is_depth == PLB_INPUT_DEPTH ? make_float2(d0, d1)
-                                                         : make_float2(rcp_nr(fmaf(a.disp_a, d0, a.disp_b)), rcp_nr(fmaf(a.disp_a, d1, a.disp_b)));
-            } else {
-                const int dh = pc.dh[s], dw = pc.dw[s];
-                int x0, x1; float lx0, lx1;
-                up_coord(xc, pc.sx[s], dw, x0, x1, lx0, lx1);
-                float Dk[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    int y0, y1; float ly0, ly1;
-                    up_coord(min(y + k, H - 1), pc.sy[s], dh, y0, y1, ly0, ly1);
-                    float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
-                    float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
-                    if (HEAD) {
-                        v00 = head_disp(v00, a.head_alpha, a.head_beta); v01 = head_disp(v01, a.head_alpha, a.head_beta);
-                        v10 = head_disp(v10, a.head_alpha, a.head_beta); v11 = head_disp(v11, a.head_alpha, a.head_beta);
-                    }
-                    if (a.input_is_depth != PLB_INPUT_DEPTH) {
-                        v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
-                        v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
-                    }
-                    Dk[k] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-                }
-                Dv = make_float2(Dk[0], Dk[1]);
-            }
-            float2 gpv = make_float2(0.0f, 0.0f);
-            rowpair_pixel<GRAD>(pc, 0, plane, H, W, xf, yv, Dv, t, w_e, vk, pf && s == 0, acc, l1acc, gpv);
-            if (GRAD) {
-                float* g = pc.g_disp[s];
-                if (g != nullptr) {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (vk[k]) {
-                            const float D = v_get(Dv, k), gp = v_get(gpv, k);
-                            float gv = (full && a.input_is_depth != PLB_INPUT_DEPTH) ? a.disp_a * D * gp : -gp * rcp_nr(D);
-                            if (full && HEAD) gv *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
-                            g[k == 0 ? o0 : o1] = gv;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    // both halves belong to the one source: fold them, then the usual warp reduction into the record
-    float accs[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) accs[k] = acc[k].x + acc[k].y;
-    flush_group<float, 1>(accs, 0, l1acc, xf, rec, lane);
-    __syncwarp();
-}
 
-// One run: consecutive rows [y, y + rows) of one 32-px strip of one (job, image) pair, NSRC sources.
-template <bool GRAD, bool IMG_GRAD, int NSRC, bool MULTI, bool HEAD>
-__device__ __forceinline__ void run_rows(const plb_photo_args& a, const PairConst& pc, int strip, int y, int rows,
-                                         int lane, float* rec) {
-    constexpr int NP = NSRC / 2, ODD = NSRC & 1;
-    const int H = a.H, W = a.W, plane = H * W;
-    const float w_e = pc.w_e;
-    const int x = strip * 32 + lane;
-    const bool valid = x < W;
-    const float xf = (float)x;
-    const float* __restrict__ tgt_b = pc.tgt;
-    int o = y * W + min(x, W - 1);
-
-    float2 accp[NP > 0 ? NP : 1][9];
-    float accs[9];
-    float l1acc = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-#pragma unroll
-        for (int g = 0; g < (NP > 0 ? NP : 1); ++g) accp[g][k] = make_float2(0.0f, 0.0f);
-        accs[k] = 0.0f;
-    }
-
-    // software pipeline: the target pixel (and the full-resolution disparity) of the NEXT row are loaded while
-    // this row is processed, so a warp pays one memory round trip per row (the taps), not two
-    float tn[3], dn = 0.0f;
+    // software pipeline: the target pixel of the NEXT row is loaded while this row is processed, so a warp pays one
+    // memory round trip per row (the taps), not two
+    int o = y * W + xc;
+    float tn[3];
     tn[0] = __ldg(tgt_b + o); tn[1] = __ldg(tgt_b + (o + plane)); tn[2] = __ldg(tgt_b + (o + 2 * plane));
-    if (!MULTI) dn = __ldg(pc.disp[0] + o);
 #pragma unroll 1
-    for (int r = 0; r < rows; ++r, ++y, o += W) {
-        float t[3], gt[3] = {0.0f, 0.0f, 0.0f};
-        t[0] = tn[0]; t[1] = tn[1]; t[2] = tn[2];
-        const float d_cur = dn;
-        const bool pf = r + 1 < rows;
-        if (pf) {
-            const int on = o + W;
-            tn[0] = __ldg(tgt_b + on); tn[1] = __ldg(tgt_b + (on + plane)); tn[2] = __ldg(tgt_b + (on + 2 * plane));
-            if (!MULTI) dn = __ldg(pc.disp[0] + on);
-        }
-        const float yf = (float)y;
-        if (!MULTI) {
-            const float d0 = HEAD ? head_disp(d_cur, a.head_alpha, a.head_beta) : d_cur;
-            const float D = a.input_is_depth == PLB_INPUT_DEPTH ? d0 : rcp_nr(fmaf(a.disp_a, d0, a.disp_b));
-            float gp = 0.0f;
+    while (y < yb) {
+        // ---- one chunk: rows [yc, yc + nr), never across a multiple of PH_CHUNK ---------------------------------
+        const int yc = y;
+        const int nr = LOW ? (min(yb, (yc / PH_CHUNK + 1) * PH_CHUNK) - yc) : (yb - yc);
+        if (LOW) {
 #pragma unroll
-            for (int g = 0; g < NP; ++g)
-                group_pixel<GRAD, IMG_GRAD, 2>(pc, 2 * g, plane, H, W, xf, yf, D, t, w_e, valid, pf, accp[g], l1acc, gp, gt);
-            if (ODD) group_pixel<GRAD, IMG_GRAD, 1>(pc, NSRC - 1, plane, H, W, xf, yf, D, t, w_e, valid, pf, accs, l1acc, gp, gt);
+            for (int d = 0; d < ND; ++d) {
+                const int s = sc[d], f = pc.fac[s];
+                float* slot = stage + d * SST + lane;
+                if ((md[d] & 3) == PH_SM_FULL) pre_full<HEAD>(a, pc.disp[s] + o, W, nr, slot);
+                else if (f > 0) pre_low_p2<HEAD>(a, pc, s, f, xc, yc, nr, slot);
+                else low_prepass<HEAD>(a, pc, s, xc, yc, nr, slot);
+            }
+        }
+        const int ye = yc + nr;
+        const int oc = o;                                  // offset of the chunk's first pixel
+        float* sp = stage + lane;
+#pragma unroll 1
+        for (; y < ye; ++y, o += W, sp += 32) {
+            float t[3], gt[3] = {0.0f, 0.0f, 0.0f};
+            t[0] = tn[0]; t[1] = tn[1]; t[2] = tn[2];
+            const bool pf = y + 1 < yb;
+            float D[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) D[d] = LOW ? sp[d * SST] : to_depth<HEAD>(a, u0[d]);
+            if (pf) {
+                const int on = o + W;
+                tn[0] = __ldg(tgt_b + on); tn[1] = __ldg(tgt_b + (on + plane)); tn[2] = __ldg(tgt_b + (on + 2 * plane));
+                if (!LOW) {
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) u0[d] = __ldg(pc.disp[sc[d]] + on);
+                }
+            }
+            V Dv;
+            if (ND == 2) { v_set(Dv, 0, D[0]); v_set(Dv, 1, D[ND - 1]); } else v_bc(Dv, D[0]);
+            const float yf = (float)y;
+            GState<NS> g;
+            V v[3][4];
+            unsigned msk[NS];
+            V gpv;
+            v_bc(gpv, 0.0f);
+            group_project<NS>(pc, cr, H, W, Ax, yf, Dv, g);
+            group_load<NS, ALL_VALID>(cbp, plane, H, W, valid, pf, g, v, msk);
+            group_blend<GRAD, IMG_GRAD, NS>(pc, cr, gsp, plane, W, yf, Dv, t, w_e, valid, g, v, msk, acc, l1acc, gpv, gt);
             if (GRAD) {
-                float* g = pc.g_disp[0];
-                // d loss / d D = -gp / D;  d D / d disp = -disp_a * D^2
-                if (valid && g != nullptr) {
-                    float gv = a.input_is_depth == PLB_INPUT_DEPTH ? -gp * rcp_nr(D) : a.disp_a * D * gp;
-                    if (HEAD) gv *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
-                    g[o] = gv;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const float gp = (ND == 2) ? v_get(gpv, d) : v_hsum(gpv);
+                    const float Dd = D[d];
+                    if (LOW) {
+                        // d loss / d D = -gp / D, for every kind of scale; the post-pass takes it from here
+                        sp[d * SST] = valid ? -gp * rcp_nr(Dd) : 0.0f;
+                    } else {
+                        float* gdst = pc.g_disp[sc[d]];
+                        if (gdst == nullptr) continue;
+                        // d loss / d D = -gp / D;  d D / d disp = -disp_a * D^2
+                        float gv = a.input_is_depth == PLB_INPUT_DEPTH ? -gp * rcp_nr(Dd) : a.disp_a * Dd * gp;
+                        if (HEAD) gv *= head_chain_from_depth(Dd, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
+                        if (valid) { if (md[d] & 4) atomicAdd(gdst + o, gv); else gdst[o] = gv; }
+                    }
                 }
             }
-        } else {
-            const int n_scales = pc.n_scales, lowres = pc.lowres;
-#pragma unroll 1
-            for (int s = 0; s < n_scales; ++s) {
-                const float* disp_b = pc.disp[s];
-                const bool full = !((lowres >> s) & 1);
-                float D, gp = 0.0f;
-                if (full) {
-                    float d = __ldg(disp_b + o);
-                    if (HEAD) d = head_disp(d, a.head_alpha, a.head_beta);
-                    D = a.input_is_depth == PLB_INPUT_DEPTH ? d : rcp_nr(fmaf(a.disp_a, d, a.disp_b));
-                } else {
-                    const int dh = pc.dh[s], dw = pc.dw[s];
-                    int x0, x1, y0, y1; float lx0, lx1, ly0, ly1;
-                    up_coord(min(x, W - 1), pc.sx[s], dw, x0, x1, lx0, lx1);
-                    up_coord(y, pc.sy[s], dh, y0, y1, ly0, ly1);
-                    float v00 = __ldg(disp_b + (y0 * dw + x0)), v01 = __ldg(disp_b + (y0 * dw + x1));
-                    float v10 = __ldg(disp_b + (y1 * dw + x0)), v11 = __ldg(disp_b + (y1 * dw + x1));
-                    if (HEAD) {
-                        v00 = head_disp(v00, a.head_alpha, a.head_beta); v01 = head_disp(v01, a.head_alpha, a.head_beta);
-                        v10 = head_disp(v10, a.head_alpha, a.head_beta); v11 = head_disp(v11, a.head_alpha, a.head_beta);
-                    }
-                    if (a.input_is_depth != PLB_INPUT_DEPTH) {
-                        v00 = rcp_nr(fmaf(a.disp_a, v00, a.disp_b)); v01 = rcp_nr(fmaf(a.disp_a, v01, a.disp_b));
-                        v10 = rcp_nr(fmaf(a.disp_a, v10, a.disp_b)); v11 = rcp_nr(fmaf(a.disp_a, v11, a.disp_b));
-                    }
-                    D = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-                }
-#pragma unroll
-                for (int g = 0; g < NP; ++g)
-                    group_pixel<GRAD, IMG_GRAD, 2>(pc, 2 * g, plane, H, W, xf, yf, D, t, w_e, valid, pf && s == 0, accp[g], l1acc, gp, gt);
-                if (ODD) group_pixel<GRAD, IMG_GRAD, 1>(pc, NSRC - 1, plane, H, W, xf, yf, D, t, w_e, valid, pf && s == 0, accs, l1acc, gp, gt);
-                if (GRAD) {
-                    float* g = pc.g_disp[s];
-                    if (valid && g != nullptr)
-                    {
-                        float gv = (full && a.input_is_depth != PLB_INPUT_DEPTH) ? a.disp_a * D * gp : -gp * rcp_nr(D);
-                        if (full && HEAD) gv *= head_chain_from_depth(D, a.disp_a, a.disp_b, a.head_alpha, a.head_beta);
-                        g[o] = gv;
-                    }
-                }
+            if (GRAD && IMG_GRAD && valid && pc.g_tgt != nullptr) {
+                float* gq = pc.g_tgt + o;
+                atomicAdd(gq, gt[0]); atomicAdd(gq + plane, gt[1]); atomicAdd(gq + 2 * plane, gt[2]);
             }
         }
-        if (GRAD && IMG_GRAD && valid && pc.g_tgt != nullptr) {
-            float* g = pc.g_tgt + o;
-            atomicAdd(g, gt[0]); atomicAdd(g + plane, gt[1]); atomicAdd(g + 2 * plane, gt[2]);
+        if (LOW && GRAD) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const int s = sc[d], f = pc.fac[s], mode = md[d] & 3;
+                float* gdst = pc.g_disp[s];
+                if (gdst == nullptr || mode == PH_SM_LOWNOGRAD) continue;
+                const float* slot = stage + d * SST + lane;
+                const bool shared = (md[d] & 4) != 0;
+                if (mode == PH_SM_FULL) {
+                    if (valid) post_full<HEAD>(a, pc.disp[s] + oc, gdst + oc, shared, W, nr, slot);
+                } else if (mode == PH_SM_LOWSCRATCH) {
+                    if (valid) post_scratch(gdst + oc, shared, W, nr, slot);
+                } else {
+                    // this contributor's [2][dh][W] partial rows
+                    if ((d == 0 ? cb.c0 : cb.c1) != 0) gdst += (size_t)a.B * 2 * pc.dh[s] * W;
+                    post_low_p2(pc, s, f, gdst, H, W, x, valid, yc, nr, slot);     // LOWFAST: f is 2, 4 or 8
+                }
+            }
         }
     }
-    // end of the run: the lane's column (and possibly the pair) changes
+    // end of the run: the pose / loss sums
+    if (NS == 2 && ND == 1) {
+        float a9[9];
 #pragma unroll
-    for (int g = 0; g < NP; ++g) flush_group<float2, 2>(accp[g], 2 * g, l1acc, xf, rec, lane);
-    if (ODD) flush_group<float, 1>(accs, NSRC - 1, l1acc, xf, rec, lane);
+        for (int k = 0; k < 9; ++k) a9[k] = v_get(acc[k], 0);
+        flush_source(a9, cb.k0, l1acc, xf, rec, lane);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a9[k] = v_get(acc[k], 1);
+        flush_source(a9, cb.k0 + 1, 0.0f, xf, rec, lane);
+    } else {
+        float a9[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a9[k] = v_hsum(acc[k]);      // both halves of a scale pair belong to the one source
+        flush_source(a9, cb.k0, l1acc, xf, rec, lane);
+    }
     __syncwarp();
 }
 
@@ -707,179 +701,219 @@ __device__ inline void photo_pose_jacobian(const plb_photo_args& a, const plb_ph
     for (int m = 0; m < 6; ++m) J[k * 6 + m] = g6[m];
 }
 
-template <bool GRAD, bool IMG_GRAD, int MAXSRC, bool MULTI, bool HEAD>
-__global__ void __launch_bounds__(photo_threads(MAXSRC, MULTI), (MAXSRC <= 2) ? PH_MIN_BLOCKS : 2)
+// first unit whose weight interval starts at or after `pos`, moved up to the next cut position of its column.
+// Units are ordered (job, image, strip, combo, row); a row segment weighs combo_w[job][combo].
+__host__ __device__ inline int photo_unit_of(const PhotoLaunch& p, int H, int pos) {
+    int j = 0;
+    while (j + 1 < p.a.n_jobs && pos >= (int)p.weight_start[j + 1]) ++j;
+    const int rel = pos - (int)p.weight_start[j];
+    const int nc = p.n_combos[j];
+    const int scw = p.combo_cw[j][nc] * H;                  // weight of one (image, strip) super column
+    const int sci = rel / scw, r2 = rel - sci * scw;
+    int c = 0;
+    while (c + 1 < nc && r2 >= p.combo_cw[j][c + 1] * H) ++c;
+    const int w = p.combo_w[j][c];
+    const int row = (r2 - p.combo_cw[j][c] * H + w - 1) / w;   // 0 .. H (H = first row of the next column)
+    int u = p.unit_start[j] + (sci * nc + c) * H + row;
+    const int al = p.combo_align[j][c];
+    if (al > 1 && row < H) {
+        const int r = row & (al - 1);                       // al is a power of two
+        if (r) { const int up = al - r, left = H - row; u += up < left ? up : left; }
+    }
+    return u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-pair constants, once per (job, image) pair instead of once per block of the main kernel: K^-1 (fp64
+// adjugate, `transform.py:92`), the pose matrix (Rodrigues with the +1e-7 / Euler, optional rigid inverse,
+// `pose_geometry.py:110-199`), P = K.[R|t], Q = P[:, :3].K^-1 composed in fp64 from the two fp32 matrices the
+// reference multiplies a pixel by and rounded once, the packed tables of the combos and every base pointer already
+// offset to the image.  One block of two warps per pair (two short dependent chains side by side: this code runs
+// cold); the main kernel is launched as a programmatic dependent and copies the entries it needs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+photo_pairs_kernel(const __grid_constant__ PhotoLaunch p, int grad, int img_grad) {
+    const plb_photo_args& a = p.a;
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (skip_launch(a.skip_if_unit)) return;
+    __shared__ PairConst pc;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, W = a.W, plane = H * W;
+    const int jb = pair / a.B, b = pair - jb * a.B;
+    const plb_photo_job& job = a.jobs[jb];
+    char* ws = (char*)a.workspace;
+    float* gup = (float*)(ws + p.L.gup);
+    float* ylow = (float*)(ws + p.L.ylow);
+    const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
+    const size_t img = (size_t)b * 3 * plane;
+    for (int k = tid; k < (int)(sizeof(PairConst) / 4); k += 64) reinterpret_cast<float*>(&pc)[k] = 0.0f;
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 1) {
+            pc.tgt = job.tgt + img;
+            pc.g_tgt = (grad && img_grad && job.g_tgt) ? job.g_tgt + img : nullptr;
+            pc.n_src = job.n_src; pc.n_scales = job.n_scales; pc.lowres = p.lowres[jb];
+            pc.w_e = p.w_e[jb] * (a.upstream ? __ldg(a.upstream) : 1.0f);
+        }
+        if (lane >= 4 && lane < 4 + job.n_scales) {
+            const int sc = lane - 4;
+            const int dh = job.dh[sc], dw = job.dw[sc];
+            const int sm = p.smode[jb][sc];
+            pc.dh[sc] = dh; pc.dw[sc] = dw; pc.smode[sc] = sm;
+            {
+                const int f = H / dh;
+                pc.fac[sc] = (f * dh == H && f * dw == W && f >= 2 && (f & (f - 1)) == 0) ? f : 0;
+            }
+            pc.sx[sc] = (float)dw / (float)W; pc.sy[sc] = (float)dh / (float)H;
+            pc.disp[sc] = job.disp[sc] + (size_t)b * dh * dw;
+            float* g = nullptr;
+            if (grad && job.g_disp[sc] != nullptr) {
+                if ((sm & 3) == PH_SM_FULL) g = job.g_disp[sc] + (size_t)b * plane;
+                else if ((sm & 3) == PH_SM_LOWSCRATCH) g = gup + ((size_t)(jb * PLB_MAX_SCALES + sc) * a.B + b) * plane;
+                else if ((sm & 3) == PH_SM_LOWFAST) g = ylow + p.L.ylow_off[jb][sc] + (size_t)b * 2 * dh * W;
+            }
+            pc.g_disp[sc] = g;
+        }
+        if (lane == 8) {
+            float ki[9];
+            kinv_f32(Kb, a.k_is_f64, ki);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) pc.kinv[k] = ki[k];
+        }
+    } else {
+        if (lane < job.n_src) {
+            float M[12], P[12];
+            pose_to_M(a.poses + ((size_t)b * a.n_pose + job.pose_index[lane]) * 6, a.rotation_mode, job.pose_inv[lane], M);
+            k_times_M(Kb, a.k_is_f64, M, P);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) pc.P[lane][r] = make_float4(P[r * 4], P[r * 4 + 1], P[r * 4 + 2], P[r * 4 + 3]);
+            pc.src[lane] = job.src[lane] + img;
+            pc.g_src[lane] = (grad && img_grad && job.g_src[lane]) ? job.g_src[lane] + img : nullptr;
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        const int n_src = job.n_src;
+        // Q = P[:, :3] . fl32(K^-1): the exact product of the two fp32 matrices the reference multiplies a
+        // pixel by (transform.py:92,137), rounded once; one lane per (source, row)
+        if (lane < 3 * n_src) {
+            const int i = lane / 3, r = lane - 3 * i;
+            const float4 P = pc.P[i][r];
+            float q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                q[c] = (float)((double)P.x * (double)pc.kinv[0 + c] + (double)P.y * (double)pc.kinv[3 + c] +
+                               (double)P.z * (double)pc.kinv[6 + c]);
+            pc.Q[i][r] = make_float4(q[0], q[1], q[2], P.w);
+        }
+        __syncwarp();
+        // packed tables for the two halves of a combo: sources (2g, 2g+1), and every source with itself
+        if (lane < PH_NT2 * 3) {
+            const int tb = lane / 3, r = lane - tb * 3;
+            const int i0 = tb < PLB_MAX_SRC / 2 ? 2 * tb : tb - PLB_MAX_SRC / 2;
+            const int i1 = tb < PLB_MAX_SRC / 2 ? 2 * tb + 1 : i0;
+            if (i1 < n_src) {
+                const float4 q0 = pc.Q[i0][r], q1 = pc.Q[i1][r];
+                pc.T2[tb][r][0] = make_float4(q0.x, q1.x, q0.z, q1.z);
+                pc.T2[tb][r][1] = make_float4(q0.y, q1.y, q0.w, q1.w);
+            }
+        }
+    }
+    __syncthreads();
+    constexpr int N4 = (int)(sizeof(PairConst) / sizeof(float4));
+    float4* out = reinterpret_cast<float4*>(ws + p.L.pairs) + (size_t)pair * N4;
+    for (int k = tid; k < N4; k += 64) out[k] = reinterpret_cast<const float4*>(&pc)[k];
+}
+
+template <bool GRAD, bool IMG_GRAD, bool HEAD, bool LOW, int CH, int CW>
+#ifdef PH_MAXNREG
+__global__ void __maxnreg__(PH_MAXNREG)
+#else
+__global__ void __launch_bounds__(PH_THREADS, PH_MIN_BLOCKS)
+#endif
 photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
-    constexpr int PH_THREADS = photo_threads(MAXSRC, MULTI), PH_WARPS = PH_THREADS / 32;
     const plb_photo_args& a = p.a;
     // the finalize grid (programmatic dependent launch) may be scheduled from now on; it waits for
     // this grid to complete before it reads the records
     asm volatile("griddepcontrol.launch_dependents;");
     if (skip_launch(a.skip_if_unit)) return;
     DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 0 : 4);
-#if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 1
-    return;
-#endif
 
     char* ws = (char*)a.workspace;
     float* records = (float*)(ws + p.L.records);
     float* gup = (float*)(ws + p.L.gup);
+    float* ylow = (float*)(ws + p.L.ylow);
 
-    const int H = a.H, W = a.W;
+    const int H = CH > 0 ? CH : a.H, W = CW > 0 ? CW : a.W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int plane = H * W;
 
     __shared__ PairConst s_pc[2];
     __shared__ float s_rec[2][PH_WARPS][PH_NREC + 3];
     __shared__ int s_pair[2];
+    __shared__ float s_stage[LOW ? PH_WARPS : 1][LOW ? 2 * PH_CHUNK * 32 : 1];   // per-lane depth / gradient slots of a chunk
 
     // ---- this warp's unit range: equal shares of the weighted unit list (32-bit maths) ---------
     auto pos_of = [&](int w) -> int { return w * p.share + min(w, p.share_rem); };
-    auto unit_of = [&](int pos) -> int {  // first unit whose weight interval starts at or after pos
-        int j = 0;
-        while (j + 1 < a.n_jobs && pos >= (int)p.weight_start[j + 1]) ++j;
-        const int rel = pos - (int)p.weight_start[j];
-        return p.unit_start[j] + (rel + p.unit_weight[j] - 1) / p.unit_weight[j];
+    auto pair_of = [&](int u) -> int {
+        const int jb = (a.n_jobs > 1 && u >= p.unit_start[1]) ? 1 : 0;      // PLB_MAX_JOBS == 2
+        return jb * a.B + (u - p.unit_start[jb]) / p.units_per_pair[jb];
     };
-#ifdef PLB_DEBUG_REVERSE_BLOCKS
-    const int vblk = gridDim.x - 1 - blockIdx.x;
-#else
     const int vblk = blockIdx.x;     // virtual block index: which share of the unit list this block owns
-#endif
     const int gw = vblk * PH_WARPS + warp;
-    const int blk_u0 = unit_of(pos_of(vblk * PH_WARPS));
-    const int blk_u1 = unit_of(pos_of(vblk * PH_WARPS + PH_WARPS));
-    const int u0 = unit_of(pos_of(gw));
-    const int u1 = unit_of(pos_of(gw + 1));
+    const int blk_u0 = photo_unit_of(p, H, pos_of(vblk * PH_WARPS));
+    const int blk_u1 = photo_unit_of(p, H, pos_of(vblk * PH_WARPS + PH_WARPS));
+    const int u0 = photo_unit_of(p, H, pos_of(gw));
+    const int u1 = photo_unit_of(p, H, pos_of(gw + 1));
     const bool empty_block = blk_u1 <= blk_u0;  // more blocks than work: still publishes (empty) records
-    const int pairA = empty_block ? 0 : blk_u0 / p.units_per_pair;
-    const int pairB = empty_block ? 0 : (blk_u1 - 1) / p.units_per_pair;
+    const int pairA = empty_block ? 0 : pair_of(blk_u0);
+    const int pairB = empty_block ? 0 : pair_of(blk_u1 - 1);
 
-#if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 2
-    if (u0 >= 0) return;
-#endif
-    // ---- block prologue: context of the (at most two) pairs this block touches ------------------
+    // ---- block prologue: context of the (at most two) pairs this block touches, copied from the table that
+    //      photo_pairs_kernel (the primary of this programmatic dependent launch) filled - everything above ran
+    //      while that grid was still working -------------------------------------------------------------------
     if (tid < 2) s_pair[tid] = empty_block ? -1 : ((tid == 0) ? pairA : (pairB != pairA ? pairB : -1));
     for (int k = tid; k < 2 * PH_WARPS * (PH_NREC + 3); k += PH_THREADS) (&s_rec[0][0][0])[k] = 0.0f;
-    {
-        const int set = warp >> 1;  // warps 0,1 -> set 0; warps 2,3 -> set 1
-        const int pair = set == 0 ? pairA : pairB;
-        if (!empty_block && warp < 4 && (set == 0 || pairB != pairA)) {
-            const int jb = pair / a.B, b = pair - jb * a.B;
-            const plb_photo_job& job = a.jobs[jb];
-            PairConst& pc = s_pc[set];
-            const void* Kb = (const char*)a.K + (size_t)b * 9 * (a.k_is_f64 ? 8 : 4);
-            const size_t img = (size_t)b * 3 * plane;
-            if ((warp & 1) == 0) {
-                if (lane == 1) {
-                    pc.tgt = job.tgt + img;
-                    pc.g_tgt = (GRAD && IMG_GRAD && job.g_tgt) ? job.g_tgt + img : nullptr;
-                    pc.n_src = job.n_src; pc.n_scales = job.n_scales; pc.lowres = p.lowres[jb];
-                    pc.w_e = p.w_e[jb] * (a.upstream ? __ldg(a.upstream) : 1.0f);
-                }
-                if (lane >= 4 && lane < 4 + job.n_scales) {
-                    const int sc = lane - 4;
-                    const int dh = job.dh[sc], dw = job.dw[sc];
-                    pc.dh[sc] = dh; pc.dw[sc] = dw;
-                    pc.sx[sc] = (float)dw / (float)W; pc.sy[sc] = (float)dh / (float)H;
-                    pc.disp[sc] = job.disp[sc] + (size_t)b * dh * dw;
-                    float* g = nullptr;
-                    if (GRAD && job.g_disp[sc] != nullptr)
-                        g = ((p.lowres[jb] >> sc) & 1)
-                                ? gup + ((size_t)(jb * PLB_MAX_SCALES + sc) * a.B + b) * plane
-                                : job.g_disp[sc] + (size_t)b * plane;
-                    pc.g_disp[sc] = g;
-                }
-                if (lane == 8) {
-                    // K^-1 (fp64 adjugate, rounded to fp32 as transform.py:92 does) - in parallel with the pose chain
-                    // of the odd warp: executed once per block, this code runs cold, and two short dependent
-                    // chains on two warps finish sooner than one long chain
-                    float ki[9];
-                    kinv_f32(Kb, a.k_is_f64, ki);
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) pc.kinv[k] = ki[k];
-                }
-            } else {
-                if (lane < job.n_src) {
-                    float M[12], P[12];
-                    pose_to_M(a.poses + ((size_t)b * a.n_pose + job.pose_index[lane]) * 6, a.rotation_mode,
-                              job.pose_inv[lane], M);
-                    k_times_M(Kb, a.k_is_f64, M, P);
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) pc.P[lane][r] = make_float4(P[r * 4], P[r * 4 + 1], P[r * 4 + 2], P[r * 4 + 3]);
-                    pc.src[lane] = job.src[lane] + img;
-                    pc.g_src[lane] = (GRAD && IMG_GRAD && job.g_src[lane]) ? job.g_src[lane] + img : nullptr;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    {
-        const int set = warp >> 1;
-        if (!empty_block && warp < 4 && (warp & 1) == 1 && (set == 0 || pairB != pairA)) {
-            PairConst& pc = s_pc[set];
-            const int n_src = pc.n_src;
-            // Q = P[:, :3] . fl32(K^-1): the exact product of the two fp32 matrices the reference multiplies a
-            // pixel by (transform.py:92,137), rounded once; one lane per (source, row)
-            if (lane < 3 * n_src) {
-                const int i = lane / 3, r = lane - 3 * i;
-                const float4 P = pc.P[i][r];
-                float q[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    q[c] = (float)((double)P.x * (double)pc.kinv[0 + c] + (double)P.y * (double)pc.kinv[3 + c] +
-                                   (double)P.z * (double)pc.kinv[6 + c]);
-                pc.Q[i][r] = make_float4(q[0], q[1], q[2], P.w);
-            }
-            __syncwarp();
-            // packed copy for source pairs (2g, 2g+1): low half = even source, high half = odd source
-            if (lane < (PLB_MAX_SRC / 2) * 3) {
-                const int g = lane / 3, r = lane - g * 3;
-                if (2 * g + 1 < n_src) {
-                    const float4 q0 = pc.Q[2 * g][r], q1 = pc.Q[2 * g + 1][r];
-                    pc.Q2[g][r][0] = make_float4(q0.x, q1.x, q0.y, q1.y);
-                    pc.Q2[g][r][1] = make_float4(q0.z, q1.z, q0.w, q1.w);
-                }
-            }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!empty_block) {
+        constexpr int N4 = (int)(sizeof(PairConst) / sizeof(float4));
+        const float4* table = reinterpret_cast<const float4*>(ws + p.L.pairs);
+        const int n_set = pairB != pairA ? 2 : 1;
+        for (int k = tid; k < n_set * N4; k += PH_THREADS) {
+            const int set = k / N4, q = k - set * N4;
+            reinterpret_cast<float4*>(&s_pc[set])[q] = __ldcg(table + (size_t)(set == 0 ? pairA : pairB) * N4 + q);
         }
     }
     __syncthreads();
     DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 1 : 5);
-#if defined(PLB_DEBUG_EXIT_AT) && PLB_DEBUG_EXIT_AT == 3
-    if (u0 >= 0) return;
-#endif
 
-    // ---- runs: consecutive rows of one 32-px strip of one (job, image) pair ---------------------
+    // ---- runs: consecutive rows of one 32-px strip of one combo of one (job, image) pair --------
     int u = u0;
 #ifdef PLB_DEBUG_SKIP_UNITS
     u = u1;   // measurement only: fixed cost of prologue + epilogue
 #endif
 #pragma unroll 1
     while (u < u1) {
-        const int pair = u / p.units_per_pair;
-        const int local = u - pair * p.units_per_pair;
-        const int strip = local / H;
-        const int y = local - strip * H;
-        const int rows = min(u1, u - y + H) - u;
-        const int set = (pair == pairA) ? 0 : 1;
+        const int jb = (a.n_jobs > 1 && u >= p.unit_start[1]) ? 1 : 0;
+        const int loc = u - p.unit_start[jb];
+        const int b = loc / p.units_per_pair[jb];
+        const int rem = loc - b * p.units_per_pair[jb];
+        const int col = rem / H;                              // (strip, combo) column of the image
+        const int y = rem - col * H;
+        const int strip = col / p.n_combos[jb];
+        const PhotoCombo cb = p.combo[jb][col - strip * p.n_combos[jb]];
+        const int rows = min(u1 - u, H - y);
+        const int set = (jb * a.B + b == pairA) ? 0 : 1;
         const PairConst& pc = s_pc[set];
         float* rec = s_rec[set][warp];
-        const int n_src = pc.n_src;
-        if (MAXSRC <= 2) {
-            if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-            else if (PH_ROWPAIR && MAXSRC > 2 && !IMG_GRAD) run_rows_single<GRAD, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-            else run_rows<GRAD, IMG_GRAD, 1, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-        } else {
-            if (n_src == 4) run_rows<GRAD, IMG_GRAD, 4, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-            else if (n_src == 3) run_rows<GRAD, IMG_GRAD, 3, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-            else if (n_src == 2) run_rows<GRAD, IMG_GRAD, 2, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-            else if (PH_ROWPAIR && MAXSRC > 2 && !IMG_GRAD) run_rows_single<GRAD, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-            else run_rows<GRAD, IMG_GRAD, 1, MULTI, HEAD>(a, pc, strip, y, rows, lane, rec);
-        }
+        float* stage = s_stage[LOW ? warp : 0];
+        if (cb.kind == PH_KIND_SRCPAIR) run_combo<GRAD, IMG_GRAD, 2, 1, HEAD, LOW, CH, CW>(a, pc, cb, strip, y, rows, lane, rec, stage);
+        else if (cb.kind == PH_KIND_SCALEPAIR) run_combo<GRAD, IMG_GRAD, 2, 2, HEAD, LOW, CH, CW>(a, pc, cb, strip, y, rows, lane, rec, stage);
+        else run_combo<GRAD, IMG_GRAD, 1, 1, HEAD, LOW, CH, CW>(a, pc, cb, strip, y, rows, lane, rec, stage);
         u += rows;
     }
 
-    // ---- block records: fixed-order sum over the 8 warps, one record per touched pair; the
+    // ---- block records: fixed-order sum over the warps, one record per touched pair; the
     //      finalize kernel combines them (no fences, no tickets here) --------------------------
     __syncthreads();
     DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 2 : 6);
@@ -908,6 +942,107 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         reinterpret_cast<float2*>(ws + p.L.lossrec)[vblk * 2 + tid] = make_float2(__int_as_float(s_pair[tid]), v);
     }
     DBG_STAMP(threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), blockIdx.x == 0 ? 3 : 7);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Low-resolution scales, second half of the transposed upsample: the main kernel left, per (job, scale,
+// contributor, image), two slots of [dh][W] rows already reduced over the full-resolution ROWS; one thread per
+// low-resolution pixel gathers the full-resolution COLUMNS of its footprint (the align_corners=False weights of
+// up_coord, the same the forward used), sums slots and contributors in a fixed order and applies the
+// depth -> disparity (-> head) chain.  Deterministic; reads (2 / factor) of a plane per scale.
+// ---------------------------------------------------------------------------------------------
+struct LowMergeItem { int jb, s, first_block, n_contrib, f, col_chunks; };
+struct LowMergeLaunch {
+    int n_items;
+    int total_blocks;
+    LowMergeItem items[PLB_MAX_JOBS * PLB_MAX_SCALES];
+};
+constexpr int LM_THREADS = 256, LM_COLS = 64, LM_ROWS = LM_THREADS / LM_COLS;   // a block: 4 low-res rows x 64 columns
+
+// Footprint of low-res column i for factor F: the F columns with x0 == i - 1 (weight l1) and the F columns with
+// x0 == i (weight l0 = 1 - l1), l1 = ((x - F/2) mod F + 0.5) / F - a triangle; at the left border the first F/2
+// columns clamp to x0 = 0 with weight 1, at the right border the last F/2 columns put both weights on column dw - 1
+// (up_coord's rules; the values are dyadic rationals, identical to its fp32 arithmetic).  Interior columns: constant
+// weights, immediate offsets, all loads in flight before the first use.
+template <int F, int NC>
+__device__ __forceinline__ float lowres_gather(const float* row0, size_t slot, size_t cstride, int i, int dw, int W) {
+    constexpr int HF = F / 2;
+    const int xs = i * F - HF;
+    float acc = 0.0f;
+    if (i > 0 && i < dw - 1) {
+        const float* q = row0 + xs;
+        float v[2 * F];
+#pragma unroll
+        for (int t = 0; t < 2 * F; ++t) {
+            v[t] = __ldg(q + t) + __ldg(q + slot + t);
+            if (NC > 1) v[t] += __ldg(q + cstride + t) + __ldg(q + cstride + slot + t);
+        }
+#pragma unroll
+        for (int t = 0; t < 2 * F; ++t) {
+            const float w = t < F ? ((float)t + 0.5f) * (1.0f / (float)F) : 1.0f - ((float)(t - F) + 0.5f) * (1.0f / (float)F);
+            acc = fmaf(w, v[t], acc);
+        }
+    } else {
+#pragma unroll 1
+        for (int t = 0; t < 2 * F; ++t) {
+            const int x = xs + t;
+            if (x < 0 || x >= W) continue;
+            float w = t < F ? ((float)t + 0.5f) * (1.0f / (float)F) : 1.0f - ((float)(t - F) + 0.5f) * (1.0f / (float)F);
+            if (x < HF) w = (i == 0) ? 1.0f : 0.0f;
+            if (i == dw - 1 && x >= W - HF) w = 1.0f;
+            float v = __ldg(row0 + x) + __ldg(row0 + slot + x);
+            if (NC > 1) v += __ldg(row0 + cstride + x) + __ldg(row0 + cstride + slot + x);
+            acc = fmaf(w, v, acc);
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(LM_THREADS)
+photo_lowres_merge_kernel(const __grid_constant__ PhotoLaunch p, const __grid_constant__ LowMergeLaunch u) {
+    const plb_photo_args& a = p.a;
+    if (skip_launch(a.skip_if_unit)) return;
+    int it = 0;
+#pragma unroll
+    for (int k = 1; k < PLB_MAX_JOBS * PLB_MAX_SCALES; ++k)
+        if (k < u.n_items && (int)blockIdx.x >= u.items[k].first_block) it = k;
+    const LowMergeItem item = u.items[it];
+    const plb_photo_job& job = a.jobs[item.jb];
+    const int s = item.s, dh = job.dh[s], dw = job.dw[s], W = a.W;
+    // block -> (group of LM_ROWS rows of the [B * dh] low-res rows, chunk of LM_COLS columns): two 32-bit divides per thread
+    const unsigned local = blockIdx.x - (unsigned)item.first_block;
+    const unsigned rg = local / (unsigned)item.col_chunks, cc = local - rg * (unsigned)item.col_chunks;
+    const unsigned bj = rg * LM_ROWS + (threadIdx.x / LM_COLS);            // b * dh + j
+    const int i = (int)(cc * LM_COLS + (threadIdx.x % LM_COLS));
+    if (bj >= (unsigned)a.B * (unsigned)dh || i >= dw) return;
+    const int b = (int)(bj / (unsigned)dh), j = (int)(bj - (unsigned)b * (unsigned)dh);
+    const float* base = (const float*)((const char*)a.workspace + p.L.ylow) + p.L.ylow_off[item.jb][s];
+    const size_t cstride = (size_t)a.B * 2 * dh * W;     // one contributor
+    const float* row0 = base + ((size_t)b * 2 * dh + j) * W;
+    const size_t slot = (size_t)dh * W;
+    float acc;
+    if (item.n_contrib > 1) {
+        if (item.f == 2) acc = lowres_gather<2, 2>(row0, slot, cstride, i, dw, W);
+        else if (item.f == 4) acc = lowres_gather<4, 2>(row0, slot, cstride, i, dw, W);
+        else acc = lowres_gather<8, 2>(row0, slot, cstride, i, dw, W);
+    } else {
+        if (item.f == 2) acc = lowres_gather<2, 1>(row0, slot, cstride, i, dw, W);
+        else if (item.f == 4) acc = lowres_gather<4, 1>(row0, slot, cstride, i, dw, W);
+        else acc = lowres_gather<8, 1>(row0, slot, cstride, i, dw, W);
+    }
+    float chain = 1.0f;
+    const size_t o = (size_t)bj * dw + i;
+    if (a.input_is_depth != PLB_INPUT_DEPTH) {
+        float d = __ldg(job.disp[s] + o), hc = 1.0f;
+        if (a.input_is_depth == PLB_INPUT_LOGIT) {
+            const float sg = 1.0f / (1.0f + expf(-d));
+            d = fmaf(a.head_alpha, sg, a.head_beta);
+            hc = a.head_alpha * sg * (1.0f - sg);
+        }
+        const float D = 1.0f / (a.disp_a * d + a.disp_b);
+        chain = -a.disp_a * D * D * hc;
+    }
+    job.g_disp[s][o] = acc * chain;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -966,8 +1101,9 @@ photo_finalize_kernel(const __grid_constant__ PhotoLaunch p, int want_grad) {
         if (jb < a.n_jobs) {
             const int pr = jb * a.B + b;
             // blocks whose range can overlap this pair (widened by one block on each side; records carry the pair id)
-            const long long w0 = p.weight_start[jb] + (long long)(pr * p.units_per_pair - p.unit_start[jb]) * p.unit_weight[jb];
-            const long long w1 = w0 + (long long)p.units_per_pair * p.unit_weight[jb];
+            const long long pw = (long long)p.strips * p.combo_cw[jb][p.n_combos[jb]] * a.H;   // weight of one image of the job
+            const long long w0 = p.weight_start[jb] + (long long)b * pw;
+            const long long w1 = w0 + pw;
             int k_lo = photo_warp_of(p, w0) / p.warps_per_block - 1;
             int k_hi = photo_warp_of(p, w1) / p.warps_per_block + 1;
             k_lo = max(k_lo, 0); k_hi = min(k_hi, p.grid - 1);
@@ -1296,7 +1432,8 @@ int validate_photo(const plb_photo_args* a) {
     if (a->B < 1 || a->H < 2 || a->W < 2 || a->n_jobs < 1 || a->n_jobs > PLB_MAX_JOBS || a->n_pose < 1)
         return PLB_EINVAL;
     if ((long long)a->H * a->W * 3 >= (1LL << 31)) return PLB_EINVAL;
-    if ((long long)a->H * ((a->W + 31) / 32) * a->B * a->n_jobs * PLB_MAX_SCALES * PLB_MAX_SRC * 8 >= (1LL << 31)) return PLB_EINVAL;
+    // the weighted unit list is indexed with 32-bit integers: <= PH_MAX_COMBOS combos per strip, <= 64 weight units each
+    if ((long long)a->H * ((a->W + 31) / 32) * a->B * a->n_jobs * PH_MAX_COMBOS * 64 >= (1LL << 31)) return PLB_EINVAL;
     if (a->rotation_mode != PLB_ROT_AXISANGLE && a->rotation_mode != PLB_ROT_EULER) return PLB_EINVAL;
     if (a->poses == nullptr || a->K == nullptr || a->loss == nullptr) return PLB_ENULL;
     for (int j = 0; j < a->n_jobs; ++j) {
@@ -1319,42 +1456,14 @@ int validate_photo(const plb_photo_args* a) {
     return PLB_OK;
 }
 
-template <bool GRAD, bool IMG, int MS, bool MULTI, bool HEAD>
-static int blocks_per_sm() {
-    static int cached = 0;
-    if (cached == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, MS, MULTI, HEAD>, photo_threads(MS, MULTI), 0) != cudaSuccess ||
-            n < 1) {
-            (void)cudaGetLastError();
-            n = 2;
-        }
-        cached = n;
-    }
-    return cached;
-}
-
-static int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
-            (void)cudaGetLastError();
-            n = 148;
-        }
-        cached = n;
-    }
-    return cached;
-}
-
 int photo_upsample_T_launch(const PhotoLaunch& p, cudaStream_t st) {
     const plb_photo_args* a = &p.a;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[PLB_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {                                    // per device: a process may drive several GPUs
         const cudaError_t e = cudaFuncSetAttribute(photo_upsample_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UT_SMEM);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     {
         UpTLaunch u;
@@ -1366,7 +1475,7 @@ int photo_upsample_T_launch(const PhotoLaunch& p, cudaStream_t st) {
             for (int j = 0; j < a->n_jobs; ++j)
                 for (int s = 0; s < a->jobs[j].n_scales; ++s) {
                     const plb_photo_job& job = a->jobs[j];
-                    if (!job.g_disp[s] || (job.dh[s] == a->H && job.dw[s] == a->W)) continue;
+                    if (photo_scale_mode(*a, j, s) != PH_SM_LOWSCRATCH) continue;
                     bool taken = false;
                     for (int k = 0; k < u.n_items; ++k) taken = taken || (u.items[k].jb == j && u.items[k].s == s);
                     if (taken) continue;
@@ -1389,6 +1498,133 @@ int photo_upsample_T_launch(const PhotoLaunch& p, cudaStream_t st) {
     return PLB_OK;
 }
 
+// ---- per-device launch constants (a process may drive several GPUs) ---------------------------------------
+static int sm_count() {
+    static int cached[PLB_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = 148;
+        }
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <bool GRAD, bool IMG, bool HEAD, bool LOW, int CH, int CW>
+static int launch_variant(const PhotoLaunch& p, int query_only, cudaStream_t st) {
+    if (query_only) {
+        static int cached[PLB_MAX_DEVICES] = {};
+        const int dev = current_device();
+        if (cached[dev] == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_l1_kernel<GRAD, IMG, HEAD, LOW, CH, CW>, PH_THREADS, 0) != cudaSuccess || n < 1) {
+                (void)cudaGetLastError();
+                n = 2;
+            }
+            cached[dev] = n;
+        }
+        return cached[dev];
+    }
+    // programmatic dependent of photo_pairs_kernel: this grid's own set-up overlaps the tail of that one
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(PH_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = PH_USE_PDL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, photo_l1_kernel<GRAD, IMG, HEAD, LOW, CH, CW>, p);
+}
+
+// the kernel variant of a launch: gradients / image gradients / folded disparity head / any low-resolution scale,
+// and - for the hot configuration (gradients, no image gradients, no head) - the image size as a compile-time
+// constant for the KITTI shapes the reference trains at (every tap address is then base + immediate)
+static int dispatch_variant(const PhotoLaunch& p, bool img_grad, bool head, bool low, int query_only, cudaStream_t st) {
+    const plb_photo_args& a = p.a;
+#define PLB_GO(G, I, HD, CH, CW) (low ? launch_variant<G, I, HD, true, CH, CW>(p, query_only, st) : launch_variant<G, I, HD, false, CH, CW>(p, query_only, st))
+    if (!a.want_grad) return head ? PLB_GO(false, false, true, 0, 0) : PLB_GO(false, false, false, 0, 0);
+    if (img_grad) return PLB_GO(true, true, false, 0, 0);
+    if (head) return PLB_GO(true, false, true, 0, 0);
+#ifndef PH_NO_FIXED_DIMS
+    if (a.H == 192 && a.W == 640) return PLB_GO(true, false, false, 192, 640);
+    if (a.H == 320 && a.W == 1024) return PLB_GO(true, false, false, 320, 1024);
+#endif
+    return PLB_GO(true, false, false, 0, 0);
+#undef PLB_GO
+}
+
+// combos of one job: source pairs at every scale, the odd source at pairs of scales, at most one single sample
+static int build_combos(const plb_photo_job& job, PhotoCombo* out, int* contrib /* [MAX_SCALES] */) {
+    int n = 0;
+    for (int s = 0; s < PLB_MAX_SCALES; ++s) contrib[s] = 0;
+    for (int g = 0; g + 1 < job.n_src; g += 2)
+        for (int s = 0; s < job.n_scales; ++s) {
+            PhotoCombo c = {};
+            c.kind = PH_KIND_SRCPAIR; c.k0 = (unsigned char)g; c.s0 = c.s1 = (unsigned char)s;
+            c.c0 = c.c1 = (unsigned char)contrib[s]++;
+            out[n++] = c;
+        }
+    if (job.n_src & 1) {
+        const int k = job.n_src - 1;
+        int s = 0;
+        for (; s + 1 < job.n_scales; s += 2) {
+            PhotoCombo c = {};
+            c.kind = PH_KIND_SCALEPAIR; c.k0 = (unsigned char)k; c.s0 = (unsigned char)s; c.s1 = (unsigned char)(s + 1);
+            c.c0 = (unsigned char)contrib[s]++; c.c1 = (unsigned char)contrib[s + 1]++;
+            out[n++] = c;
+        }
+        if (s < job.n_scales) {
+            PhotoCombo c = {};
+            c.kind = PH_KIND_SINGLE; c.k0 = (unsigned char)k; c.s0 = c.s1 = (unsigned char)s;
+            c.c0 = c.c1 = (unsigned char)contrib[s]++;
+            out[n++] = c;
+        }
+    }
+    return n;
+}
+
+// zero-fill of a gradient map two combos add into - skipped, like every launch of a guarded backward relaunch,
+// when all upstream gradients are 1 (the values written by the forward pass then stand)
+__global__ void guarded_zero_kernel(float* g, size_t n, const float* skip0, const float* skip1) {
+    const float* const flags[2] = {skip0, skip1};
+    if (skip_launch(flags)) return;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n && (reinterpret_cast<size_t>(g) & 15) == 0) {
+        *reinterpret_cast<float4*>(g + i) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    } else {
+        for (size_t k = i; k < n && k < i + 4; ++k) g[k] = 0.0f;
+    }
+}
+
+static int photo_lowres_merge_launch(const PhotoLaunch& p, cudaStream_t st) {
+    const plb_photo_args& a = p.a;
+    LowMergeLaunch u;
+    u.n_items = 0;
+    u.total_blocks = 0;
+    for (int j = 0; j < a.n_jobs; ++j)
+        for (int s = 0; s < a.jobs[j].n_scales; ++s) {
+            if ((p.smode[j][s] & 3) != PH_SM_LOWFAST) continue;
+            LowMergeItem& it = u.items[u.n_items++];
+            it.jb = j; it.s = s; it.first_block = u.total_blocks;
+            it.n_contrib = (p.smode[j][s] & 4) ? 2 : 1;
+            it.f = a.W / a.jobs[j].dw[s];
+            it.col_chunks = (a.jobs[j].dw[s] + LM_COLS - 1) / LM_COLS;
+            const long long rows = (long long)a.B * a.jobs[j].dh[s];                      // < 2^31: validate_photo
+            u.total_blocks += (int)((rows + LM_ROWS - 1) / LM_ROWS) * it.col_chunks;
+        }
+    if (u.n_items == 0) return PLB_OK;
+    photo_lowres_merge_kernel<<<u.total_blocks, LM_THREADS, 0, st>>>(p, u);
+    ++g_launches;
+    PLB_CHECK_LAUNCH();
+    return PLB_OK;
+}
+
 int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     if (a != nullptr && a->n_jobs >= 1 && a->n_jobs <= PLB_MAX_JOBS && a->jobs[0].mode == PLB_PHOTO_MIN_REPROJ)
         return photo_min_launch(a, st);
@@ -1397,87 +1633,104 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     PhotoLaunch p;
     p.a = *a;
     p.L = photo_layout(*a);
-    bool img_grad = false;
-    int maxsrc = 1;
+    bool img_grad = false, low = false, lowfast = false;
     for (int j = 0; j < a->n_jobs; ++j) {
         if (a->jobs[j].g_tgt) img_grad = true;
         for (int i = 0; i < a->jobs[j].n_src; ++i)
             if (a->jobs[j].g_src[i]) img_grad = true;
-        if (a->jobs[j].n_src > maxsrc) maxsrc = a->jobs[j].n_src;
     }
-    const bool lowres_grad = photo_has_lowres_grad(*a);
     // the disparity head folded in (PLB_INPUT_LOGIT) is its own set of kernel variants: the default variants keep
-    // their register budget (the single-scale one has none to spare)
+    // their register budget
     const bool head = a->input_is_depth == PLB_INPUT_LOGIT;
     if (head && img_grad) return PLB_EINVAL;       // image gradients: disparity / depth inputs only
     p.strips = (a->W + 31) / 32;
-    p.units_per_pair = p.strips * a->H;
     p.n_pairs = a->n_jobs * a->B;
-    long long wsum = 0;
-    int usum = 0, min_w = 1 << 30;
+    long long wsum = 0, pair_w_min = 1LL << 62;
+    int usum = 0;
     for (int j = 0; j < PLB_MAX_JOBS; ++j) {
         p.weight_start[j] = wsum;
         p.unit_start[j] = usum;
-        p.unit_weight[j] = 1;
+        p.units_per_pair[j] = 1;
+        for (int c = 0; c < PH_MAX_COMBOS; ++c) { p.combo_w[j][c] = 1; p.combo_cw[j][c] = c; p.combo_align[j][c] = 1; }
+        p.combo_cw[j][PH_MAX_COMBOS] = PH_MAX_COMBOS;
+        p.n_combos[j] = 0;
         p.w_e[j] = 0.0f;
         p.lowres[j] = 0;
+        for (int s = 0; s < PLB_MAX_SCALES; ++s) p.smode[j][s] = PH_SM_FULL;
         if (j < a->n_jobs) {
-            // cost model of a unit: a PAIR of sources runs on the packed fp32 pipe and costs less than two single
-            // (scalar) sources; the ratio is tuned per kernel variant (profiles/README.md)
-            {
-                const int wp = maxsrc <= 2 ? PH_W_PAIR : PH_W_PAIR4, wo = maxsrc <= 2 ? PH_W_ODD : PH_W_ODD4;
-                const int ws = PH_W_SINGLE4;      // a single-source job beside a 3-4-source one: row pairs on the packed pipe
-                const int n = a->jobs[j].n_src;
-                p.unit_weight[j] = a->jobs[j].n_scales * ((n == 1 && PH_ROWPAIR && maxsrc > 2 && !img_grad) ? ws : wp * (n / 2) + wo * (n & 1));
+            const plb_photo_job& job = a->jobs[j];
+            int contrib[PLB_MAX_SCALES];
+            p.n_combos[j] = build_combos(job, p.combo[j], contrib);
+            // cost model of a row segment: a packed combo costs less than two single samples on the scalar pipe; every
+            // low-resolution depth stream adds its pre- / post-pass
+            p.combo_cw[j][0] = 0;
+            for (int c = 0; c < p.n_combos[j]; ++c) {
+                const PhotoCombo& cb = p.combo[j][c];
+                int w = cb.kind == PH_KIND_SINGLE ? PH_W_ODD : PH_W_PAIR;
+                if (photo_scale_mode(*a, j, cb.s0) != PH_SM_FULL) w += PH_W_LOW;
+                if (cb.kind == PH_KIND_SCALEPAIR) {
+                    w += PH_W_SPAIR;
+                    if (photo_scale_mode(*a, j, cb.s1) != PH_SM_FULL) w += PH_W_LOW;
+                }
+                p.combo_w[j][c] = w;
+                p.combo_cw[j][c + 1] = p.combo_cw[j][c] + w;
+                // a chunk boundary or a cut may cross the footprint of a low-res row (<= 2.5 x factor rows) at most once
+                int al = 1;
+                if (photo_scale_mode(*a, j, cb.s0) == PH_SM_LOWFAST) al = 2 * (a->H / job.dh[cb.s0]);
+                if (cb.kind == PH_KIND_SCALEPAIR && photo_scale_mode(*a, j, cb.s1) == PH_SM_LOWFAST && 2 * (a->H / job.dh[cb.s1]) > al)
+                    al = 2 * (a->H / job.dh[cb.s1]);
+                p.combo_align[j][c] = al;
             }
-            if (p.unit_weight[j] < min_w) min_w = p.unit_weight[j];
-            wsum += (long long)p.unit_weight[j] * p.units_per_pair * a->B;
-            usum += p.units_per_pair * a->B;
-            p.w_e[j] = a->jobs[j].term_weight / (3.0f * (float)a->B * (float)a->H * (float)a->W);
-            for (int s = 0; s < a->jobs[j].n_scales; ++s)
-                if (a->jobs[j].dh[s] != a->H || a->jobs[j].dw[s] != a->W) p.lowres[j] |= 1 << s;
+            p.units_per_pair[j] = p.strips * p.n_combos[j] * a->H;
+            const long long pw = (long long)p.combo_cw[j][p.n_combos[j]] * p.strips * a->H;
+            if (pw < pair_w_min) pair_w_min = pw;
+            wsum += pw * a->B;
+            usum += p.units_per_pair[j] * a->B;
+            p.w_e[j] = job.term_weight / (3.0f * (float)a->B * (float)a->H * (float)a->W);
+            for (int s = 0; s < job.n_scales; ++s) {
+                const int sm = photo_scale_mode(*a, j, s);
+                if (sm != PH_SM_FULL) { p.lowres[j] |= 1 << s; low = true; }
+                if (sm == PH_SM_LOWFAST) lowfast = true;
+                const bool shared = a->want_grad && job.g_disp[s] != nullptr && contrib[s] > 1;
+                p.smode[j][s] = (unsigned char)(sm | (shared ? 4 : 0));
+                if (shared && sm != PH_SM_LOWFAST) {
+                    // two combos add into this map (two addends: the sum does not depend on their order): zero it first
+                    float* g; size_t n;
+                    if (sm == PH_SM_FULL) { g = job.g_disp[s]; n = (size_t)a->B * a->H * a->W; }
+                    else { g = (float*)((char*)a->workspace + p.L.gup) + (size_t)(j * PLB_MAX_SCALES + s) * a->B * a->H * a->W; n = (size_t)a->B * a->H * a->W; }
+                    guarded_zero_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, st>>>(g, n, p.a.skip_if_unit[0], p.a.skip_if_unit[1]);
+                    ++g_launches;
+                    PLB_CHECK_LAUNCH();
+                }
+            }
         }
     }
     p.weight_start[PLB_MAX_JOBS] = wsum;
     p.unit_start[PLB_MAX_JOBS] = usum;
 
-    bool multi = false;
-    for (int j = 0; j < a->n_jobs; ++j)
-        if (a->jobs[j].n_scales != 1 || p.lowres[j] != 0) multi = true;
-    int bps;
-#define PLB_BPS(G, I, M) (head ? (multi ? blocks_per_sm<G, false, M, true, true>() : blocks_per_sm<G, false, M, false, true>()) \
-                               : (multi ? blocks_per_sm<G, I, M, true, false>() : blocks_per_sm<G, I, M, false, false>()))
-    if (!a->want_grad) bps = maxsrc <= 2 ? PLB_BPS(false, false, 2) : PLB_BPS(false, false, 4);
-    else if (img_grad) bps = maxsrc <= 2 ? PLB_BPS(true, true, 2) : PLB_BPS(true, true, 4);
-    else bps = maxsrc <= 2 ? PLB_BPS(true, false, 2) : PLB_BPS(true, false, 4);
-#undef PLB_BPS
-    long long grid = (long long)sm_count() * bps;
+    const int bps = dispatch_variant(p, img_grad, head, low, 1, st);
+    // more blocks than are resident: the hardware hands a waiting block to whichever SM retires one first, which evens
+    // out the finishing times of the SMs (blocks of equal work do not take equal time)
+    long long grid = (long long)sm_count() * bps * PH_GRID_MULT;
     // a block's weight range must not exceed the lightest pair, so that it touches at most two pairs
-    const long long pair_w_min = (long long)min_w * p.units_per_pair;
     const long long need = (wsum + pair_w_min - 1) / pair_w_min + 1;
     if (grid > usum) grid = usum;                  // tiny problems: no more blocks than units ...
     if (grid < need) grid = need;                  // ... but never so few that a block spans three pairs
     if (grid > photo_max_grid(*a)) grid = photo_max_grid(*a);
     if (grid < 1) grid = 1;
     p.grid = (int)grid;
-    p.warps_per_block = photo_threads(maxsrc <= 2 ? 2 : 4, multi) / 32;
+    p.warps_per_block = PH_WARPS;
     p.n_warps = p.grid * p.warps_per_block;
     p.share = (int)(wsum / p.n_warps);
     p.share_rem = (int)(wsum % p.n_warps);
 
-    dim3 g(p.grid), block(photo_threads(maxsrc <= 2 ? 2 : 4, multi));
-#define PLB_LAUNCH(G, I, M)                                           \
-    do {                                                              \
-        if (head) {                                                   \
-            if (multi) photo_l1_kernel<G, false, M, true, true><<<g, block, 0, st>>>(p); \
-            else photo_l1_kernel<G, false, M, false, true><<<g, block, 0, st>>>(p);      \
-        } else if (multi) photo_l1_kernel<G, I, M, true, false><<<g, block, 0, st>>>(p); \
-        else photo_l1_kernel<G, I, M, false, false><<<g, block, 0, st>>>(p);             \
-    } while (0)
-    if (!a->want_grad) { if (maxsrc <= 2) PLB_LAUNCH(false, false, 2); else PLB_LAUNCH(false, false, 4); }
-    else if (img_grad) { if (maxsrc <= 2) PLB_LAUNCH(true, true, 2); else PLB_LAUNCH(true, true, 4); }
-    else { if (maxsrc <= 2) PLB_LAUNCH(true, false, 2); else PLB_LAUNCH(true, false, 4); }
-#undef PLB_LAUNCH
+    photo_pairs_kernel<<<p.n_pairs, 64, 0, st>>>(p, (int)a->want_grad, (int)img_grad);
+    ++g_launches;
+    PLB_CHECK_LAUNCH();
+    {
+        const int e = dispatch_variant(p, img_grad, head, low, 0, st);
+        if (e != 0) return e;
+    }
     ++g_launches;
     PLB_CHECK_LAUNCH();
     {
@@ -1496,9 +1749,15 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
         ++g_launches;
         PLB_CHECK_LAUNCH();
     }
-    if (lowres_grad) {
-        const int rc2 = photo_upsample_T_launch(p, st);
-        if (rc2 != PLB_OK) return rc2;
+    if (a->want_grad) {
+        if (lowfast) {
+            const int rc2 = photo_lowres_merge_launch(p, st);
+            if (rc2 != PLB_OK) return rc2;
+        }
+        if (photo_has_lowres_grad(*a)) {
+            const int rc2 = photo_upsample_T_launch(p, st);
+            if (rc2 != PLB_OK) return rc2;
+        }
     }
     return PLB_OK;
 }

@@ -5,19 +5,16 @@
 
 namespace plb {
 
-// Threads per block of the fused L1 kernel, per variant (tuned on B200, profiles/README.md): the
-// single-scale <= 2-source kernel runs best with 96 registers and no spills (3 x 192 threads per SM);
-// the multi-scale / many-source variants prefer 256-thread blocks.  >= 128: the prologue uses warps 0-3.
-#ifndef PH_THREADS_SINGLE
-#define PH_THREADS_SINGLE 192
+// Threads per block of the fused L1 kernel (tuned on B200, profiles/README.md): 4 x 160 threads per SM = 5 warps per
+// scheduler, the most that 96 registers per thread allow (a scheduler's quarter of the register file holds
+// 16384 / (32 x 96) = 5.3 warps; 3 x 192 leaves two schedulers a warp short).
+#ifndef PH_THREADS
+#define PH_THREADS 160
 #endif
-#ifndef PH_THREADS_MULTI
-#define PH_THREADS_MULTI 256
+#ifndef PH_MIN_BLOCKS
+#define PH_MIN_BLOCKS 4           // resident blocks per SM the kernel is compiled for
 #endif
-__host__ __device__ constexpr int photo_threads(int maxsrc, bool multi) {
-    return (maxsrc <= 2 && !multi) ? PH_THREADS_SINGLE : PH_THREADS_MULTI;
-}
-constexpr int PH_MAX_WARPS = 8;
+constexpr int PH_WARPS = PH_THREADS / 32;
 constexpr int PH_NREC = PLB_MAX_SRC * 12 + 1;  // per (job,image) record: dP[src][12], sum|diff|
 constexpr int PH_REC_STRIDE = 64;  // floats per (block, set) record = two 128-byte lines: [0..PH_NREC) values, [PH_REC_ID] pair id
 constexpr int PH_REC_ID = 63;
@@ -27,29 +24,47 @@ constexpr int PH_REC_ID = 63;
 #ifndef PH_PF_SRC
 #define PH_PF_SRC 1               // L1 prefetch of the source row this many rows below the current footprint (0 = off)
 #endif
-#ifndef PH_ROWPAIR
-#define PH_ROWPAIR 1                // single-source directions of the 3-4-source kernels: two rows per iteration on the packed pipe
-#endif
-#ifndef PH_MIN_BLOCKS
-#define PH_MIN_BLOCKS 3           // resident blocks per SM the <= 2-source kernels are compiled for
-#endif
-
+// cost model of one row segment of a combo (the unit list is cut into equal WEIGHT shares, one per warp)
 #ifndef PH_W_PAIR
-#define PH_W_PAIR 8               // relative cost of a source pair (packed pipe) ...
+#define PH_W_PAIR 27              // a packed combo (two (source, scale) samples on the packed fp32 pipe) ...
 #endif
 #ifndef PH_W_ODD
-#define PH_W_ODD 5                // ... and of a single source (scalar pipe) in the unit weights, <= 2-source kernels
+#define PH_W_ODD 19               // ... a single sample on the scalar pipe ...
 #endif
-#ifndef PH_W_SINGLE4
-#define PH_W_SINGLE4 4             // a single-source job in the 3-4-source kernels (two rows per iteration on the packed pipe)
+#ifndef PH_W_LOW
+#define PH_W_LOW 3                // ... and what every low-resolution depth stream of the combo adds (pre- and post-pass of a chunk)
 #endif
-#ifndef PH_W_PAIR4
-#define PH_W_PAIR4 4              // the same for the 3-4-source kernels (both <= 8)
+#ifndef PH_W_SPAIR
+#define PH_W_SPAIR 14              // ... and a scale pair (two gradient maps instead of one)
 #endif
-#ifndef PH_W_ODD4
-#define PH_W_ODD4 5                // (measured: the odd source of the 4-source variant costs MORE than a packed pair)
+#ifndef PH_GRID_MULT
+#define PH_GRID_MULT 1            // blocks launched per resident block slot
+#endif
+#ifndef PH_ROW_ALIGN
+#define PH_ROW_ALIGN 16           // rows of a chunk (shared-memory staging of a low-resolution stream): >= 2 x the largest LOWFAST factor
 #endif
 
+// A COMBO is what one warp evaluates per target pixel: two (source, scale) samples on the two halves of the packed
+// fp32 pipe - two sources at one scale, or one source at two scales (same pixel ray, two depths) - or, when a job
+// has an odd number of samples, one sample on the scalar pipe.
+constexpr int PH_MAX_COMBOS = PLB_MAX_SRC * PLB_MAX_SCALES / 2 + 1;
+enum { PH_KIND_SRCPAIR = 0, PH_KIND_SCALEPAIR = 1, PH_KIND_SINGLE = 2 };
+struct PhotoCombo {
+    unsigned char kind, k0, s0, s1;   // sources k0 (and k0 + 1 for a source pair), scales s0 (and s1 for a scale pair)
+    unsigned char c0, c1, pad[2];     // which contributor (0 / 1) of scale s0 / s1 this combo is: with more than two sources
+                                      // two combos of a job feed the gradient of one scale
+};
+
+// How a scale of a job's pyramid is read and how its gradient leaves the main kernel.
+enum {
+    PH_SM_FULL = 0,        // full resolution: one disparity per pixel, gradient written in place
+    PH_SM_LOWFAST = 1,     // low resolution, integer factor 2/4/8: depth upsampled on the fly (streaming rows), the gradient
+                           // reduced over the rows in registers and left as [2][dh][W] partial rows for photo_lowres_merge_kernel
+    PH_SM_LOWSCRATCH = 2,  // any other ratio: per-pixel gradient into a full-resolution scratch plane + photo_upsample_T_kernel
+    PH_SM_LOWNOGRAD = 3    // low resolution, no gradient wanted
+};
+
+constexpr size_t PH_PAIRCONST_BYTES = 2048;   // >= sizeof(PairConst) (static_assert below)
 struct PhotoLayout {
     size_t tickets;   // int32 [n_pairs + 1]
     size_t records;   // float [grid][2][PH_REC_STRIDE]
@@ -57,7 +72,10 @@ struct PhotoLayout {
                       // finalize kernel reads ALL of them, and a 224-byte stride costs it 32 L1 wavefronts per load
     size_t ws_pose;   // float [n_pairs][MAX_SRC][6] (photo_min.cu)
     size_t ws_loss;   // double [n_pairs]
-    size_t gup;       // float [n_jobs][MAX_SCALES][B*H*W]  (only when a low scale carries a gradient)
+    size_t gup;       // float [n_jobs][MAX_SCALES][B*H*W]  (only when a scale is PH_SM_LOWSCRATCH)
+    size_t pairs;     // PairConst [n_pairs] (photo_pairs_kernel -> photo_l1_kernel)
+    size_t ylow;      // float: per PH_SM_LOWFAST (job, scale) [B][2][dh][W] y-reduced gradient rows (two partial slots)
+    size_t ylow_off[PLB_MAX_JOBS][PLB_MAX_SCALES];   // float offset of each (job, scale) from `ylow`
     size_t total;
 };
 
@@ -66,12 +84,18 @@ struct PhotoLaunch {
     plb_photo_args a;
     PhotoLayout L;
     int grid;                            // number of blocks
-    int warps_per_block;                 // photo_threads() / 32 of the launched variant
+    int warps_per_block;                 // PH_WARPS
     int n_warps;                         // grid * warps_per_block
     int strips;                          // ceil(W / 32)
-    int units_per_pair;                  // strips * H
     int n_pairs;                         // n_jobs * B
-    int unit_weight[PLB_MAX_JOBS];       // n_scales * (PH_W_PAIR * pairs + PH_W_ODD * odd source)
+    int n_combos[PLB_MAX_JOBS];
+    PhotoCombo combo[PLB_MAX_JOBS][PH_MAX_COMBOS];
+    unsigned char smode[PLB_MAX_JOBS][PLB_MAX_SCALES];   // PH_SM_*, | 4 when two combos of the job feed the scale's gradient
+    int units_per_pair[PLB_MAX_JOBS];    // strips * n_combos * H: units (rows of one combo of one strip) of one image of the job
+    int combo_w[PLB_MAX_JOBS][PH_MAX_COMBOS];       // weight of one row segment of each combo
+    int combo_align[PLB_MAX_JOBS][PH_MAX_COMBOS];   // cuts inside a column of the combo fall on multiples of this many rows:
+                                                    // 2 x the largest factor of its PH_SM_LOWFAST streams (1: anywhere)
+    int combo_cw[PLB_MAX_JOBS][PH_MAX_COMBOS + 1];  // prefix sums of combo_w: a (strip, all combos) super column weighs combo_cw[n] * H
     long long weight_start[PLB_MAX_JOBS + 1];  // cumulative weight at the start of each job
     int unit_start[PLB_MAX_JOBS + 1];    // cumulative unit index at the start of each job
     float w_e[PLB_MAX_JOBS];             // term_weight / (3*B*H*W)
@@ -81,11 +105,27 @@ struct PhotoLaunch {
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// PH_SM_* of scale s of job j (host).  The in-register path needs an integer power-of-two factor <= 8 in both
+// directions; the SSIM / min-reprojection kernel (photo_min.cu) always uses the scratch planes.
+static inline int photo_scale_mode(const plb_photo_args& a, int j, int s) {
+    const plb_photo_job& job = a.jobs[j];
+    if (job.dh[s] == a.H && job.dw[s] == a.W) return PH_SM_FULL;
+    if (!a.want_grad || job.g_disp[s] == nullptr) return PH_SM_LOWNOGRAD;
+    if (job.mode == PLB_PHOTO_MIN_REPROJ) return PH_SM_LOWSCRATCH;
+    if (job.dh[s] < 1 || job.dw[s] < 1 || a.H % job.dh[s] != 0 || a.W % job.dw[s] != 0) return PH_SM_LOWSCRATCH;
+    const int f = a.H / job.dh[s];
+    if (f != a.W / job.dw[s] || (f != 2 && f != 4 && f != 8)) return PH_SM_LOWSCRATCH;
+#ifdef PH_NO_LOWFAST
+    return PH_SM_LOWSCRATCH;
+#endif
+    return PH_SM_LOWFAST;
+}
+
+// a low scale whose gradient goes through the scratch planes + photo_upsample_T_kernel
 static inline bool photo_has_lowres_grad(const plb_photo_args& a) {
-    if (!a.want_grad) return false;
     for (int j = 0; j < a.n_jobs; ++j)
         for (int s = 0; s < a.jobs[j].n_scales; ++s)
-            if (a.jobs[j].g_disp[s] && (a.jobs[j].dh[s] != a.H || a.jobs[j].dw[s] != a.W)) return true;
+            if (photo_scale_mode(a, j, s) == PH_SM_LOWSCRATCH) return true;
     return false;
 }
 
@@ -94,7 +134,7 @@ static inline int photo_max_grid(const plb_photo_args& a) {
     const long long strips = (a.W + 31) / 32;
     const long long units = strips * a.H * (long long)a.B * a.n_jobs;
     (void)units;
-    long long g = 148LL * 8;                         // 148 SMs x at most 8 resident blocks
+    long long g = 160LL * 8 * PH_GRID_MULT;          // SMs x at most 8 resident blocks (B200: 148 SMs) x waves
     const long long pairs_bound = 1LL * a.n_jobs * a.B * PLB_MAX_SCALES * PLB_MAX_SRC + 2;
     if (g < pairs_bound) g = pairs_bound;
     return (int)g;
@@ -117,29 +157,48 @@ static inline PhotoLayout photo_layout(const plb_photo_args& a) {
     L.gup = off;
     if (photo_has_lowres_grad(a))
         off = align_up(off + sizeof(float) * (size_t)a.n_jobs * PLB_MAX_SCALES * a.B * a.H * a.W, 256);
+    L.pairs = off; off = align_up(off + PH_PAIRCONST_BYTES * n_pairs, 256);
+    L.ylow = off;
+    size_t yl = 0;
+    for (int j = 0; j < PLB_MAX_JOBS; ++j)
+        for (int s = 0; s < PLB_MAX_SCALES; ++s) {
+            L.ylow_off[j][s] = yl;
+            if (j < a.n_jobs && s < a.jobs[j].n_scales && photo_scale_mode(a, j, s) == PH_SM_LOWFAST) {
+                const int n_contrib = a.jobs[j].n_src / 2 + (a.jobs[j].n_src & 1);   // combos that feed one scale (<= 2)
+                yl += align_up((size_t)n_contrib * a.B * 2 * a.jobs[j].dh[s] * a.W, 64);
+            }
+        }
+    off = align_up(off + sizeof(float) * yl, 256);
     L.total = off;
     return L;
 }
 
 // shared-memory context of one (job, image) pair, built once per block: K^-1, P per source and
 // every base pointer already offset to image b, so the unit loop does no 64-bit address maths.
+constexpr int PH_NT2 = PLB_MAX_SRC / 2 + PLB_MAX_SRC;   // packed constant tables: source pairs, then every source twice
 struct __align__(16) PairConst {
     float4 P[PLB_MAX_SRC][3];        // K . [R|t] (photo_min.cu)
     float4 Q[PLB_MAX_SRC][3];        // [P[:, :3] . K^-1 | P[:, 3]] (photo.cu: cam = D * Q.(x, y, 1) + p3)
-    float4 Q2[PLB_MAX_SRC / 2][3][2]; // the same for source pairs, interleaved (even, odd) for packed fp32 maths
+    // the same for the two halves of a packed combo, per cam row r: [0] = (qx_lo, qx_hi, qz_lo, qz_hi),
+    // [1] = (qy_lo, qy_hi, p3_lo, p3_hi).  Table g < MAX_SRC/2: sources (2g, 2g+1); table MAX_SRC/2 + k: source k twice
+    float4 T2[PH_NT2][3][2];
     float kinv[12];
     const float* tgt;
     float* g_tgt;
     const float* src[PLB_MAX_SRC];
     float* g_src[PLB_MAX_SRC];
     const float* disp[PLB_MAX_SCALES];
-    float* g_disp[PLB_MAX_SCALES];   // full-res scales: the user's buffer; low-res scales: the gup scratch plane
+    float* g_disp[PLB_MAX_SCALES];   // FULL: the user's buffer; LOWSCRATCH: the gup scratch plane; LOWFAST: the [2][dh][W] partial rows
     int dh[PLB_MAX_SCALES], dw[PLB_MAX_SCALES];
     float sx[PLB_MAX_SCALES], sy[PLB_MAX_SCALES];
+    int smode[PLB_MAX_SCALES];
+    int fac[PLB_MAX_SCALES];         // integer power-of-two upsampling factor of the scale (both directions), else 0
     int n_src, n_scales, lowres, pad;
     float w_e, pad2[3];
 };
 
+
+static_assert(sizeof(PairConst) <= PH_PAIRCONST_BYTES && sizeof(PairConst) % 16 == 0, "pair table entry");
 
 // tile of the SSIM-mode kernel (photo_min.cu); needed here to size the record area
 constexpr int PM_TW = 32, PM_TH = 8;

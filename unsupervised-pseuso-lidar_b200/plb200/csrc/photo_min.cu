@@ -530,12 +530,13 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
 
 template <bool GRAD, int NSMAX, bool HEAD>
 static int pm_launch_variant(const PminLaunch& p, dim3 grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[PLB_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {                                    // per device: a process may drive several GPUs
         const cudaError_t e = cudaFuncSetAttribute(photo_min_kernel<GRAD, NSMAX, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)sizeof(PminSmem));
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     photo_min_kernel<GRAD, NSMAX, HEAD><<<grid, PM_THREADS, sizeof(PminSmem), st>>>(p);
     return PLB_OK;
