@@ -300,6 +300,33 @@ typedef struct plb_velo_args {
 size_t plb_velo_workspace_bytes(const plb_velo_args* args);
 int plb_velo_project(const plb_velo_args* args, void* stream);
 
+/*
+ * Loader-side frame preparation.  Replaces, for a batch of decoded uint8 frames,
+ * the transform chain `ToTensor -> ToPILImage -> Resize((H, W)) -> ToTensor -> Normalize` (trainer.py:97-103) that
+ * KittiDataset.load_img (dataloaders.py:32-49) applies to `np.asarray(Image.open(path), float32) / 255.0`, and the
+ * intrinsics scaling of dataloaders.py:95-98.  Bit-exact: the float32 round trip in front of ToPILImage truncates,
+ * Resize is Pillow's antialiased bilinear ImagingResample in 8-bit fixed point (coefficient tables in fp64, horizontal
+ * pass then vertical pass, each rounded to uint8), ToTensor / Normalize are IEEE fp32 operations.
+ */
+typedef struct plb_prep_args {
+    int32_t B;                 /* frames                                                            */
+    int32_t in_h, in_w;        /* size of the decoded frames                                        */
+    int32_t H, W;              /* network resolution (config: image_height, image_width)            */
+    int32_t reserved;
+    const uint8_t* frames;     /* [B, in_h, in_w, 3] uint8 RGB, HWC as PIL decodes them             */
+    float mean[3];             /* 0.485, 0.456, 0.406 in the reference                              */
+    float stdev[3];            /* 0.229, 0.224, 0.225                                               */
+    float* out_planar;         /* out [B,3,H,W] fp32 (the layout the networks and the loss read) or NULL */
+    float* out_nhwc4;          /* out [B,H,W,4] fp32 (r,g,b,0) or NULL (at least one of the two)     */
+    const double* K_in;        /* [B,3,3] f64 intrinsics at the decoded size, or NULL               */
+    double* K_out;             /* out [B,3,3] f64: row 0 * W / in_w, row 1 * H / in_h (NULL iff K_in is NULL) */
+    void* workspace;           /* plb_prep_workspace_bytes() bytes (no initialisation needed)       */
+    size_t workspace_bytes;
+} plb_prep_args;
+
+size_t plb_prep_workspace_bytes(const plb_prep_args* args);
+int plb_prep_frames(const plb_prep_args* args, void* stream);
+
 /* Library identification: "plb200 <version> sm_100a". */
 const char* plb_version(void);
 /* Number of kernel launches issued by this library since load (all entry points). */

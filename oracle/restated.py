@@ -414,3 +414,86 @@ def disp_head(x, alpha=10.0, beta=0.01):
     `predict_disp` ends in `nn.Sigmoid()` (`:24-28`) and `alpha = 10`, `beta = 0.01` (`:53-57`).  `x` is the
     convolution output in front of the sigmoid."""
     return alpha * torch.sigmoid(x) + beta
+
+
+# --------------------------------------------------------------------------
+# dataloaders.py:32-49 + trainer.py:97-103  (SURVEY.md section 8(f) rank 4: the loader's transform chain)
+# --------------------------------------------------------------------------
+
+def _pil_bilinear_coeffs(in_size, out_size):
+    """Pillow's `precompute_coeffs` + `normalize_coeffs_8bpc` (src/libImaging/Resample.c; Pillow 12.2 installed here,
+    unpinned by the reference) for the bilinear filter: per output sample the first input sample, the tap count and
+    the taps in 22-bit fixed point.  Double arithmetic in Pillow's operation order; the support of the triangle is
+    scaled by the reduction factor (antialiasing)."""
+    scale = float(np.float32(in_size) - np.float32(0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int64)
+    kk = np.zeros((out_size, ksize), np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = np.zeros(ksize)
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            a = -a if a < 0 else a
+            k[x] = 1.0 - a if a < 1.0 else 0.0
+            ww += k[x]
+        if ww != 0.0:
+            k[:xmax] /= ww
+        bounds[xx] = (xmin, xmax)
+        for x in range(ksize):
+            kk[xx, x] = int(-0.5 + k[x] * (1 << 22)) if k[x] < 0 else int(0.5 + k[x] * (1 << 22))
+    return bounds, kk
+
+
+def pil_resize_bilinear(img, H, W):
+    """`Image.resize((W, H), BILINEAR)` on an RGB uint8 array [h, w, 3] - what `transforms.Resize((H, W))` runs on a
+    PIL image (trainer.py:100): horizontal pass, then vertical pass, each only when that size changes, each rounded
+    to uint8 through `((1 << 21) + sum) >> 22` and clipped (`ImagingResampleHorizontal_8bpc` / `Vertical_8bpc`)."""
+    h0, w0, _ = img.shape
+    out = img.astype(np.int64)
+    if W != w0:
+        b, kk = _pil_bilinear_coeffs(w0, W)
+        tmp = np.zeros((h0, W, 3), np.int64)
+        for xx in range(W):
+            xmin, n = b[xx]
+            acc = (1 << 21) + (out[:, xmin:xmin + n, :] * kk[xx, :n][None, :, None]).sum(1)
+            tmp[:, xx, :] = np.clip(acc >> 22, 0, 255)
+        out = tmp
+    if H != h0:
+        b, kk = _pil_bilinear_coeffs(h0, H)
+        tmp = np.zeros((H, out.shape[1], 3), np.int64)
+        for yy in range(H):
+            ymin, n = b[yy]
+            acc = (1 << 21) + (out[ymin:ymin + n] * kk[yy, :n][:, None, None]).sum(0)
+            tmp[yy] = np.clip(acc >> 22, 0, 255)
+        out = tmp
+    return out.astype(np.uint8)
+
+
+def load_img_chain(frame_u8, H, W, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """`KittiDataset.load_img` (dataloaders.py:32-49) with the transform list of trainer.py:97-103 on a decoded
+    uint8 RGB frame [h, w, 3] -> normalised float32 [3, H, W]:
+      `np.asarray(img, float32) / 255.0`  (dataloaders.py:33-38)
+      ToTensor (float input: transpose only) -> ToPILImage (`mul(255).byte()`: the float32 round trip TRUNCATES)
+      -> Resize((H, W)) on the PIL image -> ToTensor (`/ 255`) -> Normalize (`sub_(mean).div_(std)`)."""
+    f = frame_u8.astype(np.float32) / np.float32(255.0)
+    u8 = (f * np.float32(255.0)).astype(np.uint8)                      # mul(255).byte(): truncation toward zero
+    r = pil_resize_bilinear(u8, H, W)
+    t = np.transpose(r, (2, 0, 1)).astype(np.float32) / np.float32(255.0)
+    m = np.asarray(mean, dtype=np.float32).reshape(3, 1, 1)
+    s = np.asarray(std, dtype=np.float32).reshape(3, 1, 1)
+    return (t - m) / s
+
+
+def scale_intrinsics(K, in_h, in_w, H, W):
+    """dataloaders.py:95-98: `intrinsics[0] *= W / og_w; intrinsics[1] *= H / og_h` (float64)."""
+    K = np.array(K, dtype=np.float64, copy=True)
+    K[..., 0, :] *= W / in_w
+    K[..., 1, :] *= H / in_h
+    return K

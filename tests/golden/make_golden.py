@@ -231,7 +231,74 @@ def head_case(name):
     print(name, [tuple(o.shape) for o in out])
 
 
+def make_frame(h, w, seed):
+    """Synthetic decoded camera frame, uint8 HWC: smooth colour field + texture + noise, every value of 0..255 used."""
+    rng = np.random.default_rng(seed)
+    v = np.arange(h, dtype=np.float64)[:, None, None]
+    u = np.arange(w, dtype=np.float64)[None, :, None]
+    ph = np.array([0.0, 2.1, 4.2])[None, None, :]
+    x = 127.5 + 100.0 * np.sin(2 * np.pi * u / 97.0 + ph) * np.cos(2 * np.pi * v / 61.0) + 40.0 * rng.standard_normal((h, w, 3))
+    x[: h // 8] = rng.integers(0, 256, (h // 8, w, 3))          # a band of pure noise: worst case for the filter
+    return np.clip(np.rint(x), 0, 255).astype(np.uint8)
+
+
+def prep_case(name):
+    """`KittiDataset.load_img` (dataloaders.py:32-49, the UNMODIFIED method) with the transform list of
+    `trainer.py:97-103` on PNG files written here, and the intrinsics scaling of `dataloaders.py:95-98`."""
+    from PIL import Image
+    from torchvision import transforms
+    for m in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, __import__("types").ModuleType(m))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    for k in [k for k in sys.modules if k == "geometry" or k.startswith("geometry.")]:
+        del sys.modules[k]                                     # the reference's own geometry package for its star-imports
+    sys.path.insert(0, reference_shim.REFERENCE_ROOT)
+    import dataloaders as ref_dl
+    assert ref_dl.__file__.startswith(reference_shim.REFERENCE_ROOT)
+
+    def chain(img_height, img_width):
+        # trainer.py:97-103, verbatim structure
+        return [transforms.ToTensor(), transforms.ToPILImage(), transforms.Resize((img_height, img_width)),
+                transforms.ToTensor(), transforms.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))]
+
+    class Self:                                                # what load_img reads from the dataset object
+        pass
+    out = {}
+    cases = {"down": (94, 311, 48, 160), "same": (48, 160, 48, 160), "up": (30, 50, 48, 80), "odd": (53, 97, 20, 33)}
+    with tempfile.TemporaryDirectory() as d:
+        for tag, (h0, w0, H, W) in cases.items():
+            frame = make_frame(h0, w0, seed=hash(tag) % 1000 if False else {"down": 1, "same": 2, "up": 3, "odd": 4}[tag])
+            path = os.path.join(d, tag + ".png")
+            Image.fromarray(frame).save(path)
+            me = Self()
+            me.transforms = chain(H, W)
+            img, oh, ow = ref_dl.KittiDataset.load_img(me, path)
+            assert (oh, ow) == (h0, w0)
+            out[tag + "_frame"], out[tag + "_out"] = frame, _np(img)
+            out[tag + "_size"] = np.array([H, W])
+            K = synth.kitti_intrinsics(1, h0, w0)[0].numpy().copy()
+            out[tag + "_K_in"] = K.copy()
+            K[0] *= W / ow                                     # dataloaders.py:95-97
+            K[1] *= H / oh
+            out[tag + "_K_out"] = K
+        # full KITTI size -> network resolution: checksum + two rows of every channel
+        frame = make_frame(375, 1242, seed=5)
+        path = os.path.join(d, "full.png")
+        Image.fromarray(frame).save(path)
+        me = Self()
+        me.transforms = chain(192, 640)
+        img = _np(ref_dl.KittiDataset.load_img(me, path)[0])
+        out["full_seed"] = np.array(5)
+        out["full_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(img).tobytes()).digest(), dtype=np.uint8)
+        out["full_rows"] = img[:, [0, 95, 191], :]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("_out")})
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "prep":
+        prep_case("prep_frames")
+        return
     torch.manual_seed(0)
     torch.set_num_threads(1)  # fixed reduction order for the committed vectors
     ref = reference_shim.load(patch_batch=False)
@@ -243,6 +310,7 @@ def main():
     cloud_case(ref, "cloud_kitti")
     velo_case(ref, "velo_kitti")
     head_case("head_dispnet")
+    prep_case("prep_frames")
     ref = reference_shim.load(patch_batch=True)
     live_case(ref, "live_b2_s2_32x48_patched", 2, 32, 48, 2, seed=14, regime="trained")
     live_case(ref, "live_b3_s1_24x40_patched", 3, 24, 40, 1, seed=15, regime="trained")

@@ -152,3 +152,14 @@ def test_live_reference_if_present():
                                            "unsupervised-pseuso-lidar_b200"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
+def test_loader_chain_oracle_matches_reference_bit_for_bit():
+    """`oracle.load_img_chain` / `scale_intrinsics` against the unmodified `KittiDataset.load_img` + trainer transform
+    list (tests/golden/prep_frames.npz): down- and up-sampling, identity size, odd sizes.  Bit-exact."""
+    g = load_golden("prep_frames")
+    for tag in ("down", "same", "up", "odd"):
+        H, W = (int(v) for v in g[tag + "_size"])
+        frame = g[tag + "_frame"]
+        assert np.array_equal(O.load_img_chain(frame, H, W), g[tag + "_out"]), tag
+        assert np.array_equal(O.scale_intrinsics(g[tag + "_K_in"], frame.shape[0], frame.shape[1], H, W), g[tag + "_K_out"])

@@ -181,6 +181,18 @@ class VeloArgs(C.Structure):
     ]
 
 
+class PrepArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("reserved", C.c_int32),
+        ("frames", _fp),
+        ("mean", C.c_float * 3), ("stdev", C.c_float * 3),
+        ("out_planar", _fp), ("out_nhwc4", _fp),
+        ("K_in", _fp), ("K_out", _fp),
+        ("workspace", _fp), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # every symbol include/plb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "plb_photo_workspace_bytes": (C.c_size_t, [C.POINTER(PhotoArgs)]),
@@ -205,6 +217,8 @@ SYMBOLS = {
     "plb_cloud_project": (C.c_int, [C.POINTER(CloudArgs), C.c_void_p]),
     "plb_velo_workspace_bytes": (C.c_size_t, [C.POINTER(VeloArgs)]),
     "plb_velo_project": (C.c_int, [C.POINTER(VeloArgs), C.c_void_p]),
+    "plb_prep_workspace_bytes": (C.c_size_t, [C.POINTER(PrepArgs)]),
+    "plb_prep_frames": (C.c_int, [C.POINTER(PrepArgs), C.c_void_p]),
     "plb_version": (C.c_char_p, []),
     "plb_launch_count": (C.c_uint64, []),
 }

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libplb200.so")
-SOURCES = ["api.cu", "photo.cu", "photo_min.cu", "ssim.cu", "smooth.cu", "edge.cu", "warp.cu", "cloud.cu", "velo.cu"]
+SOURCES = ["api.cu", "photo.cu", "photo_min.cu", "ssim.cu", "smooth.cu", "edge.cu", "warp.cu", "cloud.cu", "velo.cu", "prep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
               "-I", os.path.join(ROOT, "include")]

@@ -27,6 +27,8 @@ int cloud_launch(const plb_cloud_args*, cudaStream_t);
 size_t cloud_workspace_bytes(const plb_cloud_args*);
 int velo_launch(const plb_velo_args*, cudaStream_t);
 size_t velo_workspace_bytes(const plb_velo_args*);
+int prep_launch(const plb_prep_args*, cudaStream_t);
+size_t prep_workspace_bytes(const plb_prep_args*);
 }  // namespace plb
 
 extern "C" {
@@ -80,7 +82,10 @@ int plb_cloud_project(const plb_cloud_args* a, void* stream) { return plb::cloud
 size_t plb_velo_workspace_bytes(const plb_velo_args* a) { return a ? plb::velo_workspace_bytes(a) : 0; }
 int plb_velo_project(const plb_velo_args* a, void* stream) { return plb::velo_launch(a, (cudaStream_t)stream); }
 
-const char* plb_version(void) { return "plb200 0.1 sm_100a"; }
+size_t plb_prep_workspace_bytes(const plb_prep_args* a) { return a ? plb::prep_workspace_bytes(a) : 0; }
+int plb_prep_frames(const plb_prep_args* a, void* stream) { return plb::prep_launch(a, (cudaStream_t)stream); }
+
+const char* plb_version(void) { return "plb200 0.2 sm_100a"; }
 uint64_t plb_launch_count(void) { return plb::g_launches; }
 
 }  // extern "C"

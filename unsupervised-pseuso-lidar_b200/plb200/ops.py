@@ -607,3 +607,47 @@ def smooth_only(depth_maps, input_is_depth=True, fused_backward=True):
     # with do_photo=False the first tensor only supplies the batch size and device
     _, smooth = FusedLossFn.apply(cfg, d0.detach(), poses, K, *depth_maps)
     return smooth
+
+
+# ---------------------------------------------------------------------------
+# loader-side frame preparation
+# ---------------------------------------------------------------------------
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def prep_frames(frames, height, width, K=None, mean=IMAGENET_MEAN, std=IMAGENET_STD, want_planar=True, want_nhwc4=False,
+                out=None):
+    """frames [B,h,w,3] uint8 CUDA (decoded RGB, HWC) -> dict(planar [B,3,H,W] f32, nhwc4 [B,H,W,4] f32, K [B,3,3] f64):
+    the reference loader's transform chain and intrinsics scaling (trainer.py:97-103, dataloaders.py:32-49,95-98),
+    bit-exact.  `out`: an optional preallocated [B,3,H,W] float32 tensor for the planar result.  No sync."""
+    _need_cuda(frames, K)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+        raise ValueError("frames must be uint8 [B, h, w, 3]")
+    frames = frames.contiguous()
+    B, h, w, _ = frames.shape
+    dev = frames.device
+    a = _lib.PrepArgs()
+    a.B, a.in_h, a.in_w, a.H, a.W = B, h, w, int(height), int(width)
+    a.frames = frames.data_ptr()
+    for c in range(3):
+        a.mean[c], a.stdev[c] = float(mean[c]), float(std[c])
+    res = {}
+    if want_planar:
+        if out is not None:
+            if out.shape != (B, 3, a.H, a.W) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous float32 [B,3,H,W] tensor")
+            res["planar"] = out
+        else:
+            res["planar"] = torch.empty(B, 3, a.H, a.W, dtype=torch.float32, device=dev)
+        a.out_planar = res["planar"].data_ptr()
+    if want_nhwc4:
+        res["nhwc4"] = torch.empty(B, a.H, a.W, 4, dtype=torch.float32, device=dev)
+        a.out_nhwc4 = res["nhwc4"].data_ptr()
+    if K is not None:
+        K = K.to(torch.float64).contiguous()
+        res["K"] = torch.empty_like(K)
+        a.K_in, a.K_out = K.data_ptr(), res["K"].data_ptr()
+    ws = _workspace("prep", lib.plb_prep_workspace_bytes(a), dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    check(lib.plb_prep_frames(a, _stream()), "plb_prep_frames")
+    return res
