@@ -24,6 +24,10 @@ for p in (ROOT, PKG):
 import torch  # noqa: E402
 
 METRIC = "photometric loss fwd+bwd Mpix/s at 192x640 x3 frames"
+# N > 1: the network-gradient all-reduce runs beside the loss; its CTAs need whole SMs, so the collective is capped at
+# NCCL_CTAS CTAs and the persistent grid of the loss is sized for the remaining SMs (B200: 148)
+NCCL_CTAS = int(os.environ.get("PLB_NCCL_CTAS", "16"))
+SM_COUNT_FOR_LOSS = 148 - NCCL_CTAS
 UNIT = "Mpix/s"
 
 # name -> (B per GPU, H, W, n_src, n_scales, loss variant)
@@ -300,11 +304,16 @@ def run_ours(args, cfg):
     rank, world, local = dist_env()
     if world > 1:
         import torch.distributed as dist
+        if not args.no_comm:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local if world > 1 else 0)
     torch.cuda.set_device(dev)
     criterion = Losses()
+    if world > 1 and not args.no_comm:
+        from plb200 import ops as _ops
+        _ops.set_sm_limit(SM_COUNT_FOR_LOSS)      # (before the step is captured: the launch geometry is part of the graph)
     n_sets = args.sets
     cpu_sets = make_sets(cfg, n_sets, 1234 + 1000 * rank, dev)
     gpu_sets = [synth.to_device(s, dev) for s in cpu_sets]
@@ -344,35 +353,89 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        device_step(i)
+    # ---- the exchange step of a data-parallel step (N > 1): all-reduce of the depth + pose
+    #      network gradients - the networks are out of scope, so the payload is a synthetic fp32 arena of the
+    #      reference configuration's size (DispResNet 14.8 M + PoseFc 1.64 M parameters = 66 MB,
+    #      configs/basic_config.yaml:3-10) - in 25 MB buckets on a side stream, the two loss scalars fused into the
+    #      last bucket.  It is launched at the start of a step and the step ends when both it and the loss have
+    #      finished: what is not hidden behind the loss kernels is exposed in ms_per_step. -------------------------
+    red = None
+    if world > 1 and not args.no_comm:
+        from plb200 import dist as pdist
+        n_grad = 14_800_000 + 1_640_000
+        arena = torch.zeros(n_grad + 2, dtype=torch.float32, device=dev)
+        red = pdist.GradBucketReducer(arena, bucket_mb=25.0)
+    last_loss = [torch.zeros((), device=dev), torch.zeros((), device=dev)]
+
+    def timed_loop(n, with_comm):
+        for i in range(n):
+            if with_comm and red is not None:
+                red.launch(losses=last_loss, B_local=cfg["B"], B_global=cfg["B"] * world)
+            o = device_step(i)
+            if use_graph:
+                o = outs[i % n_sets]
+            if with_comm and red is not None:
+                last_loss[0] = o[0]
+                last_loss[1] = o[0]
+                red.wait()
+
+    def timed(n, with_comm):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        timed_loop(n, with_comm)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    timed_loop(args.warmup, True)
     barrier()
+    comm = None
+    if red is not None:
+        ms_nocomm = timed(args.steps, False) / args.steps
+        barrier()
+        ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ec0.record()
+        for i in range(args.steps):
+            red.launch(losses=last_loss, B_local=cfg["B"], B_global=cfg["B"] * world)
+            red.wait()
+        ec1.record()
+        barrier()
+        comm = {"payload_bytes": int(arena.numel() * 4), "buckets": len(red.bounds), "bucket_mb": 25.0,
+                "ms_per_step_without_exchange": ms_nocomm, "allreduce_alone_ms": ec0.elapsed_time(ec1) / args.steps}
     sampler = ClockSampler(dev.index)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        device_step(i)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = timed(args.steps, True)
     clocks = sampler.stop()
+    if red is not None:
+        comm["loss_grid_sms"], comm["nccl_max_ctas"] = SM_COUNT_FOR_LOSS, NCCL_CTAS
+        _ops.set_sm_limit(0)                       # the kernel-alone and e2e measurements below have the GPU to themselves
 
     # ---- dominant kernel alone (photo_l1 fused fwd+grad), back-to-back launches -----
     kern_ms = time_photo_kernel(criterion, gpu_sets, cfg, dev, max(20, min(args.steps, 200)))
 
     # ---- e2e: host (pinned) inputs -> H2D -> public API fwd+bwd -> D2H loss ----------
     e2e = time_e2e(criterion, cpu_sets, cfg, dev, max(5, min(args.steps, 50)), barrier)
+    e2e_full = eager_step = None
+    if world == 1 and not args.no_cloud:
+        # the same with frames at KITTI's decoded size: the GPU does the resize as well (secondary number)
+        f = time_e2e(criterion, cpu_sets, cfg, dev, max(5, min(args.steps, 30)), barrier, frame_hw=(375, 1242))
+        e2e_full = {"value": px_per_step / 1e6 / (f["ms_per_step"] / 1e3), "unit": UNIT, "ms_per_step": f["ms_per_step"],
+                    "h2d_bytes_per_step": f["h2d"], "frames": f["frames"]}
+        ems, hms = time_eager(criterion, gpu_sets, cfg, dev, max(20, min(args.steps, 100)))
+        eager_step = {"value": px_per_step / 1e6 / (ems / 1e3), "unit": UNIT, "ms_per_step": ems, "host_ms_per_step": hms,
+                      "note": "same step issued eagerly through Losses.forward / backward (no CUDA graph), device-resident inputs"}
 
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms_total, e2e["ms_per_step"], kern_ms], device=dev, dtype=torch.float64)
+        c0 = comm["ms_per_step_without_exchange"] if comm else 0.0
+        c1 = comm["allreduce_alone_ms"] if comm else 0.0
+        t = torch.tensor([ms_total, e2e["ms_per_step"], kern_ms, c0, c1], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e["ms_per_step"], kern_ms = [float(x) for x in t]
-        # the path's only exchange: the two logged loss scalars
-        lt = (outs[0][0] if use_graph else torch.zeros((), device=dev)).clone().reshape(1)
-        dist.all_reduce(lt)
+        ms_total, e2e["ms_per_step"], kern_ms, c0, c1 = [float(x) for x in t]
+        if comm:
+            comm["ms_per_step_without_exchange"], comm["allreduce_alone_ms"] = c0, c1
+            comm["exposed_ms_per_step"] = max(0.0, ms_total / args.steps - c0)
     ms_step = ms_total / args.steps
     value = world * px_per_step / 1e6 / (ms_step / 1e3)
     e2e_value = world * px_per_step / 1e6 / (e2e["ms_per_step"] / 1e3)
@@ -427,12 +490,18 @@ def run_ours(args, cfg):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, cfg), "global_batch": cfg["B"] * world,
-                       "parallelism": "batch-sharded x%d, no data-path collective" % world,
+                       "parallelism": ("batch-sharded x%d, no data-path collective; per step: 66 MB network-gradient all-reduce in "
+                                       "25 MB buckets on a side stream (synthetic payload of the reference's DispResNet + PoseFc), "
+                                       "the two loss scalars fused into its last bucket" % world) if comm else
+                                      "batch-sharded x%d, no data-path collective" % world,
                        "l2": "inputs rotate over %d distinct sets (%.0f MB per GPU) > 126 MB L2" % (n_sets, pool_mb),
                        "step": "CUDA-graph replay of Losses.forward + backward" if use_graph else "eager public API"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "ms_per_step": e2e["ms_per_step"]},
+                    "ms_per_step": e2e["ms_per_step"], "frames": e2e["frames"], "frame_bytes_per_step": e2e["frame_bytes"],
+                    "fullres": e2e_full},
+            "exchange": comm,
+            "eager": eager_step,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "photo_l1_kernel<GRAD> (fused fwd+grad, all directions/scales)",
@@ -553,17 +622,32 @@ def time_velo(dev, B=32, N=123577, H=375, W=1242, iters=20):
             "mpoints_s": B * N / 1e6 / (ms / 1e3), "algorithmic_bytes": abytes, "achieved_gbs": abytes / (ms / 1e3) / 1e9}
 
 
-def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier):
-    """Public API with HOST buffers.  Every step copies that step's inputs from pinned host memory to the
-    device and reads the step's loss back to the host, all inside the timed region.  The copy of step i+1
-    runs on a copy stream while step i computes (two device buffer sets): the way a training loop feeds
-    the loss, and the PCIe transfer (59-69 MB per step) is what bounds this number."""
+def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier, frame_hw=None):
+    """Public API with HOST buffers, the way a training loop that owns its staging memory feeds the loss: every step
+    copies that step's inputs from pinned host memory to the device - the decoded frames as uint8 [B,h,w,3] (what the
+    loader holds before the reference's transform chain), the disparity pyramids, poses and intrinsics - runs the
+    loader chain on the device (`FramePrep`: resize + normalise + intrinsics scaling, bit-exact with
+    trainer.py:97-103 / dataloaders.py:32-49,95-98), then `Losses.forward` + backward, and reads the step's loss back
+    to the host; all inside the timed region.  The copy of step i+1 runs on a copy stream while step i computes (two
+    device buffer sets).  `frame_hw`: size of the decoded frames (default: the network resolution - a loader that
+    resizes the bytes on the host; (375, 1242) = the GPU also does the resize)."""
+    from plb200 import synth
+    from plb200.frameprep import FramePrep
+    H, W, B, n_src = cfg["H"], cfg["W"], cfg["B"], cfg["n_src"]
+    fh, fw = frame_hw or (H, W)
+    prep = FramePrep(H, W)
+
+    def host_set(k, s):
+        frames = synth.make_frames_u8(B, fh, fw, n_frames=1 + n_src, seed=900 + 31 * k)
+        K_dec = synth.kitti_intrinsics(B, fh, fw)          # intrinsics at the decoded size
+        return {"frames": torch.cat(frames, 0), "disparity": s["disparity"], "poses": s["poses"], "K": K_dec}
+
     def flat(g):
-        return [g["tgt"]] + list(g["ref_imgs"]) + [d for fr in g["disparity"] for d in fr] + [g["poses"], g["intrinsics"]]
+        return [g["frames"]] + [d for fr in g["disparity"] for d in fr] + [g["poses"], g["K"]]
 
     def arena_like(s, **kw):
         """One contiguous byte arena holding every input of a step (256-byte aligned views): the H2D copy of a
-        step is ONE transfer, the way a loader that owns its staging memory hands a batch over."""
+        step is ONE transfer."""
         ts = flat(s)
         offs, n = [], 0
         for t in ts:
@@ -571,23 +655,26 @@ def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier):
             n += (t.numel() * t.element_size() + 255) // 256 * 256
         arena = torch.empty(n, dtype=torch.uint8, **kw)
         views = [arena[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape) for o, t in zip(offs, ts)]
-        k = 1 + len(s["ref_imgs"])
-        g = {"tgt": views[0], "ref_imgs": views[1:k], "disparity": [], "poses": views[-2], "intrinsics": views[-1]}
+        g = {"frames": views[0], "disparity": [], "poses": views[-2], "K": views[-1]}
+        k = 1
         for fr in s["disparity"]:
             g["disparity"].append(views[k:k + len(fr)])
             k += len(fr)
         return arena, g
 
+    host_sets = [host_set(k, s) for k, s in enumerate(cpu_sets)]
     pinned = []
-    for s in cpu_sets:
+    for s in host_sets:
         arena, g = arena_like(s, pin_memory=True)
         for dst, src in zip(flat(g), flat(s)):
             dst.copy_(src)
         pinned.append((arena, g))
     h2d = pinned[0][0].numel()                            # bytes actually copied per step (views are 256-byte aligned)
+    frame_bytes = host_sets[0]["frames"].numel()
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
-    bufs = [arena_like(cpu_sets[0], device=dev), arena_like(cpu_sets[0], device=dev)]
+    bufs = [arena_like(host_sets[0], device=dev), arena_like(host_sets[0], device=dev)]
+    planar = [torch.empty((1 + n_src) * B, 3, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
     main_st = torch.cuda.current_stream()
     copy_st = torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event(), torch.cuda.Event()]     # H2D of the buffer finished
@@ -610,7 +697,12 @@ def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier):
                 upload(i + 1)                              # overlaps with the compute of step i
             k = i % 2
             main_st.wait_event(copied[k])
-            total, _, _ = step_fn(criterion, bufs[k][1], cfg)
+            g = bufs[k][1]
+            out = prep(g["frames"], g["K"], out=planar[k])
+            img = out["planar"]
+            step_in = {"tgt": img[:B], "ref_imgs": [img[(1 + j) * B:(2 + j) * B] for j in range(n_src)],
+                       "disparity": g["disparity"], "poses": g["poses"], "intrinsics": out["K"]}
+            total, _, _ = step_fn(criterion, step_in, cfg)
             consumed[k].record(main_st)
             host_loss.copy_(total, non_blocking=False)     # D2H of the step's result (synchronises)
             last = float(host_loss)
@@ -623,7 +715,25 @@ def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier):
     run(iters)
     e1.record()
     barrier()
-    return {"ms_per_step": e0.elapsed_time(e1) / iters, "h2d": h2d, "d2h": 4}
+    return {"ms_per_step": e0.elapsed_time(e1) / iters, "h2d": h2d, "d2h": 4, "frame_bytes": frame_bytes,
+            "frames": "uint8 [%d,%d,%d,3] decoded frames -> FramePrep on the device" % ((1 + n_src) * B, fh, fw)}
+
+
+def time_eager(criterion, gpu_sets, cfg, dev, iters):
+    """The same step issued eagerly through the public API (no CUDA graph): what a trainer that calls
+    `criterion.forward` + `backward` every iteration gets, host time included."""
+    for i in range(5):
+        step_fn(criterion, gpu_sets[i % len(gpu_sets)], cfg)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(iters):
+        step_fn(criterion, gpu_sets[i % len(gpu_sets)], cfg)
+    e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / iters
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, host_ms
 
 
 def main():
@@ -637,6 +747,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cloud", action="store_true", help="skip the secondary pseudo-LiDAR (config C4) timing")
+    ap.add_argument("--no-comm", action="store_true", help="N > 1: leave the network-gradient all-reduce out of the step")
     ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-CUDA incumbent (gpu_eager_baseline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -95,6 +95,9 @@ typedef struct plb_photo_args {
     int32_t want_grad;         /* 0: loss only (no_grad / eval)                                    */
     int32_t deterministic;     /* reserved (loss, pose and disparity gradients are always
                                   bitwise repeatable; image gradients use float atomics)            */
+    int32_t sm_limit;          /* 0: the persistent grid fills every SM; n > 0: it is sized for n SMs, leaving the rest
+                                  to kernels that run beside it (the CTAs of an NCCL all-reduce need whole SMs)      */
+    int32_t reserved2;
     const float* poses;        /* [B,n_pose,6]                                                     */
     const void* K;             /* [B,3,3] f64 or f32                                               */
     float* g_poses;            /* out (written) [B,n_pose,6]; NULL = not wanted                    */

@@ -40,6 +40,23 @@ def _worker(rank, world, port, out):
     ok &= torch.allclose(poses.grad, fp.grad[lo:hi], rtol=1e-4, atol=1e-9)
     ok &= torch.allclose(disp[0][0].grad, fd[0][0].grad[lo:hi], rtol=1e-4, atol=1e-10)
     ok &= tmax == float(world)
+    # the exchange step: bucketed gradient all-reduce (mean) with the loss scalars fused into the last bucket
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (1000, 37, 5000)]
+    for k, p_ in enumerate(params):
+        p_.grad = torch.full_like(p_, float(rank + 1) * (k + 1))
+    red = pdist.GradBucketReducer(params, bucket_mb=0.008)            # 2000 floats per bucket: four buckets
+    ok &= len(red.bounds) == 4 and red.bounds[-1][1] == red.n + 2
+    red.launch(losses=loss, B_local=hi - lo, B_global=B)
+    means = red.wait()
+    for k, p_ in enumerate(params):
+        ok &= bool(torch.allclose(p_.grad, torch.full_like(p_, 1.5 * (k + 1))))   # mean of (1, 2) * (k + 1)
+    for a, b in zip(means, fl):
+        ok &= abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)          # a flat arena, two trailing scalar slots
+    red2 = pdist.GradBucketReducer(flat, bucket_mb=25)
+    red2.launch()
+    red2.wait()
+    ok &= bool(torch.allclose(flat[:8], torch.arange(8, dtype=torch.float32) * 1.5)) and float(flat[8:].abs().sum()) == 0.0
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

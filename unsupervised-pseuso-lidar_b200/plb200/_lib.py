@@ -52,6 +52,8 @@ class PhotoArgs(C.Structure):
         ("head_alpha", C.c_float), ("head_beta", C.c_float),
         ("want_grad", C.c_int32),
         ("deterministic", C.c_int32),
+        ("sm_limit", C.c_int32),
+        ("reserved2", C.c_int32),
         ("poses", _fp),
         ("K", _fp),
         ("g_poses", _fp),

@@ -1711,7 +1711,9 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     const int bps = dispatch_variant(p, img_grad, head, low, 1, st);
     // more blocks than are resident: the hardware hands a waiting block to whichever SM retires one first, which evens
     // out the finishing times of the SMs (blocks of equal work do not take equal time)
-    long long grid = (long long)sm_count() * bps * PH_GRID_MULT;
+    int sms = sm_count();
+    if (a->sm_limit > 0 && a->sm_limit < sms) sms = a->sm_limit;     // leave SMs to kernels running beside this one
+    long long grid = (long long)sms * bps * PH_GRID_MULT;
     // a block's weight range must not exceed the lightest pair, so that it touches at most two pairs
     const long long need = (wsum + pair_w_min - 1) / pair_w_min + 1;
     if (grid > usum) grid = usum;                  // tiny problems: no more blocks than units ...

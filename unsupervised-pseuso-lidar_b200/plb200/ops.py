@@ -50,6 +50,17 @@ def _workspace(tag, nbytes, device):
     return buf
 
 
+_sm_limit = 0
+
+
+def set_sm_limit(n):
+    """Size the persistent grid of the fused loss for `n` SMs (0 = all of them).  A data-parallel step that runs an
+    NCCL all-reduce beside the loss leaves the collective's CTAs their SMs this way: they need whole SMs, and a
+    persistent grid that fills the GPU makes them wait for its blocks to retire."""
+    global _sm_limit
+    _sm_limit = int(n)
+
+
 def _need_cuda(*tensors):
     """Every tensor must live on the CURRENT CUDA device: the kernels are launched on that device's stream, and a
     launch with another device's pointers would fault (or, with peer access, silently run on the wrong GPU)."""
@@ -123,6 +134,7 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
         if cfg.disp_head:
             a.head_alpha, a.head_beta = cfg.disp_head
         a.want_grad = int(want_grad)
+        a.sm_limit = _sm_limit
         a.poses, a.K = poses.data_ptr(), K.data_ptr()
         a.g_poses = _ptr(g_poses) if want_grad else 0
         a.loss = out.data_ptr()

@@ -101,6 +101,23 @@ def make_photo_inputs(B, H, W, n_src=2, n_scales=1, seed=1234, regime="trained",
     return out
 
 
+def make_frames_u8(B, H, W, n_frames=3, seed=1234, noise=0.1):
+    """Decoded camera frames as the loader sees them: n_frames x [B,H,W,3] uint8 RGB (target, then sources) - the same
+    smooth colour field + noise as `_field`, quantised to bytes, sources shifted against the target."""
+    gen = torch.Generator().manual_seed(seed)
+    shifts = [(0, 0), (-3, -1), (3, 1), (-6, -2), (6, 2)]
+    frames = []
+    for k in range(n_frames):
+        sh = shifts[k % 5]
+        v = torch.arange(H, dtype=torch.float32).view(1, H, 1, 1) + sh[1]
+        u = torch.arange(W, dtype=torch.float32).view(1, 1, W, 1) + sh[0]
+        phase = torch.tensor([0.0, 2.1, 4.2]).view(1, 1, 1, 3)
+        smooth = 0.5 + 0.25 * torch.sin(2 * math.pi * u / 97.0 + phase) * torch.cos(2 * math.pi * v / 61.0)
+        x = (smooth + noise * torch.randn(B, H, W, 3, generator=gen)).clamp_(0.0, 1.0)
+        frames.append((x * 255.0).round().to(torch.uint8).contiguous())
+    return frames
+
+
 def to_device(x, device):
     if isinstance(x, torch.Tensor):
         return x.to(device)
