@@ -93,8 +93,12 @@ typedef struct plb_photo_args {
     float disp_a, disp_b;      /* 10, 0.01 in the reference                                        */
     float head_alpha, head_beta; /* 10, 0.01 in the reference's DispNet (PLB_INPUT_LOGIT only)      */
     int32_t want_grad;         /* 0: loss only (no_grad / eval)                                    */
-    int32_t deterministic;     /* reserved (loss, pose and disparity gradients are always
-                                  bitwise repeatable; image gradients use float atomics)            */
+    int32_t deterministic;     /* loss, pose and disparity gradients are always bitwise repeatable.  The image gradients
+                                  (g_src / g_tgt: the scatter that replaces grid_sampler_2d_backward behind
+                                  geometry/pose_geometry.py:227) use float atomics when 0; when 1 every contribution is
+                                  rounded once to a 2^-30 fixed-point fraction of the largest per-pixel weight and summed
+                                  with 64-bit integer atomics (order independent => bitwise repeatable), then converted;
+                                  costs 8 B of workspace per image-gradient element                  */
     int32_t sm_limit;          /* 0: the persistent grid fills every SM; n > 0: it is sized for n SMs, leaving the rest
                                   to kernels that run beside it (the CTAs of an NCCL all-reduce need whole SMs)      */
     int32_t reserved2;

@@ -20,14 +20,15 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _run_ours(tgt, refs, disparity, poses, K, fused_backward=True, image_grads=False, upstream=(1.0, 1.0)):
+def _run_ours(tgt, refs, disparity, poses, K, fused_backward=True, image_grads=False, upstream=(1.0, 1.0),
+              deterministic=None):
     from losses import Losses
     dev = _dev()
     tgt = tgt.to(dev).requires_grad_(image_grads)
     refs = [r.to(dev).requires_grad_(image_grads) for r in refs]
     disp = [[d.to(dev).requires_grad_(True) for d in fr] for fr in disparity]
     p = poses.to(dev).requires_grad_(True)
-    loss = Losses(fused_backward=fused_backward).forward(tgt, refs, disp, p, K.to(dev), None)
+    loss = Losses(fused_backward=fused_backward, deterministic=deterministic).forward(tgt, refs, disp, p, K.to(dev), None)
     (upstream[0] * loss[0] + upstream[1] * loss[1]).backward()
     return loss, disp, p, tgt, refs
 
@@ -71,11 +72,13 @@ def test_golden_loss_and_grads(name, fused):
             _check_grad(t.grad.cpu(), g["g_disp_f%d_s%d" % (f, s)], xd[f][s], ("disp", f, s))
 
 
+@pytest.mark.parametrize("det", [False, True])
 @pytest.mark.parametrize("name", ["live_b4_s1_32x48", "live_b4_s4_32x64"])
-def test_golden_image_grads(name):
+def test_golden_image_grads(name, det):
+    """det: the image gradients accumulated in order-independent 2^-30 fixed point (plb_photo_args.deterministic)."""
     g = load_golden(name)
     tgt, refs, disparity, poses, K = golden_inputs(g)
-    loss, disp, p, t, r = _run_ours(tgt, refs, disparity, poses, K, image_grads=True)
+    loss, disp, p, t, r = _run_ours(tgt, refs, disparity, poses, K, image_grads=True, deterministic=det)
     xp, _, xt, xr = _golden_fp64(g)
     _check_grad(t.grad.cpu(), g["g_tgt"], xt, "tgt")
     for i in range(2):
@@ -170,6 +173,30 @@ def test_bitwise_repeatable():
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
         for a, b in zip(o[3], outs[0][3]):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,H,W,S", [(3, 96, 320, 3), (64, 192, 640, 4)])
+def test_bitwise_repeatable_image_grads(B, H, W, S):
+    """Deterministic mode: EVERY output - the image gradients too (the scatter that replaces grid_sampler_2d_backward,
+    geometry/pose_geometry.py:227) - is bitwise repeatable, up to the C5 shape (B=64, 192x640, 4 scales); with a
+    non-unit upstream; and equal to the float-atomics mode within the gradient tolerance."""
+    from plb200 import synth
+    inp = synth.make_photo_inputs(B, H, W, n_src=2, n_scales=S, seed=9)
+    outs = []
+    for _ in range(3):
+        loss, disp, p, t, r = _run_ours(inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"],
+                                        image_grads=True, deterministic=True, upstream=(0.75, 1.0))
+        outs.append([loss[0].clone(), loss[1].clone(), p.grad.clone(), t.grad.clone()] + [x.grad.clone() for x in r] +
+                    [x.grad.clone() for fr in disp for x in fr])
+        del loss, disp, p, t, r
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert torch.equal(a, b)
+    _, _, _, t, r = _run_ours(inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"],
+                              image_grads=True, deterministic=False, upstream=(0.75, 1.0))
+    errs = [rel_err(outs[0][3], t.grad)] + [rel_err(outs[0][4 + i], r[i].grad) for i in range(2)]
+    print("deterministic vs float-atomic image gradients, rel err:", ["%.2e" % e for e in errs])
+    assert max(errs) < 1e-5
 
 
 def test_no_grad_forward_only():

@@ -32,7 +32,7 @@ class Losses:
     """`losses.py:56-271`.  Constructor takes no arguments in the reference
     (trainer.py:79); the keyword options only select implementation variants."""
 
-    def __init__(self, rotation_mode="axisangle", fused_backward=True, disp_head=None):
+    def __init__(self, rotation_mode="axisangle", fused_backward=True, disp_head=None, deterministic=None):
         self.SSIM = SSIM()
         self.clip_loss = 0.5
         self.rotation_mode = rotation_mode
@@ -41,6 +41,9 @@ class Losses:
         # head `alpha * sigmoid(x) + beta` (models/depth/disp_net.py:121-139: alpha=10, beta=0.01) inside the
         # kernels, returning gradients with respect to x
         self.disp_head = disp_head
+        # deterministic=True: image gradients (when a frame requires grad) are accumulated in order-independent
+        # fixed point, so EVERY output is bitwise repeatable; None follows torch.use_deterministic_algorithms()
+        self.deterministic = deterministic
 
     # ---- live path -------------------------------------------------------
     def forward(self, tgt_img, ref_imgs, disparity, poses, intrinsics, gt=None):
@@ -48,7 +51,7 @@ class Losses:
         pyr = [list(frame) if isinstance(frame, (list, tuple)) else [frame] for frame in disparity]
         mam, smooth = ops.fused_losses(tgt_img, list(ref_imgs), pyr, poses, intrinsics, input_is_depth=False,
                                        rotation_mode=self.rotation_mode, fused_backward=self.fused_backward,
-                                       disp_head=self.disp_head)
+                                       disp_head=self.disp_head, deterministic=self.deterministic)
         return [mam, smooth]
 
     __call__ = forward
@@ -60,7 +63,8 @@ class Losses:
             raise NotImplementedError("mode %r is dead code in the reference (undefined self.L2, losses.py:230-235)" % mode)
         pyr = [list(frame) if isinstance(frame, (list, tuple)) else [frame] for frame in depths]
         mam, _ = ops.fused_losses(tgt, list(refs), pyr, poses, intrinsics, input_is_depth=True, do_smooth=False,
-                                  rotation_mode=self.rotation_mode, fused_backward=self.fused_backward)
+                                  rotation_mode=self.rotation_mode, fused_backward=self.fused_backward,
+                                  deterministic=self.deterministic)
         return mam
 
     def smooth_loss(self, pred_map):
@@ -92,5 +96,6 @@ class Losses:
         flags = (_lib.PHOTO_NO_SSIM if no_ssim else 0) | (0 if automask else _lib.PHOTO_NO_AUTOMASK)
         mam, _ = ops.fused_losses(tgt_img, list(ref_imgs), pyr, poses, intrinsics, input_is_depth=True,
                                   do_smooth=False, rotation_mode=self.rotation_mode,
-                                  fused_backward=self.fused_backward, mode=_lib.PHOTO_MIN_REPROJ, flags=flags)
+                                  fused_backward=self.fused_backward, mode=_lib.PHOTO_MIN_REPROJ, flags=flags,
+                                  deterministic=self.deterministic)
         return mam

@@ -279,7 +279,10 @@ __device__ __forceinline__ void group_blend(const PairConst& pc, ComboRef cr, fl
         acc[3] = v_fma(hx, yv, acc[3]); acc[4] = v_fma(hy, yv, acc[4]); acc[5] = v_fma(hz, yv, acc[5]);
         acc[6] = v_add(acc[6], gcx); acc[7] = v_add(acc[7], gcy); acc[8] = v_add(acc[8], gcz);
         if (IMG_GRAD) {
-            const float m = valid ? w_e : 0.0f;
+            // deterministic mode: contributions in units of the call's largest weight (pc.det_rho = this job's share),
+            // rounded once to 2^-30 and added as 64-bit integers (photo_common.cuh)
+            const bool det = pc.det_rho > 0.0f;
+            const float m = valid ? (det ? pc.det_rho * PH_DET_ONE : w_e) : 0.0f;
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
 #pragma unroll
@@ -293,11 +296,19 @@ __device__ __forceinline__ void group_blend(const PairConst& pc, ComboRef cr, fl
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float ec = m * e[k][c];
-                        float* q = gbase + (og + c * plane);
-                        if (msk[k] & 1u) atomicAdd(q, wnw * ec);
-                        if (msk[k] & 2u) atomicAdd(q + 1, wne * ec);
-                        if (msk[k] & 4u) atomicAdd(q + W, wsw * ec);
-                        if (msk[k] & 8u) atomicAdd(q + W + 1, wse * ec);
+                        if (det) {
+                            unsigned long long* q = reinterpret_cast<unsigned long long*>(gbase) + (og + c * plane);
+                            if (msk[k] & 1u) atomicAdd(q, (unsigned long long)__float2ll_rn(wnw * ec));
+                            if (msk[k] & 2u) atomicAdd(q + 1, (unsigned long long)__float2ll_rn(wne * ec));
+                            if (msk[k] & 4u) atomicAdd(q + W, (unsigned long long)__float2ll_rn(wsw * ec));
+                            if (msk[k] & 8u) atomicAdd(q + W + 1, (unsigned long long)__float2ll_rn(wse * ec));
+                        } else {
+                            float* q = gbase + (og + c * plane);
+                            if (msk[k] & 1u) atomicAdd(q, wnw * ec);
+                            if (msk[k] & 2u) atomicAdd(q + 1, wne * ec);
+                            if (msk[k] & 4u) atomicAdd(q + W, wsw * ec);
+                            if (msk[k] & 8u) atomicAdd(q + W + 1, wse * ec);
+                        }
                     }
                 }
             }
@@ -629,8 +640,15 @@ __device__ __forceinline__ void run_combo(const plb_photo_args& a, const PairCon
                 }
             }
             if (GRAD && IMG_GRAD && valid && pc.g_tgt != nullptr) {
-                float* gq = pc.g_tgt + o;
-                atomicAdd(gq, gt[0]); atomicAdd(gq + plane, gt[1]); atomicAdd(gq + 2 * plane, gt[2]);
+                if (pc.det_rho > 0.0f) {
+                    unsigned long long* gq = reinterpret_cast<unsigned long long*>(pc.g_tgt) + o;
+                    atomicAdd(gq, (unsigned long long)__float2ll_rn(gt[0]));
+                    atomicAdd(gq + plane, (unsigned long long)__float2ll_rn(gt[1]));
+                    atomicAdd(gq + 2 * plane, (unsigned long long)__float2ll_rn(gt[2]));
+                } else {
+                    float* gq = pc.g_tgt + o;
+                    atomicAdd(gq, gt[0]); atomicAdd(gq + plane, gt[1]); atomicAdd(gq + 2 * plane, gt[2]);
+                }
             }
         }
         if (LOW && GRAD) {
@@ -752,6 +770,10 @@ photo_pairs_kernel(const __grid_constant__ PhotoLaunch p, int grad, int img_grad
         if (lane == 1) {
             pc.tgt = job.tgt + img;
             pc.g_tgt = (grad && img_grad && job.g_tgt) ? job.g_tgt + img : nullptr;
+            if (pc.g_tgt != nullptr && p.det)   // (a float* that holds the address of the image's int64 accumulators)
+                pc.g_tgt = reinterpret_cast<float*>(reinterpret_cast<long long*>(ws + p.L.detacc) +
+                                                    ((size_t)p.det_tgt[jb] * a.B * 3 * plane + img));
+            pc.det_rho = (grad && img_grad && p.det) ? p.det_rho[jb] : 0.0f;
             pc.n_src = job.n_src; pc.n_scales = job.n_scales; pc.lowres = p.lowres[jb];
             pc.w_e = p.w_e[jb] * (a.upstream ? __ldg(a.upstream) : 1.0f);
         }
@@ -789,6 +811,9 @@ photo_pairs_kernel(const __grid_constant__ PhotoLaunch p, int grad, int img_grad
             for (int r = 0; r < 3; ++r) pc.P[lane][r] = make_float4(P[r * 4], P[r * 4 + 1], P[r * 4 + 2], P[r * 4 + 3]);
             pc.src[lane] = job.src[lane] + img;
             pc.g_src[lane] = (grad && img_grad && job.g_src[lane]) ? job.g_src[lane] + img : nullptr;
+            if (pc.g_src[lane] != nullptr && p.det)
+                pc.g_src[lane] = reinterpret_cast<float*>(reinterpret_cast<long long*>(ws + p.L.detacc) +
+                                                          ((size_t)p.det_src[jb][lane] * a.B * 3 * plane + img));
         }
     }
     __syncthreads();
@@ -859,7 +884,11 @@ photo_l1_kernel(const __grid_constant__ PhotoLaunch p) {
         const int jb = (a.n_jobs > 1 && u >= p.unit_start[1]) ? 1 : 0;      // PLB_MAX_JOBS == 2
         return jb * a.B + (u - p.unit_start[jb]) / p.units_per_pair[jb];
     };
-    const int vblk = blockIdx.x;     // virtual block index: which share of the unit list this block owns
+    // virtual block index: which share of the unit list this block owns.  The hardware deals blocks to the SMs round
+    // robin, so block i and block i + SMs share an SM: with perm_sms set, the blocks resident on ONE SM own ADJACENT
+    // shares - the same job and combo kind (one code path in the SM's instruction cache instead of all of them) and
+    // neighbouring rows of one image (shared L1 lines).  Any mapping is correct; this one is only faster.
+    const int vblk = p.perm_sms > 0 ? (int)(blockIdx.x % p.perm_sms) * p.perm_bps + (int)(blockIdx.x / p.perm_sms) : (int)blockIdx.x;
     const int gw = vblk * PH_WARPS + warp;
     const int blk_u0 = photo_unit_of(p, H, pos_of(vblk * PH_WARPS));
     const int blk_u1 = photo_unit_of(p, H, pos_of(vblk * PH_WARPS + PH_WARPS));
@@ -1602,6 +1631,26 @@ __global__ void guarded_zero_kernel(float* g, size_t n, const float* skip0, cons
     }
 }
 
+// Deterministic image gradients, second half: fixed-point accumulators -> the caller's float buffers (ACCUMULATED,
+// one writer per element), accumulators re-zeroed for the next call.
+struct DetConvert { float* out[PH_DET_MAX]; int n; float scale; };
+__global__ void __launch_bounds__(256)
+photo_det_convert_kernel(long long* __restrict__ acc, const __grid_constant__ DetConvert d, size_t per, const float* upstream) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= per) return;
+    const float scale = d.scale * (upstream ? __ldg(upstream) : 1.0f);
+#pragma unroll
+    for (int u = 0; u < PH_DET_MAX; ++u) {
+        if (u >= d.n) break;
+        long long* q = acc + (size_t)u * per + i;
+        const long long v = *q;
+        if (v != 0) {
+            d.out[u][i] += (float)((double)v * (double)scale);
+            *q = 0;
+        }
+    }
+}
+
 static int photo_lowres_merge_launch(const PhotoLaunch& p, cudaStream_t st) {
     const plb_photo_args& a = p.a;
     LowMergeLaunch u;
@@ -1707,6 +1756,16 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     }
     p.weight_start[PLB_MAX_JOBS] = wsum;
     p.unit_start[PLB_MAX_JOBS] = usum;
+    // deterministic image gradients: accumulator slots and the weight of every job relative to the largest one
+    const PhotoDetSlots dslots = photo_det_slots(*a);
+    p.det = (img_grad && dslots.n > 0) ? 1 : 0;
+    float w_max = 0.0f;
+    for (int j = 0; j < a->n_jobs; ++j) w_max = p.w_e[j] > w_max ? p.w_e[j] : w_max;
+    for (int j = 0; j < PLB_MAX_JOBS; ++j) {
+        p.det_tgt[j] = dslots.tgt[j];
+        for (int i = 0; i < PLB_MAX_SRC; ++i) p.det_src[j][i] = dslots.src[j][i];
+        p.det_rho[j] = (j < a->n_jobs && w_max > 0.0f) ? p.w_e[j] / w_max : 0.0f;
+    }
 
     const int bps = dispatch_variant(p, img_grad, head, low, 1, st);
     // more blocks than are resident: the hardware hands a waiting block to whichever SM retires one first, which evens
@@ -1721,6 +1780,10 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     if (grid > photo_max_grid(*a)) grid = photo_max_grid(*a);
     if (grid < 1) grid = 1;
     p.grid = (int)grid;
+    p.perm_sms = p.perm_bps = 0;
+#ifdef PH_SM_GROUP   // measured (profiles/README.md): c2 192 vs 185 us, c3 461 vs 451, c5 947 vs 951 - off
+    if (grid == (long long)sms * bps && bps > 1) { p.perm_sms = sms; p.perm_bps = bps; }
+#endif
     p.warps_per_block = PH_WARPS;
     p.n_warps = p.grid * p.warps_per_block;
     p.share = (int)(wsum / p.n_warps);
@@ -1748,6 +1811,17 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
         cfg.numAttrs = 1;
         const cudaError_t e = cudaLaunchKernelEx(&cfg, photo_finalize_kernel, p, (int)a->want_grad);
         if (e != cudaSuccess) return (int)e;
+        ++g_launches;
+        PLB_CHECK_LAUNCH();
+    }
+    if (p.det) {
+        DetConvert d;
+        d.n = dslots.n;
+        for (int k = 0; k < PH_DET_MAX; ++k) d.out[k] = dslots.out[k];
+        d.scale = w_max / PH_DET_ONE;
+        const size_t per = (size_t)a->B * 3 * a->H * a->W;
+        photo_det_convert_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<long long*>((char*)a->workspace + p.L.detacc), d, per, a->upstream);
         ++g_launches;
         PLB_CHECK_LAUNCH();
     }

@@ -76,14 +76,51 @@ struct PhotoLayout {
     size_t pairs;     // PairConst [n_pairs] (photo_pairs_kernel -> photo_l1_kernel)
     size_t ylow;      // float: per PH_SM_LOWFAST (job, scale) [B][2][dh][W] y-reduced gradient rows (two partial slots)
     size_t ylow_off[PLB_MAX_JOBS][PLB_MAX_SCALES];   // float offset of each (job, scale) from `ylow`
+    size_t detacc;    // int64 [det_n][B*3*H*W]: fixed-point accumulators of the image gradients (deterministic mode)
+    int det_n;        // distinct image-gradient buffers of the call (0: not deterministic / no image gradients)
     size_t total;
 };
+
+// Deterministic image gradients.  The bilinear scatter of d loss / d source (and the per-combo sums into
+// d loss / d target) are the only results that several warps add into in an order the hardware picks.  In
+// deterministic mode every contribution is rounded ONCE to a 2^-30 fixed-point fraction of the largest per-pixel
+// weight of the call and added with 64-bit INTEGER atomics - integer addition is associative, so the sums are
+// bitwise repeatable whatever the order - and photo_det_convert_kernel turns the accumulators into floats (and
+// re-zeroes them).  |contribution| <= 2^30 and at most B*H*W*samples < 2^32 of them meet in one pixel: no overflow.
+constexpr float PH_DET_ONE = 1073741824.0f;           // 2^30
+constexpr int PH_DET_MAX = PLB_MAX_SRC + 2;           // distinct image-gradient buffers of a call (sources + targets)
+struct PhotoDetSlots {
+    int n;
+    float* out[PH_DET_MAX];                           // the caller's buffers, in first-seen order
+    int src[PLB_MAX_JOBS][PLB_MAX_SRC], tgt[PLB_MAX_JOBS];   // slot of every job's g_src[i] / g_tgt, -1 = not wanted
+};
+static inline PhotoDetSlots photo_det_slots(const plb_photo_args& a) {
+    PhotoDetSlots d;
+    d.n = 0;
+    for (int k = 0; k < PH_DET_MAX; ++k) d.out[k] = nullptr;
+    auto slot = [&](float* g) -> int {
+        if (g == nullptr) return -1;
+        for (int k = 0; k < d.n; ++k) if (d.out[k] == g) return k;
+        if (d.n >= PH_DET_MAX) return -1;
+        d.out[d.n] = g;
+        return d.n++;
+    };
+    for (int j = 0; j < PLB_MAX_JOBS; ++j) {
+        d.tgt[j] = -1;
+        for (int i = 0; i < PLB_MAX_SRC; ++i) d.src[j][i] = -1;
+        if (j >= a.n_jobs || !a.want_grad || !a.deterministic) continue;
+        d.tgt[j] = slot(a.jobs[j].g_tgt);
+        for (int i = 0; i < a.jobs[j].n_src && i < PLB_MAX_SRC; ++i) d.src[j][i] = slot(a.jobs[j].g_src[i]);
+    }
+    return d;
+}
 
 // Launch-time constants computed once on the host (kept out of the kernel's instruction stream).
 struct PhotoLaunch {
     plb_photo_args a;
     PhotoLayout L;
     int grid;                            // number of blocks
+    int perm_sms, perm_bps;              // > 0: block i owns share (i % perm_sms) * perm_bps + i / perm_sms (grid == perm_sms * perm_bps)
     int warps_per_block;                 // PH_WARPS
     int n_warps;                         // grid * warps_per_block
     int strips;                          // ceil(W / 32)
@@ -99,6 +136,9 @@ struct PhotoLaunch {
     long long weight_start[PLB_MAX_JOBS + 1];  // cumulative weight at the start of each job
     int unit_start[PLB_MAX_JOBS + 1];    // cumulative unit index at the start of each job
     float w_e[PLB_MAX_JOBS];             // term_weight / (3*B*H*W)
+    int det;                             // deterministic image gradients (fixed-point accumulators, see PhotoLayout::detacc)
+    int det_src[PLB_MAX_JOBS][PLB_MAX_SRC], det_tgt[PLB_MAX_JOBS];   // accumulator slot of g_src[i] / g_tgt, -1 = none
+    float det_rho[PLB_MAX_JOBS];         // w_e[j] / max_j w_e[j]: a contribution of job j in units of the largest weight
     int lowres[PLB_MAX_JOBS];            // bit s set: scale s is not full resolution
     int share, share_rem;                // warp w starts at weight w*share + min(w, share_rem)
 };
@@ -169,6 +209,9 @@ static inline PhotoLayout photo_layout(const plb_photo_args& a) {
             }
         }
     off = align_up(off + sizeof(float) * yl, 256);
+    L.detacc = off;
+    L.det_n = photo_det_slots(a).n;
+    off = align_up(off + sizeof(long long) * (size_t)L.det_n * a.B * 3 * a.H * a.W, 256);
     L.total = off;
     return L;
 }
@@ -194,7 +237,7 @@ struct __align__(16) PairConst {
     int smode[PLB_MAX_SCALES];
     int fac[PLB_MAX_SCALES];         // integer power-of-two upsampling factor of the scale (both directions), else 0
     int n_src, n_scales, lowres, pad;
-    float w_e, pad2[3];
+    float w_e, det_rho, pad2[2];     // det_rho > 0: g_src / g_tgt point at int64 fixed-point accumulators (deterministic mode)
 };
 
 

@@ -98,7 +98,7 @@ class LossConfig:
 
     def __init__(self, n_src, scales_per_frame, input_is_depth=False, do_photo=True, do_smooth=True,
                  rotation_mode="axisangle", fused_backward=True, disp_a=10.0, disp_b=0.01, scale_decay=2.3,
-                 mode=_lib.PHOTO_L1_MEAN, flags=0, disp_head=None):
+                 mode=_lib.PHOTO_L1_MEAN, flags=0, disp_head=None, deterministic=None):
         self.n_src = n_src
         self.scales_per_frame = list(scales_per_frame)  # e.g. [4, 4]: frames with a depth pyramid
         self.input_is_depth = bool(input_is_depth)
@@ -107,6 +107,9 @@ class LossConfig:
         self.fused_backward = fused_backward
         self.disp_a, self.disp_b, self.scale_decay = disp_a, disp_b, scale_decay
         self.mode, self.flags = mode, flags
+        # image gradients through order-independent fixed-point accumulation (everything else is always repeatable);
+        # None follows torch.use_deterministic_algorithms()
+        self.deterministic = torch.are_deterministic_algorithms_enabled() if deterministic is None else bool(deterministic)
         # (alpha, beta): the pyramids hold the disparity head's PRE-ACTIVATION x and disp = alpha * sigmoid(x) + beta
         # (models/depth/disp_net.py:121-139) is evaluated inside the kernels; gradients come back with respect to x
         self.disp_head = None if disp_head is None else (float(disp_head[0]), float(disp_head[1]))
@@ -134,6 +137,7 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
         if cfg.disp_head:
             a.head_alpha, a.head_beta = cfg.disp_head
         a.want_grad = int(want_grad)
+        a.deterministic = int(cfg.deterministic)
         a.sm_limit = _sm_limit
         a.poses, a.K = poses.data_ptr(), K.data_ptr()
         a.g_poses = _ptr(g_poses) if want_grad else 0
