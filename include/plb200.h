@@ -47,6 +47,10 @@ extern "C" {
 /* plb_photo_job.flags (MIN_REPROJ mode) */
 #define PLB_PHOTO_NO_SSIM 1u
 #define PLB_PHOTO_NO_AUTOMASK 2u
+#define PLB_PHOTO_CLIP 4u  /* clamp every photometric map (each warped source at each scale, each automask
+                              reference) at mean + clip_loss * std of that whole [B,3,H,W] map, the threshold
+                              detached, as compute_photometric_loss does (losses.py:79-82); two more launches
+                              (map statistics, thresholds) precede the fused kernel */
 
 /*
  * One "direction" of Losses.reprojection_loss (losses.py:190-228): a target
@@ -68,7 +72,7 @@ typedef struct plb_photo_job {
     float term_weight;                  /* weight of each (scale, source) mean in the final loss   */
     int32_t mode;                       /* PLB_PHOTO_*                                             */
     uint32_t flags;
-    int32_t reserved;
+    float clip_loss;                    /* PLB_PHOTO_CLIP: 0.5 in the reference (losses.py:58)     */
 } plb_photo_job;
 
 /*

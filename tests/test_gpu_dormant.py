@@ -78,30 +78,81 @@ def test_photometric_map_backward_vs_oracle(B, C, H, W, variant):
     assert rel_err(gy.grad.cpu(), ry.grad) < 5e-4
 
 
-def _run_min(tgt, refs, disp_scales, poses, K, automask, no_ssim=False):
-    """disparity -> depth (our kernel) -> fused min-reprojection loss; gradients back to disparity."""
+def _run_min(tgt, refs, disp_scales, poses, K, automask, no_ssim=False, clip=None, image_grads=False,
+             deterministic=None, upstream=1.0):
+    """disparity -> depth (our kernel) -> fused min-reprojection loss; gradients back to disparity (and, with
+    image_grads, to the frames: the tensors are returned as the 4th / 5th value)."""
     from losses import Losses
     from geometry.pose_geometry import disp_to_depth
     dev = _dev()
     disp = [d.to(dev).requires_grad_(True) for d in disp_scales]
     p = poses.to(dev).requires_grad_(True)
+    t = tgt.to(dev).requires_grad_(image_grads)
+    r = [x.to(dev).requires_grad_(image_grads) for x in refs]
     depth = disp_to_depth([disp])[0]
-    loss = Losses().multiview_reprojection_loss(tgt.to(dev), [r.to(dev) for r in refs], depth, p, K.to(dev),
-                                                automask=automask, no_ssim=no_ssim)
-    loss.backward()
+    loss = Losses(deterministic=deterministic).multiview_reprojection_loss(t, r, depth, p, K.to(dev), automask=automask,
+                                                                           no_ssim=no_ssim, clip=clip)
+    (upstream * loss).backward()
+    if image_grads:
+        return loss, disp, p, t, r
     return loss, disp, p
 
 
 @pytest.mark.parametrize("automask", [True, False])
-def test_min_reprojection_golden(automask):
+@pytest.mark.parametrize("variant", ["noclip", "clip"])
+def test_min_reprojection_golden(automask, variant):
+    """Golden composition of the reference's own functions (make_golden.py::dormant_case): `clip` = through
+    compute_photometric_loss with its mean + 0.5 std clamp per map (losses.py:79-82), the way
+    notes/toy_problem/losses.py:107-129 composes it; `noclip` = the same without the clamp.  Loss, pose, disparity and
+    source-image gradients."""
     g = load_golden("dormant_b4_s2_32x48")
     tgt, refs, disparity, poses, K = golden_inputs(g)
-    tag = "noclip_%s" % ("auto" if automask else "noauto")
-    loss, disp, p = _run_min(tgt, refs, disparity[0], poses, K, automask)
-    assert abs(float(loss) - float(g["loss_" + tag])) <= LOSS_TOL * abs(float(g["loss_" + tag]))
-    assert rel_err(p.grad.cpu(), g["g_poses_" + tag]) < GRAD_TOL
-    for s, t in enumerate(disp):
-        assert rel_err(t.grad.cpu(), g["g_disp_s%d_%s" % (s, tag)]) < GRAD_TOL, s
+    tag = "%s_%s" % (variant, "auto" if automask else "noauto")
+    clip = 0.5 if variant == "clip" else None
+    loss, disp, p, t, r = _run_min(tgt, refs, disparity[0], poses, K, automask, clip=clip, image_grads=True)
+    errs = {"loss": abs(float(loss) - float(g["loss_" + tag])) / abs(float(g["loss_" + tag])),
+            "poses": rel_err(p.grad.cpu(), g["g_poses_" + tag])}
+    for s, d in enumerate(disp):
+        errs["disp%d" % s] = rel_err(d.grad.cpu(), g["g_disp_s%d_%s" % (s, tag)])
+    for i in range(2):
+        errs["ref%d" % i] = rel_err(r[i].grad.cpu(), g["g_ref%d_%s" % (i, tag)])
+    print(tag, {k: "%.2e" % v for k, v in errs.items()})
+    assert errs.pop("loss") <= LOSS_TOL
+    assert max(errs.values()) < GRAD_TOL, errs
+    # without image gradients (the single-pass variant) the other gradients are the same
+    loss2, disp2, p2 = _run_min(tgt, refs, disparity[0], poses, K, automask, clip=clip)
+    assert abs(float(loss2) - float(loss)) <= 1e-6 * abs(float(loss))
+    assert rel_err(p2.grad, p.grad) < 1e-6
+
+
+@pytest.mark.parametrize("clip", [None, 0.5])
+def test_min_reprojection_image_grads_vs_oracle(clip):
+    """Gradients with respect to the TARGET and the source frames against autograd through the oracle composition
+    (the golden vectors hold source gradients only), float-atomic and deterministic accumulation; the deterministic
+    mode is bitwise repeatable."""
+    from plb200 import synth
+    from oracle import restated as O
+    inp = synth.make_photo_inputs(3, 40, 70, n_src=2, n_scales=2, seed=411)
+    tgt, refs, poses, K = inp["tgt"], inp["ref_imgs"], inp["poses"], inp["intrinsics"]
+    rt = tgt.double().requires_grad_(True)
+    rr = [x.double().requires_grad_(True) for x in refs]
+    rd = [d.double().requires_grad_(True) for d in inp["disparity"][0]]
+    rl = O.min_reprojection_loss(rt, rr, O.disp_to_depth([rd])[0], poses.double(), K, automask=True, clip_loss=clip)
+    (0.6 * rl).backward()
+    outs = []
+    for det in (False, True, True):
+        loss, disp, p, t, r = _run_min(tgt, refs, inp["disparity"][0], poses, K, True, clip=clip, image_grads=True,
+                                       deterministic=det, upstream=0.6)
+        errs = [rel_err(t.grad.cpu(), rt.grad)] + [rel_err(r[i].grad.cpu(), rr[i].grad) for i in range(2)] + \
+               [rel_err(d.grad.cpu(), x.grad) for d, x in zip(disp, rd)]
+        print("clip", clip, "det", det, "rel err tgt / ref0 / ref1 / disp:", ["%.2e" % e for e in errs])
+        assert abs(float(loss) - float(rl)) <= 2 * LOSS_TOL * abs(float(rl))
+        # fp32 kernel against the fp64 evaluation of the reference's formulas: selections that tie to fp32 rounding
+        # (min / mask / channel max / clamp) move single elements
+        assert max(errs[:3]) < GRAD_TOL, errs
+        outs.append([t.grad.clone()] + [x.grad.clone() for x in r])
+    for a, b in zip(outs[1], outs[2]):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("B,H,W,S,automask,no_ssim", [(1, 9, 35, 1, True, False), (3, 50, 131, 3, True, False),
@@ -161,5 +212,5 @@ def test_min_reprojection_repeatable_and_forward_only():
     with torch.no_grad():
         depth = [1.0 / (10.0 * d.to(dev) + 0.01) for d in inp["disparity"][0]]
         l2 = Losses().multiview_reprojection_loss(inp["tgt"].to(dev), [r.to(dev) for r in inp["ref_imgs"]], depth,
-                                                  inp["poses"].to(dev), inp["intrinsics"].to(dev))
+                                                  inp["poses"].to(dev), inp["intrinsics"].to(dev), clip=None)
     assert abs(float(l2) - float(outs[0][0])) <= 1e-5 * abs(float(l2))

@@ -87,15 +87,18 @@ class Losses:
         return ops.photometric_map(pred, target, no_ssim=no_ssim, clip=self.clip_loss)
 
     def multiview_reprojection_loss(self, tgt_img, ref_imgs, depth, poses, intrinsics, mode='min',
-                                    automask=True, no_ssim=False):
+                                    automask=True, no_ssim=False, clip='default'):
         """Min-reprojection + automask composition (`losses.py:86-181` as the
-        commented lines and `notes/toy_problem/losses.py:107-129` spell it)."""
+        commented lines and `notes/toy_problem/losses.py:107-129` spell it).  Every photometric map goes
+        through `compute_photometric_loss`, i.e. is clamped at mean + `self.clip_loss` * std of that map
+        (`losses.py:79-82`); `clip=None` leaves the maps unclamped, a number replaces `self.clip_loss`."""
         if mode != 'min':
             raise NotImplementedError(mode)
         pyr = [list(depth) if isinstance(depth, (list, tuple)) else [depth]]
         flags = (_lib.PHOTO_NO_SSIM if no_ssim else 0) | (0 if automask else _lib.PHOTO_NO_AUTOMASK)
+        clip_loss = self.clip_loss if clip == 'default' else clip
         mam, _ = ops.fused_losses(tgt_img, list(ref_imgs), pyr, poses, intrinsics, input_is_depth=True,
                                   do_smooth=False, rotation_mode=self.rotation_mode,
                                   fused_backward=self.fused_backward, mode=_lib.PHOTO_MIN_REPROJ, flags=flags,
-                                  deterministic=self.deterministic)
+                                  deterministic=self.deterministic, clip_loss=clip_loss)
         return mam

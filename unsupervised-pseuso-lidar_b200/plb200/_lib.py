@@ -14,7 +14,7 @@ MAX_SRC, MAX_SCALES, MAX_JOBS = 4, 4, 2
 ROT_AXISANGLE, ROT_EULER = 0, 1
 PHOTO_L1_MEAN, PHOTO_MIN_REPROJ = 0, 1
 INPUT_DISP, INPUT_DEPTH, INPUT_LOGIT = 0, 1, 2
-PHOTO_NO_SSIM, PHOTO_NO_AUTOMASK = 1, 2
+PHOTO_NO_SSIM, PHOTO_NO_AUTOMASK, PHOTO_CLIP = 1, 2, 4
 
 _fp = C.c_void_p  # device pointers are passed as integers
 
@@ -36,7 +36,7 @@ class PhotoJob(C.Structure):
         ("term_weight", C.c_float),
         ("mode", C.c_int32),
         ("flags", C.c_uint32),
-        ("reserved", C.c_int32),
+        ("clip_loss", C.c_float),
     ]
 
 

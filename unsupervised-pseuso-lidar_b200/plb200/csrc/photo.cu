@@ -1651,6 +1651,21 @@ photo_det_convert_kernel(long long* __restrict__ acc, const __grid_constant__ De
     }
 }
 
+int photo_det_convert_launch(const plb_photo_args& a, const PhotoLayout& L, float unit, cudaStream_t st) {
+    const PhotoDetSlots dslots = photo_det_slots(a);
+    if (dslots.n == 0) return PLB_OK;
+    DetConvert d;
+    d.n = dslots.n;
+    for (int k = 0; k < PH_DET_MAX; ++k) d.out[k] = dslots.out[k];
+    d.scale = unit;
+    const size_t per = (size_t)a.B * 3 * a.H * a.W;
+    photo_det_convert_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<long long*>((char*)a.workspace + L.detacc), d, per, a.upstream);
+    ++g_launches;
+    PLB_CHECK_LAUNCH();
+    return PLB_OK;
+}
+
 static int photo_lowres_merge_launch(const PhotoLaunch& p, cudaStream_t st) {
     const plb_photo_args& a = p.a;
     LowMergeLaunch u;
@@ -1815,15 +1830,8 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
         PLB_CHECK_LAUNCH();
     }
     if (p.det) {
-        DetConvert d;
-        d.n = dslots.n;
-        for (int k = 0; k < PH_DET_MAX; ++k) d.out[k] = dslots.out[k];
-        d.scale = w_max / PH_DET_ONE;
-        const size_t per = (size_t)a->B * 3 * a->H * a->W;
-        photo_det_convert_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<long long*>((char*)a->workspace + p.L.detacc), d, per, a->upstream);
-        ++g_launches;
-        PLB_CHECK_LAUNCH();
+        const int rc2 = photo_det_convert_launch(*a, p.L, w_max / PH_DET_ONE, st);
+        if (rc2 != PLB_OK) return rc2;
     }
     if (a->want_grad) {
         if (lowfast) {

@@ -64,6 +64,8 @@ enum {
     PH_SM_LOWNOGRAD = 3    // low resolution, no gradient wanted
 };
 
+// maps of the SSIM-mode composition that carry their own clip threshold: (scale, source) and the automask references
+constexpr int PM_MAXMAPS = PLB_MAX_SCALES * PLB_MAX_SRC + PLB_MAX_SRC;
 constexpr size_t PH_PAIRCONST_BYTES = 2048;   // >= sizeof(PairConst) (static_assert below)
 struct PhotoLayout {
     size_t tickets;   // int32 [n_pairs + 1]
@@ -76,6 +78,8 @@ struct PhotoLayout {
     size_t pairs;     // PairConst [n_pairs] (photo_pairs_kernel -> photo_l1_kernel)
     size_t ylow;      // float: per PH_SM_LOWFAST (job, scale) [B][2][dh][W] y-reduced gradient rows (two partial slots)
     size_t ylow_off[PLB_MAX_JOBS][PLB_MAX_SCALES];   // float offset of each (job, scale) from `ylow`
+    size_t pm_thr;    // float [PM_MAXMAPS]: clip thresholds of the SSIM-mode maps (photo_min.cu, PLB_PHOTO_CLIP)
+    size_t pm_stat;   // double [tiles * B][PM_MAXMAPS][2]: per-block (sum, sum of squares) of every map
     size_t detacc;    // int64 [det_n][B*3*H*W]: fixed-point accumulators of the image gradients (deterministic mode)
     int det_n;        // distinct image-gradient buffers of the call (0: not deterministic / no image gradients)
     size_t total;
@@ -109,7 +113,8 @@ static inline PhotoDetSlots photo_det_slots(const plb_photo_args& a) {
         d.tgt[j] = -1;
         for (int i = 0; i < PLB_MAX_SRC; ++i) d.src[j][i] = -1;
         if (j >= a.n_jobs || !a.want_grad || !a.deterministic) continue;
-        d.tgt[j] = slot(a.jobs[j].g_tgt);
+        // (the SSIM-mode kernel owns every target pixel: its target gradient is written directly, no accumulator)
+        if (a.jobs[j].mode != PLB_PHOTO_MIN_REPROJ) d.tgt[j] = slot(a.jobs[j].g_tgt);
         for (int i = 0; i < a.jobs[j].n_src && i < PLB_MAX_SRC; ++i) d.src[j][i] = slot(a.jobs[j].g_src[i]);
     }
     return d;
@@ -209,6 +214,12 @@ static inline PhotoLayout photo_layout(const plb_photo_args& a) {
             }
         }
     off = align_up(off + sizeof(float) * yl, 256);
+    L.pm_thr = off; L.pm_stat = off;
+    if (a.n_jobs >= 1 && a.jobs[0].mode == PLB_PHOTO_MIN_REPROJ && (a.jobs[0].flags & PLB_PHOTO_CLIP)) {
+        off = align_up(off + sizeof(float) * PM_MAXMAPS, 256);
+        L.pm_stat = off;
+        off = align_up(off + sizeof(double) * (size_t)((a.W + 31) / 32) * ((a.H + 7) / 8) * a.B * PM_MAXMAPS * 2, 256);
+    }
     L.detacc = off;
     L.det_n = photo_det_slots(a).n;
     off = align_up(off + sizeof(long long) * (size_t)L.det_n * a.B * 3 * a.H * a.W, 256);
@@ -250,6 +261,8 @@ static inline int photo_min_tiles(const plb_photo_args& a) {
 }
 
 int photo_upsample_T_launch(const PhotoLaunch& p, cudaStream_t st);   // photo.cu
+// fixed-point accumulators (PhotoLayout::detacc) -> the caller's buffers; `unit`: value of one accumulator count
+int photo_det_convert_launch(const plb_photo_args& a, const PhotoLayout& L, float unit, cudaStream_t st);   // photo.cu
 int photo_min_launch(const plb_photo_args* a, cudaStream_t st);       // photo_min.cu
 
 }  // namespace plb

@@ -15,6 +15,17 @@
 // (3) gathers d loss / d warped for the tile pixels from their 3x3 neighbours (with the
 // multiplicities reflection padding induces) and pushes it through the bilinear sampler and the
 // projection as the L1 kernel does.  Reductions are fixed-order (bitwise repeatable).
+//
+// The clip of compute_photometric_loss (losses.py:79-82: every map clamped at mean + 0.5 std of that whole map,
+// threshold detached) is a grid-wide dependency, so PLB_PHOTO_CLIP runs the kernel twice: the STATS variant stops
+// after stage (2) and leaves per-block (sum, sum of squares) of every map - each warped source at each scale, each
+// automask reference - pmin_thresholds_kernel reduces them in block order (fp64) into one threshold per map, and
+// the main variant clamps each term (a clamped term carries no gradient) before the min / mask / max selections.
+//
+// Image gradients (IMG variant): d loss / d warped is scattered through the bilinear weights into the source
+// gradients (float atomics, or the 64-bit fixed-point accumulators of the deterministic mode); the target enters
+// SSIM as y and the L1 term, d rp / d y_q = da + cb * y_q + cc * x_q - cl at the centre, gathered with the same 3x3
+// pass and written directly (every target pixel has one owner).  The automask references only feed a comparison.
 #include "photo_common.cuh"
 
 namespace plb {
@@ -33,7 +44,12 @@ struct PminLaunch {
     int tiles_x, tiles;
     float w_e;   // term_weight / (B*H*W): weight of one pixel's max_c in the loss
     float C1, C2;
+    int clip;    // PLB_PHOTO_CLIP: thresholds at L.pm_thr (written by pmin_thresholds_kernel)
+    int det;     // deterministic source-image gradients: int64 accumulators at L.detacc
+    int det_src[PLB_MAX_SRC];
 };
+constexpr float PM_DET_ONE = 16777216.0f;   // 2^24: the source-gradient accumulators count 2^-24 of (w_e x upstream)
+enum { PM_VAR_MAIN = 0, PM_VAR_STATS = 1, PM_VAR_IMG = 2 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
     // ReflectionPad2d(1) index rule extended so that any tile position maps inside the image
@@ -118,20 +134,23 @@ struct __align__(16) PminSmem {
     float rec[PM_THREADS / 32][PH_NREC + 3];
     float red[PH_NREC + 3];
     float part4[4][64];
+    float thr[PM_MAXMAPS];                  // clip thresholds (3e38: no clip)
+    float da[3][PM_N1];                     // IMG: constant term of d rp / d y_q (the target's side of SSIM)
+    double stat[PM_THREADS / 32][PM_MAXMAPS][2];   // STATS: per-warp (sum, sum of squares) of every map
     int flag;
 };
 
 // photometric value of one (pixel, channel) from its 3x3 window sums, and the coefficients of its
 // derivative w.r.t. the predicted image at window position q:
 //   d rp / d x_q = ca + cb * x_q + cc * y_q   (+ cl at the centre)
-struct Photo { float rp, ca, cb, cc, cl; };
+struct Photo { float rp, ca, cb, cc, cl, da; };
 __device__ __forceinline__ Photo photo_from_sums(float sx, float sxx, float sxy, float sy, float syy, float xc, float yc,
                                                  float C1, float C2, bool no_ssim) {
     Photo r;
     const float diff = xc - yc;
     const float sg = (diff > 0.0f ? 1.0f : 0.0f) - (diff < 0.0f ? 1.0f : 0.0f);
     if (no_ssim) {
-        r.rp = fabsf(diff); r.ca = r.cb = r.cc = 0.0f; r.cl = sg;
+        r.rp = fabsf(diff); r.ca = r.cb = r.cc = r.da = 0.0f; r.cl = sg;
         return r;
     }
     const float i9 = 1.0f / 9.0f;
@@ -149,6 +168,8 @@ __device__ __forceinline__ Photo photo_from_sums(float sx, float sxx, float sxy,
     //                  + y_q ((2/9) N1 / (D1 D2));   d rp / d x_q = -0.425 * (that) inside the clamp
     const float k = (h > 0.0f && h < 1.0f) ? (-0.425f * 2.0f * i9) : 0.0f;
     r.ca = k * (muy * (N2 - N1) * iD - ssim * mux * (iD1 - iD2));
+    // (SSIM is symmetric in x and y: d ssim / d y_q has the same x_q / y_q coefficients swapped and this constant)
+    r.da = k * (mux * (N2 - N1) * iD - ssim * muy * (iD1 - iD2));
     r.cb = k * (-ssim * iD2);
     r.cc = k * (N1 * iD);
     r.cl = 0.15f * sg;
@@ -162,81 +183,113 @@ __device__ __forceinline__ Photo photo_from_sums(float sx, float sxx, float sxy,
 //   MODE 0: first sources of the scale: write val / src / coef;  MODE 1: later sources: update when smaller;
 //   MODE 2 / 3: the same for the automask reference (raw sources), value only.
 constexpr int PM_S2_ITEMS = 3 * PM_W1 * 2;
-template <int NS, int MODE>
-__device__ __forceinline__ void pm_stage2(PminSmem& S, int i0, int tid, int tx0, int ty0, int H, int W, float C1, float C2,
-                                          bool no_ssim) {
-    if (tid >= PM_S2_ITEMS) return;
-    const int ch = tid / (2 * PM_W1), r = tid - ch * (2 * PM_W1);
-    const int grp = r / PM_W1, col = r - grp * PM_W1;
-    const float* __restrict__ T = S.T[ch];
-    int k = (5 * grp) * PM_W2 + col;        // tile + 2 index of the window's top-left corner
-    float hy[3], hyy[3], hx[NS][3], hxx[NS][3], hxy[NS][3];
-    float yc = 0.0f, xc[NS];
-    const int gx = tx0 + col - 1;
-    const bool colin = gx >= 0 && gx < W;
+template <int NS, int MODE, int VAR>
+__device__ __forceinline__ void pm_stage2(PminSmem& S, int i0, int map0, int tid, int tx0, int ty0, int H, int W, float C1,
+                                          float C2, bool no_ssim) {
+    float st[NS][2];
 #pragma unroll
-    for (int rr = 0; rr < 7; ++rr, k += PM_W2) {
-        const int slot = rr % 3;
-        const float y0 = T[k], y1 = T[k + 1], y2 = T[k + 2];
-        hy[slot] = (y0 + y1) + y2;
-        hyy[slot] = fmaf(y2, y2, fmaf(y1, y1, y0 * y0));
-        float xn[NS];
+    for (int q = 0; q < NS; ++q) st[q][0] = st[q][1] = 0.0f;
+    if (tid < PM_S2_ITEMS) {
+        const int ch = tid / (2 * PM_W1), r = tid - ch * (2 * PM_W1);
+        const int grp = r / PM_W1, col = r - grp * PM_W1;
+        const float* __restrict__ T = S.T[ch];
+        int k = (5 * grp) * PM_W2 + col;        // tile + 2 index of the window's top-left corner
+        float hy[3], hyy[3], hx[NS][3], hxx[NS][3], hxy[NS][3];
+        float yc = 0.0f, xc[NS];
+        float thr[NS];
 #pragma unroll
-        for (int q = 0; q < NS; ++q) {
-            const float* __restrict__ X = S.X[i0 + q][ch];
-            const float x0 = X[k], x1 = X[k + 1], x2 = X[k + 2];
-            hx[q][slot] = (x0 + x1) + x2;
-            hxx[q][slot] = fmaf(x2, x2, fmaf(x1, x1, x0 * x0));
-            hxy[q][slot] = fmaf(x2, y2, fmaf(x1, y1, x0 * y0));
-            xn[q] = x1;
-        }
-        if (rr >= 2) {
-            const int o = 5 * grp + rr - 2;            // row of tile + 1
-            const int p1 = o * PM_W1 + col;
-            const int gy = ty0 + o - 1;
-            const bool in = colin && gy >= 0 && gy < H;
-            const float sy = (hy[0] + hy[1]) + hy[2], syy = (hyy[0] + hyy[1]) + hyy[2];
-            Photo m; m.rp = 3.0e38f; m.ca = m.cb = m.cc = m.cl = 0.0f;
-            int mi = 0;
+        for (int q = 0; q < NS; ++q) thr[q] = S.thr[map0 + q];
+        const int gx = tx0 + col - 1;
+        const bool colin = gx >= 0 && gx < W;
+#pragma unroll
+        for (int rr = 0; rr < 7; ++rr, k += PM_W2) {
+            const int slot = rr % 3;
+            const float y0 = T[k], y1 = T[k + 1], y2 = T[k + 2];
+            hy[slot] = (y0 + y1) + y2;
+            hyy[slot] = fmaf(y2, y2, fmaf(y1, y1, y0 * y0));
+            float xn[NS];
 #pragma unroll
             for (int q = 0; q < NS; ++q) {
-                const Photo t = photo_from_sums((hx[q][0] + hx[q][1]) + hx[q][2], (hxx[q][0] + hxx[q][1]) + hxx[q][2],
-                                                (hxy[q][0] + hxy[q][1]) + hxy[q][2], sy, syy, xc[q], yc, C1, C2, no_ssim);
-                if (t.rp < m.rp) { m = t; mi = i0 + q; }
+                const float* __restrict__ X = S.X[i0 + q][ch];
+                const float x0 = X[k], x1 = X[k + 1], x2 = X[k + 2];
+                hx[q][slot] = (x0 + x1) + x2;
+                hxx[q][slot] = fmaf(x2, x2, fmaf(x1, x1, x0 * x0));
+                hxy[q][slot] = fmaf(x2, y2, fmaf(x1, y1, x0 * y0));
+                xn[q] = x1;
             }
-            if (MODE >= 2) {
-                S.aut[ch][p1] = (MODE == 2) ? m.rp : fminf(m.rp, S.aut[ch][p1]);
-            } else {
-                const bool take = (MODE == 0) || m.rp < S.val[ch][p1];
-                if (take) {
-                    S.val[ch][p1] = in ? m.rp : 3.0e38f;
-                    S.src[ch][p1] = (signed char)mi;
-                    S.coef[ch][p1] = make_float4(m.ca, m.cb, m.cc, m.cl);
+            if (rr >= 2) {
+                const int o = 5 * grp + rr - 2;            // row of tile + 1
+                const int p1 = o * PM_W1 + col;
+                const int gy = ty0 + o - 1;
+                const bool in = colin && gy >= 0 && gy < H;
+                const float sy = (hy[0] + hy[1]) + hy[2], syy = (hyy[0] + hyy[1]) + hyy[2];
+                Photo m; m.rp = 3.0e38f; m.ca = m.cb = m.cc = m.cl = m.da = 0.0f;
+                int mi = 0;
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    Photo t = photo_from_sums((hx[q][0] + hx[q][1]) + hx[q][2], (hxx[q][0] + hxx[q][1]) + hxx[q][2],
+                                              (hxy[q][0] + hxy[q][1]) + hxy[q][2], sy, syy, xc[q], yc, C1, C2, no_ssim);
+                    if (VAR == PM_VAR_STATS) {
+                        // the map's own statistics: every pixel of the image once (the tile's interior)
+                        if (in && col >= 1 && col <= PM_TW && o >= 1 && o <= PM_TH) { st[q][0] += t.rp; st[q][1] = fmaf(t.rp, t.rp, st[q][1]); }
+                    } else if (t.rp > thr[q]) {
+                        // torch.clamp(max=thr): the value is the threshold and no gradient passes (losses.py:82)
+                        t.rp = thr[q]; t.ca = t.cb = t.cc = t.cl = t.da = 0.0f;
+                    }
+                    if (t.rp < m.rp) { m = t; mi = i0 + q; }
+                }
+                if (VAR == PM_VAR_STATS) {
+                } else if (MODE >= 2) {
+                    S.aut[ch][p1] = (MODE == 2) ? m.rp : fminf(m.rp, S.aut[ch][p1]);
+                } else {
+                    const bool take = (MODE == 0) || m.rp < S.val[ch][p1];
+                    if (take) {
+                        S.val[ch][p1] = in ? m.rp : 3.0e38f;
+                        S.src[ch][p1] = (signed char)mi;
+                        S.coef[ch][p1] = make_float4(m.ca, m.cb, m.cc, m.cl);
+                        if (VAR == PM_VAR_IMG) S.da[ch][p1] = m.da;
+                    }
                 }
             }
-        }
-        yc = y1;
+            yc = y1;
 #pragma unroll
-        for (int q = 0; q < NS; ++q) xc[q] = xn[q];
+            for (int q = 0; q < NS; ++q) xc[q] = xn[q];
+        }
+    }
+    if (VAR == PM_VAR_STATS) {
+        // warp butterfly (fixed order), then this warp's own slot: no atomics, repeatable
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            double a = (double)st[q][0], b = (double)st[q][1];
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, k);
+                b += __shfl_xor_sync(0xffffffffu, b, k);
+            }
+            if (lane == 0) { S.stat[warp][map0 + q][0] += a; S.stat[warp][map0 + q][1] += b; }
+        }
     }
 }
 
-template <int MODE0>
-__device__ __forceinline__ void pm_stage2_all(PminSmem& S, int n_src, int tid, int tx0, int ty0, int H, int W, float C1,
-                                              float C2, bool no_ssim) {
+// MODE0 = 0: the warped sources of a scale (maps map0 + i); MODE0 = 2: the raw sources (automask reference)
+template <int MODE0, int VAR>
+__device__ __forceinline__ void pm_stage2_all(PminSmem& S, int n_src, int map0, int tid, int tx0, int ty0, int H, int W,
+                                              float C1, float C2, bool no_ssim) {
     // sources two at a time (they share the target's window sums); block-uniform control flow
-    if (n_src >= 2) pm_stage2<2, MODE0>(S, 0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
-    else pm_stage2<1, MODE0>(S, 0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+    if (n_src >= 2) pm_stage2<2, MODE0, VAR>(S, 0, map0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+    else pm_stage2<1, MODE0, VAR>(S, 0, map0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
     if (n_src > 2) {
         __syncthreads();
-        if (n_src == 4) pm_stage2<2, MODE0 + 1>(S, 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
-        else pm_stage2<1, MODE0 + 1>(S, 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+        if (n_src == 4) pm_stage2<2, MODE0 + 1, VAR>(S, 2, map0 + 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+        else pm_stage2<1, MODE0 + 1, VAR>(S, 2, map0 + 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
     }
 }
 
-template <bool GRAD, int NSMAX, bool HEAD>
+template <bool GRAD, int NSMAX, bool HEAD, int VAR>
 __global__ void __launch_bounds__(PM_THREADS, 3)
 photo_min_kernel(const __grid_constant__ PminLaunch p) {
+    constexpr bool STATS = VAR == PM_VAR_STATS, IMG = VAR == PM_VAR_IMG;
     const plb_photo_args& a = p.a;
     if (skip_launch(a.skip_if_unit)) return;
     char* ws = (char*)a.workspace;
@@ -265,6 +318,7 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
             if (lane == 0) kinv_f32(Kb, a.k_is_f64, pc.kinv);
             if (lane == 1) {
                 pc.tgt = job.tgt + img;
+                pc.g_tgt = (GRAD && IMG && job.g_tgt) ? job.g_tgt + img : nullptr;
                 pc.n_src = job.n_src; pc.n_scales = job.n_scales;
                 pc.w_e = p.w_e * (a.upstream ? __ldg(a.upstream) : 1.0f);
             }
@@ -287,9 +341,21 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
             pc.P[lane][1] = make_float4(P[4], P[5], P[6], P[7]);
             pc.P[lane][2] = make_float4(P[8], P[9], P[10], P[11]);
             pc.src[lane] = job.src[lane] + img;
+            float* g = nullptr;
+            if (GRAD && IMG && job.g_src[lane] != nullptr) {
+                g = job.g_src[lane] + img;
+                if (p.det)   // (a float* that holds the address of the image's int64 accumulators)
+                    g = reinterpret_cast<float*>(reinterpret_cast<long long*>(ws + p.L.detacc) +
+                                                 ((size_t)p.det_src[lane] * a.B * 3 * plane + img));
+            }
+            pc.g_src[lane] = g;
+        } else if (warp == 2 && lane < PM_MAXMAPS) {
+            S.thr[lane] = (!STATS && p.clip) ? __ldcg((const float*)(ws + p.L.pm_thr) + lane) : 3.0e38f;
         }
     }
     for (int k = tid; k < (PM_THREADS / 32) * (PH_NREC + 3); k += PM_THREADS) (&S.rec[0][0])[k] = 0.0f;
+    if (STATS)
+        for (int k = tid; k < (PM_THREADS / 32) * PM_MAXMAPS * 2; k += PM_THREADS) (&S.stat[0][0][0])[k] = 0.0;
     __syncthreads();
     const int n_src = pc.n_src, n_scales = pc.n_scales;
     const float w_e = pc.w_e / (float)n_scales;        // scales are averaged
@@ -309,11 +375,12 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
                 for (int c = 0; c < 3; ++c) S.X[i][c][k] = __ldg(pc.src[i] + (o + c * plane));
     }
     __syncthreads();
-    if (automask) pm_stage2_all<2>(S, n_src, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
+    if (automask) pm_stage2_all<2, VAR>(S, n_src, PLB_MAX_SCALES * PLB_MAX_SRC, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
     __syncthreads();
 
     float acc[NSMAX][12];
     float lsum = 0.0f;
+    float gta[3] = {0.0f, 0.0f, 0.0f};                 // IMG: d loss / d target of this thread's pixel, all scales
 #pragma unroll
     for (int i = 0; i < NSMAX; ++i)
 #pragma unroll
@@ -353,8 +420,9 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
         }
         __syncthreads();
         // ---- (2) photometric mix and min over sources per channel (separable, sliding) ------------
-        pm_stage2_all<0>(S, n_src, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
+        pm_stage2_all<0, VAR>(S, n_src, s * PLB_MAX_SRC, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
         __syncthreads();
+        if (STATS) continue;                              // the statistics pass ends here
         // ---- (2b) automask, max over channels on tile + 1 ------------------------------------------
         for (int k1 = tid; k1 < PM_N1; k1 += PM_THREADS) {
             const int ly = k1 / PM_W1, lx = k1 - ly * PM_W1;
@@ -384,6 +452,7 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
             if (qin) {
                 // d loss / d warped_i(q, c): the selected terms of the 3x3 neighbours p, by (source, channel)
                 float e[NSMAX][3];
+                float gt[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int i = 0; i < NSMAX; ++i) e[i][0] = e[i][1] = e[i][2] = 0.0f;
 #pragma unroll
@@ -394,20 +463,32 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
                         const int sel = S.sel[pk1];
                         const int sc = max(sel, 0), c = sc & 3, i = sc >> 2;
                         const float4 cf = S.coef[c][pk1];
-                        float g = fmaf(cf.y, S.X[i][c][qk2], fmaf(cf.z, S.T[c][qk2], cf.x));
+                        const float xq = S.X[i][c][qk2], tq = S.T[c][qk2];
+                        float g = fmaf(cf.y, xq, fmaf(cf.z, tq, cf.x));
+                        float gy_ = 0.0f;
+                        if (IMG) gy_ = fmaf(cf.y, tq, fmaf(cf.z, xq, S.da[c][pk1]));
                         if (border) {
                             // multiplicity of q in p's reflection-padded window
                             const int pxg = qx + dx, pyg = qy + dy;
                             const float mx = 1.0f + ((pxg == 0 && dx == -1) ? 1.0f : 0.0f) + ((pxg == W - 1 && dx == 1) ? 1.0f : 0.0f);
                             const float my = 1.0f + ((pyg == 0 && dy == -1) ? 1.0f : 0.0f) + ((pyg == H - 1 && dy == 1) ? 1.0f : 0.0f);
                             g *= mx * my;
+                            gy_ *= mx * my;
                         }
-                        if (dx == 0 && dy == 0) g += cf.w;
+                        if (dx == 0 && dy == 0) { g += cf.w; gy_ -= cf.w; }
 #pragma unroll
                         for (int ii = 0; ii < NSMAX; ++ii)
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) e[ii][cc] += (sel == cc + 4 * ii) ? g : 0.0f;
+                        if (IMG) {
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) gt[cc] += (sel >= 0 && c == cc) ? gy_ : 0.0f;
+                        }
                     }
+                if (IMG) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) gta[cc] = fmaf(w_e, gt[cc], gta[cc]);
+                }
                 D = pm_depth<HEAD>(a, pc, s, full, qx, qy, W);
                 const float xf = (float)qx, yf = (float)qy;
                 const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
@@ -437,6 +518,30 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
                         acc[i][0] = fmaf(hx, rx, acc[i][0]); acc[i][1] = fmaf(hx, ry, acc[i][1]); acc[i][2] = fmaf(hx, rz, acc[i][2]); acc[i][3] += gcx;
                         acc[i][4] = fmaf(hy, rx, acc[i][4]); acc[i][5] = fmaf(hy, ry, acc[i][5]); acc[i][6] = fmaf(hy, rz, acc[i][6]); acc[i][7] += gcy;
                         acc[i][8] = fmaf(hz, rx, acc[i][8]); acc[i][9] = fmaf(hz, ry, acc[i][9]); acc[i][10] = fmaf(hz, rz, acc[i][10]); acc[i][11] += gcz;
+                        if (IMG && pc.g_src[i] != nullptr) {
+                            // d loss / d source: e scattered through the bilinear weights (zero-padded taps get nothing)
+                            const float wnw = (1.0f - q.fx) * (1.0f - q.fy), wne = q.fx * (1.0f - q.fy);
+                            const float wsw = (1.0f - q.fx) * q.fy, wse = q.fx * q.fy;
+                            const float m = p.det ? PM_DET_ONE : w_e;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float ec = m * e[i][c];
+                                if (ec == 0.0f) continue;
+                                if (p.det) {
+                                    unsigned long long* g = reinterpret_cast<unsigned long long*>(pc.g_src[i]) + (q.o00 + c * plane);
+                                    if (q.mask & 1u) atomicAdd(g, (unsigned long long)__float2ll_rn(wnw * ec));
+                                    if (q.mask & 2u) atomicAdd(g + 1, (unsigned long long)__float2ll_rn(wne * ec));
+                                    if (q.mask & 4u) atomicAdd(g + W, (unsigned long long)__float2ll_rn(wsw * ec));
+                                    if (q.mask & 8u) atomicAdd(g + W + 1, (unsigned long long)__float2ll_rn(wse * ec));
+                                } else {
+                                    float* g = pc.g_src[i] + (q.o00 + c * plane);
+                                    if (q.mask & 1u) atomicAdd(g, wnw * ec);
+                                    if (q.mask & 2u) atomicAdd(g + 1, wne * ec);
+                                    if (q.mask & 4u) atomicAdd(g + W, wsw * ec);
+                                    if (q.mask & 8u) atomicAdd(g + W + 1, wse * ec);
+                                }
+                            }
+                        }
                     }
                 }
                 float* g = pc.g_disp[s];
@@ -448,6 +553,24 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
             }
         }
         __syncthreads();   // X / selection arrays are rewritten by the next scale
+    }
+
+    if (STATS) {
+        // ---- per-block (sum, sum of squares) of every map: fixed-order sum over the warps --------------
+        double* out = (double*)(ws + p.L.pm_stat) + ((size_t)b * p.tiles + tile) * PM_MAXMAPS * 2;
+        if (tid < PM_MAXMAPS * 2) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < PM_THREADS / 32; ++w) v += (&S.stat[w][0][0])[tid];
+            out[tid] = v;
+        }
+        return;
+    }
+    if (GRAD && IMG && qin && pc.g_tgt != nullptr) {
+        // every target pixel has exactly one owner: plain accumulation into the caller's (zeroed) buffer
+        float* g = pc.g_tgt + (qy * W + qx);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[c * plane] += gta[c];
     }
 
     // ---- block record: warp butterflies, fixed-order sum over warps --------------------------------
@@ -528,17 +651,45 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     }
 }
 
-template <bool GRAD, int NSMAX, bool HEAD>
+// Clip thresholds: one block per map sums the per-block partials in block order (fp64) and writes
+// thr = mean + clip * std (unbiased), rounded as the reference's float() of fp32 tensors rounds it (losses.py:80-82).
+constexpr int PT_THREADS = 256;
+__global__ void __launch_bounds__(PT_THREADS)
+pmin_thresholds_kernel(const __grid_constant__ PminLaunch p, int n_blocks, double n_elems, float clip) {
+    const plb_photo_args& a = p.a;
+    if (skip_launch(a.skip_if_unit)) return;
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const double* part = (const double*)((const char*)a.workspace + p.L.pm_stat);
+    __shared__ double s_a[PT_THREADS], s_b[PT_THREADS];
+    double sa = 0.0, sb = 0.0;
+    for (int k = tid; k < n_blocks; k += PT_THREADS) {
+        sa += __ldcg(part + ((size_t)k * PM_MAXMAPS + m) * 2);
+        sb += __ldcg(part + ((size_t)k * PM_MAXMAPS + m) * 2 + 1);
+    }
+    s_a[tid] = sa; s_b[tid] = sb;
+    __syncthreads();
+    for (int k = PT_THREADS / 2; k > 0; k >>= 1) {
+        if (tid < k) { s_a[tid] += s_a[tid + k]; s_b[tid] += s_b[tid + k]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double mean = s_a[0] / n_elems;
+        const double var = n_elems > 1.0 ? fmax((s_b[0] - n_elems * mean * mean) / (n_elems - 1.0), 0.0) : 0.0;
+        ((float*)((char*)a.workspace + p.L.pm_thr))[m] = (float)((float)mean + clip * (float)sqrt(var));
+    }
+}
+
+template <bool GRAD, int NSMAX, bool HEAD, int VAR>
 static int pm_launch_variant(const PminLaunch& p, dim3 grid, cudaStream_t st) {
     static bool attr_set[PLB_MAX_DEVICES] = {};
     const int dev = current_device();
     if (!attr_set[dev]) {                                    // per device: a process may drive several GPUs
-        const cudaError_t e = cudaFuncSetAttribute(photo_min_kernel<GRAD, NSMAX, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const cudaError_t e = cudaFuncSetAttribute(photo_min_kernel<GRAD, NSMAX, HEAD, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)sizeof(PminSmem));
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = true;
     }
-    photo_min_kernel<GRAD, NSMAX, HEAD><<<grid, PM_THREADS, sizeof(PminSmem), st>>>(p);
+    photo_min_kernel<GRAD, NSMAX, HEAD, VAR><<<grid, PM_THREADS, sizeof(PminSmem), st>>>(p);
     return PLB_OK;
 }
 
@@ -547,9 +698,10 @@ int photo_min_launch(const plb_photo_args* a, cudaStream_t st) {
     if (rc != PLB_OK) return rc;
     if (a->n_jobs != 1) return PLB_EINVAL;            // the dormant composition has one direction
     const plb_photo_job& job = a->jobs[0];
-    if (job.g_tgt != nullptr) return PLB_EINVAL;      // image gradients: L1 mode only
-    for (int i = 0; i < job.n_src; ++i)
-        if (job.g_src[i] != nullptr) return PLB_EINVAL;
+    bool img = a->want_grad && job.g_tgt != nullptr;
+    for (int i = 0; i < job.n_src; ++i) img = img || (a->want_grad && job.g_src[i] != nullptr);
+    const bool head = a->input_is_depth == PLB_INPUT_LOGIT;
+    if (img && head) return PLB_EINVAL;               // image gradients: disparity / depth inputs only
     PminLaunch p;
     p.a = *a;
     p.L = photo_layout(*a);
@@ -557,15 +709,35 @@ int photo_min_launch(const plb_photo_args* a, cudaStream_t st) {
     p.tiles = photo_min_tiles(*a);
     p.w_e = job.term_weight / ((float)a->B * (float)a->H * (float)a->W);
     p.C1 = 1e-4f; p.C2 = 9e-4f;
+    p.clip = (job.flags & PLB_PHOTO_CLIP) ? 1 : 0;
+    const PhotoDetSlots dslots = photo_det_slots(*a);
+    p.det = (img && dslots.n > 0) ? 1 : 0;
+    for (int i = 0; i < PLB_MAX_SRC; ++i) p.det_src[i] = dslots.src[0][i];
     dim3 grid(p.tiles, a->B);
-    const bool head = a->input_is_depth == PLB_INPUT_LOGIT;
-#define PM_GO(G, N) (head ? pm_launch_variant<G, N, true>(p, grid, st) : pm_launch_variant<G, N, false>(p, grid, st))
-    if (a->want_grad) rc = job.n_src <= 2 ? PM_GO(true, 2) : PM_GO(true, PLB_MAX_SRC);
-    else rc = job.n_src <= 2 ? PM_GO(false, 2) : PM_GO(false, PLB_MAX_SRC);
+#define PM_GO(G, N, V) (head ? pm_launch_variant<G, N, true, V>(p, grid, st) : pm_launch_variant<G, N, false, V>(p, grid, st))
+    if (p.clip) {
+        // phase A: the statistics of every map, then one threshold per map
+        rc = job.n_src <= 2 ? PM_GO(false, 2, PM_VAR_STATS) : PM_GO(false, PLB_MAX_SRC, PM_VAR_STATS);
+        if (rc != PLB_OK) return rc;
+        ++g_launches;
+        PLB_CHECK_LAUNCH();
+        pmin_thresholds_kernel<<<PM_MAXMAPS, PT_THREADS, 0, st>>>(p, p.tiles * a->B, (double)a->B * 3.0 * a->H * a->W, job.clip_loss);
+        ++g_launches;
+        PLB_CHECK_LAUNCH();
+    }
+    if (img) rc = job.n_src <= 2 ? pm_launch_variant<true, 2, false, PM_VAR_IMG>(p, grid, st)
+                                 : pm_launch_variant<true, PLB_MAX_SRC, false, PM_VAR_IMG>(p, grid, st);
+    else if (a->want_grad) rc = job.n_src <= 2 ? PM_GO(true, 2, PM_VAR_MAIN) : PM_GO(true, PLB_MAX_SRC, PM_VAR_MAIN);
+    else rc = job.n_src <= 2 ? PM_GO(false, 2, PM_VAR_MAIN) : PM_GO(false, PLB_MAX_SRC, PM_VAR_MAIN);
 #undef PM_GO
     if (rc != PLB_OK) return rc;
     ++g_launches;
     PLB_CHECK_LAUNCH();
+    if (p.det) {
+        // one accumulator count = 2^-24 of (w_e / n_scales) x upstream (the upstream is applied by the conversion)
+        rc = photo_det_convert_launch(*a, p.L, p.w_e / (float)job.n_scales / PM_DET_ONE, st);
+        if (rc != PLB_OK) return rc;
+    }
     if (photo_has_lowres_grad(*a)) {
         PhotoLaunch pl;
         pl.a = *a;

@@ -98,7 +98,7 @@ class LossConfig:
 
     def __init__(self, n_src, scales_per_frame, input_is_depth=False, do_photo=True, do_smooth=True,
                  rotation_mode="axisangle", fused_backward=True, disp_a=10.0, disp_b=0.01, scale_decay=2.3,
-                 mode=_lib.PHOTO_L1_MEAN, flags=0, disp_head=None, deterministic=None):
+                 mode=_lib.PHOTO_L1_MEAN, flags=0, disp_head=None, deterministic=None, clip_loss=None):
         self.n_src = n_src
         self.scales_per_frame = list(scales_per_frame)  # e.g. [4, 4]: frames with a depth pyramid
         self.input_is_depth = bool(input_is_depth)
@@ -107,6 +107,10 @@ class LossConfig:
         self.fused_backward = fused_backward
         self.disp_a, self.disp_b, self.scale_decay = disp_a, disp_b, scale_decay
         self.mode, self.flags = mode, flags
+        # PHOTO_MIN_REPROJ: clamp every photometric map at mean + clip_loss * std (losses.py:79-82); None = no clamp
+        self.clip_loss = None if clip_loss is None else float(clip_loss)
+        if self.clip_loss is not None:
+            self.flags |= _lib.PHOTO_CLIP
         # image gradients through order-independent fixed-point accumulation (everything else is always repeatable);
         # None follows torch.use_deterministic_algorithms()
         self.deterministic = torch.are_deterministic_algorithms_enabled() if deterministic is None else bool(deterministic)
@@ -175,6 +179,7 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
                 job.g_disp[s] = _ptr(g_pyr[j][s]) if (want_grad and g_pyr is not None) else 0
             job.term_weight = 1.0 if cfg.mode == _lib.PHOTO_MIN_REPROJ else 1.0 / (entries * job.n_src)
             job.mode, job.flags = cfg.mode, cfg.flags
+            job.clip_loss = cfg.clip_loss if cfg.clip_loss is not None else 0.0
         nbytes = lib.plb_photo_workspace_bytes(a)
         ws_photo = _workspace("photo", nbytes, dev)
         a.workspace, a.workspace_bytes = ws_photo.data_ptr(), ws_photo.numel()
@@ -246,8 +251,6 @@ class FusedLossFn(torch.autograd.Function):
         pyr = [[_f32c(d) for d in p] for p in pyr]
         need = ctx.needs_input_grad
         img_grad = need[1] or any(need[4:4 + cfg.n_src])
-        if img_grad and cfg.mode == _lib.PHOTO_MIN_REPROJ:
-            raise NotImplementedError("image gradients are implemented for the live L1 loss only")
         any_grad = img_grad or need[2] or any(need[4 + cfg.n_src:])
         fused = any_grad and cfg.fused_backward and not img_grad
         both = cfg.do_photo and cfg.do_smooth
