@@ -90,3 +90,15 @@ def test_integration_stub_matches_the_abi(L):
     assert C.sizeof(ns["Job"]) == C.sizeof(L.PhotoJob)
     assert C.sizeof(ns["Args"]) == C.sizeof(L.PhotoArgs)
     assert [f[0] for f in ns["Args"]._fields_] == [f[0] for f in L.PhotoArgs._fields_]
+
+
+def test_torch_binding_loads_and_refuses_cpu_tensors(L):
+    """The thin torch C++ binding (csrc/torch_binding.cpp) is built in-tree, links the same libplb200.so, and has no
+    CPU path either (both bindings are checked: the default one and the ctypes one)."""
+    from plb200 import ops, synth, _tb
+    assert _tb.mod is not None and os.path.isfile(_tb.PATH)
+    assert _tb.mod.version() == L.version()
+    inp = synth.make_photo_inputs(1, 8, 16)
+    for binding in ("torch", "ctypes"):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ops.fused_losses(inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"], binding=binding)

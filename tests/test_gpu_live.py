@@ -232,3 +232,54 @@ def test_reprojection_and_smooth_individually():
     assert abs(float(ls) - float(rs)) <= LOSS_TOL * abs(float(rs))
     for a, b in zip(gd[0] + gd[1], rd[0] + rd[1]):
         assert rel_err(a.grad.cpu(), b.grad) < GRAD_TOL
+
+
+@pytest.mark.parametrize("image_grads,upstream", [(False, (1.0, 1.0)), (False, (0.7, 2.5)), (True, (1.0, 1.0))])
+def test_torch_binding_matches_ctypes(image_grads, upstream):
+    """The torch C++ binding (csrc/torch_binding.cpp) and the ctypes binding (ops.FusedLossFn) drive the same C ABI:
+    identical losses and gradients, bit for bit (image gradients: float atomics, so to rounding)."""
+    from plb200 import ops, synth, _tb
+    assert _tb.mod is not None, "the torch C++ binding must be built (plb200/build.py --torch)"
+    inp = synth.make_photo_inputs(3, 64, 96, n_src=2, n_scales=3, seed=21)
+    dev = _dev()
+    res = []
+    for binding in ("ctypes", "torch"):
+        tgt = inp["tgt"].to(dev).requires_grad_(image_grads)
+        refs = [r.to(dev).requires_grad_(image_grads) for r in inp["ref_imgs"]]
+        disp = [[d.to(dev).requires_grad_(True) for d in fr] for fr in inp["disparity"]]
+        p = inp["poses"].to(dev).requires_grad_(True)
+        loss = ops.fused_losses(tgt, refs, disp, p, inp["intrinsics"].to(dev), binding=binding)
+        (upstream[0] * loss[0] + upstream[1] * loss[1]).backward()
+        res.append((loss, p.grad, [d.grad for fr in disp for d in fr], [tgt.grad] + [r.grad for r in refs]))
+    (l0, p0, d0, i0), (l1, p1, d1, i1) = res
+    assert torch.equal(l0[0], l1[0]) and torch.equal(l0[1], l1[1]) and torch.equal(p0, p1)
+    for a, b in zip(d0, d1):
+        assert torch.equal(a, b)
+    if image_grads:
+        for a, b in zip(i0, i1):
+            assert rel_err(a, b) < 1e-6
+    # forward only
+    with torch.no_grad():
+        l2 = ops.fused_losses(inp["tgt"].to(dev), [r.to(dev) for r in inp["ref_imgs"]],
+                              [[d.to(dev) for d in fr] for fr in inp["disparity"]], inp["poses"].to(dev),
+                              inp["intrinsics"].to(dev), binding="torch")
+    assert torch.equal(l2[0], l0[0]) and not l2[0].requires_grad
+
+
+def test_torch_binding_backward_twice_and_errors():
+    """retain_graph: the second backward recomputes (the forward's buffers went to autograd with the first); a CPU
+    tensor raises instead of falling back."""
+    from plb200 import ops, synth
+    inp = synth.make_photo_inputs(2, 32, 64, n_src=2, n_scales=2, seed=5)
+    dev = _dev()
+    disp = [[d.to(dev).requires_grad_(True) for d in fr] for fr in inp["disparity"]]
+    p = inp["poses"].to(dev).requires_grad_(True)
+    loss = ops.fused_losses(inp["tgt"].to(dev), [r.to(dev) for r in inp["ref_imgs"]], disp, p, inp["intrinsics"].to(dev),
+                            binding="torch")
+    sum(loss).backward(retain_graph=True)
+    g1 = p.grad.clone()
+    p.grad = None
+    sum(loss).backward()
+    assert torch.equal(g1, p.grad)
+    with pytest.raises(RuntimeError):
+        ops.fused_losses(inp["tgt"], [r.to(dev) for r in inp["ref_imgs"]], disp, p, inp["intrinsics"].to(dev), binding="torch")

@@ -53,5 +53,36 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TORCH_LIB = os.path.join(HERE, "_plb200_torch.so")
+
+
+def build_torch(force=False):
+    """The thin torch C++ binding (csrc/torch_binding.cpp): plain g++ against torch's headers, linked to
+    libplb200.so beside it ($ORIGIN).  Host code only - the kernels live in libplb200.so."""
+    src = os.path.join(CSRC, "torch_binding.cpp")
+    deps = [src, os.path.join(ROOT, "include", "plb200.h"), __file__]
+    if not force and os.path.isfile(TORCH_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(TORCH_LIB) for d in deps):
+        return TORCH_LIB
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    tlib = ce.library_paths()[0]
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", TORCH_LIB,
+           "-DTORCH_EXTENSION_NAME=_plb200_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           "-I", os.path.join(ROOT, "include"), "-I", sysconfig.get_paths()["include"], "-I", os.path.join(cuda_home, "include")]
+    for inc in ce.include_paths():
+        cmd += ["-isystem", inc]
+    cmd += ["-L", tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+            "-L", HERE, "-l:libplb200.so", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + tlib, "-Wno-attributes"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("torch binding failed to build:\n" + out.stdout[-4000:])
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--torch" in sys.argv:
+        print(build_torch(force="--force" in sys.argv))

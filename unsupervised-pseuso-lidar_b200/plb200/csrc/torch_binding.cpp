@@ -1,0 +1,339 @@
+// Thin torch C++ binding over the C ABI (include/plb200.h) for the hot public call:
+//     Losses.forward(tgt, ref_imgs, disparity, poses, intrinsics, gt)  +  sum(loss).backward()
+// (`/root/reference` trainer.py:312,264).  Same semantics as the ctypes path of plb200/ops.py (FusedLossFn), which
+// stays as the portable binding and the one the parity tests can cross-check against; this one exists because an
+// eager trainer pays the HOST cost of every step: ctypes struct marshalling, a Python autograd.Function and a dozen
+// Python-level allocations cost ~250 us per c2 step against 213 us of GPU work.  Here the argument structs are plain
+// C++ structs, the autograd node is a torch::autograd::Function, and nothing allocates beyond the gradient buffers.
+//
+// torch is plumbing: device memory (at::empty), the current stream, the autograd graph.  Every computation is a
+// libplb200.so kernel; a non-zero return code becomes a C++ exception (-> Python RuntimeError), mirroring how the
+// reference surfaces errors.
+//
+// Gradient strategy (DESIGN.md "single-pass forward+backward"): with gradients needed the forward launch also writes
+// them for a unit upstream; backward() relaunches the same launches with the real upstream scalars behind the
+// device-side "all upstream == 1" guard (they return at once for sum(loss).backward()).
+#include <torch/extension.h>
+#include <c10/cuda/CUDAStream.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "plb200.h"
+
+namespace {
+
+using torch::Tensor;
+using torch::autograd::AutogradContext;
+using torch::autograd::variable_list;
+
+struct Cfg {
+    int n_src = 2;
+    std::vector<int64_t> scales;     // scales per frame that carries a pyramid
+    int input_kind = PLB_INPUT_DISP;
+    bool do_photo = true, do_smooth = true;
+    int rotation_mode = PLB_ROT_AXISANGLE;
+    bool fused_backward = true;
+    float disp_a = 10.0f, disp_b = 0.01f, scale_decay = 2.3f;
+    int mode = PLB_PHOTO_L1_MEAN;
+    uint32_t flags = 0;
+    float head_alpha = 0.0f, head_beta = 0.0f;
+    bool deterministic = false;
+    float clip_loss = 0.0f;
+    int sm_limit = 0;
+};
+
+void check(int rc, const char* what) {
+    if (rc == 0) return;
+    const char* msg = rc == PLB_EINVAL ? "PLB_EINVAL: bad shape / count / flag"
+                    : rc == PLB_ENULL ? "PLB_ENULL: a required pointer is NULL"
+                    : rc == PLB_EWORKSPACE ? "PLB_EWORKSPACE: workspace missing or too small" : nullptr;
+    if (msg) TORCH_CHECK(false, what, ": ", msg);
+    TORCH_CHECK(false, what, ": CUDA error ", rc);
+}
+
+// zero-filled once, then self-cleaning (the kernels reset their tickets); one buffer per (op, device, stream)
+Tensor workspace(int tag, size_t nbytes, const torch::Device& dev, cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, uintptr_t>, Tensor> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_tuple(tag, (int)dev.index(), (uintptr_t)st);
+    auto it = cache.find(key);
+    if (it == cache.end() || (size_t)it->second.numel() < nbytes) {
+        Tensor buf = torch::zeros({(int64_t)std::max<size_t>(nbytes, 256)}, torch::TensorOptions().dtype(torch::kUInt8).device(dev));
+        cache[key] = buf;
+        return buf;
+    }
+    return it->second;
+}
+
+float* fptr(const Tensor& t) { return t.defined() ? t.data_ptr<float>() : nullptr; }
+
+Tensor f32c(const Tensor& t) {
+    Tensor r = t.scalar_type() == torch::kFloat32 ? t : t.to(torch::kFloat32);
+    return r.contiguous();
+}
+
+// what one call needs to stay alive / be relaunched
+struct State : torch::CustomClassHolder {
+    Cfg cfg;
+    Tensor tgt, poses, K;
+    std::vector<Tensor> refs;
+    std::vector<std::vector<Tensor>> pyr, g_pyr;
+    Tensor g_poses;
+    plb_photo_args a;
+    plb_smooth_args s;
+    cudaStream_t st = nullptr;
+    Tensor ws_photo, ws_smooth;
+    bool fused = false, img_grad = false, used = false, have_args = false;
+    std::vector<bool> need;
+};
+
+// One photometric launch (all directions) + one smoothness launch - plb200/ops.py::_launch_loss.
+void launch_loss(State& S, bool want_grad, const std::vector<std::vector<Tensor>>* g_pyr, const Tensor& g_poses,
+                 const Tensor& g_tgt, const std::vector<Tensor>* g_refs, float* out, const float* up0, const float* up1,
+                 bool skip) {
+    const Cfg& cfg = S.cfg;
+    const int64_t B = S.tgt.size(0), H = S.tgt.size(2), W = S.tgt.size(3);
+    const torch::Device dev = S.tgt.device();
+    cudaStream_t st = c10::cuda::getCurrentCUDAStream(dev.index()).stream();
+    S.st = st;
+    if (cfg.do_photo) {
+        plb_photo_args& a = S.a;
+        a = plb_photo_args();
+        a.B = (int)B; a.H = (int)H; a.W = (int)W;
+        a.n_pose = (int)S.poses.size(1);
+        a.rotation_mode = cfg.rotation_mode;
+        a.k_is_f64 = S.K.scalar_type() == torch::kFloat64 ? 1 : 0;
+        a.input_is_depth = cfg.input_kind;
+        a.disp_a = cfg.disp_a; a.disp_b = cfg.disp_b;
+        a.head_alpha = cfg.head_alpha; a.head_beta = cfg.head_beta;
+        a.want_grad = want_grad ? 1 : 0;
+        a.deterministic = cfg.deterministic ? 1 : 0;
+        a.sm_limit = cfg.sm_limit;
+        a.poses = S.poses.data_ptr<float>();
+        a.K = S.K.data_ptr();
+        a.g_poses = want_grad ? fptr(g_poses) : nullptr;
+        a.loss = out;
+        a.upstream = up0;
+        if (skip) { a.skip_if_unit[0] = up0; a.skip_if_unit[1] = up1; }
+        const int n_jobs = (int)S.pyr.size();
+        a.n_jobs = n_jobs;
+        size_t entries = 0;
+        for (auto& p : S.pyr) entries += p.size();
+        for (int j = 0; j < n_jobs; ++j) {
+            plb_photo_job& job = a.jobs[j];
+            if (j == 0) {
+                job.tgt = S.tgt.data_ptr<float>();
+                job.n_src = (int)S.refs.size();
+                for (int i = 0; i < job.n_src; ++i) {
+                    job.src[i] = S.refs[i].data_ptr<float>();
+                    job.pose_index[i] = i;
+                    job.pose_inv[i] = 0;
+                    job.g_src[i] = (want_grad && g_refs) ? fptr((*g_refs)[i]) : nullptr;
+                }
+                job.g_tgt = want_grad ? fptr(g_tgt) : nullptr;
+            } else {
+                // losses.py:199-203: target = refs[indx], source = [tgt], pose = poses[indx-1] inverted
+                job.tgt = S.refs[j].data_ptr<float>();
+                job.n_src = 1;
+                job.src[0] = S.tgt.data_ptr<float>();
+                job.pose_index[0] = j - 1;
+                job.pose_inv[0] = 1;
+                job.g_src[0] = want_grad ? fptr(g_tgt) : nullptr;
+                job.g_tgt = (want_grad && g_refs) ? fptr((*g_refs)[j]) : nullptr;
+            }
+            job.n_scales = (int)S.pyr[j].size();
+            for (int s = 0; s < job.n_scales; ++s) {
+                const Tensor& d = S.pyr[j][s];
+                job.disp[s] = d.data_ptr<float>();
+                job.dh[s] = (int)d.size(-2); job.dw[s] = (int)d.size(-1);
+                job.g_disp[s] = (want_grad && g_pyr) ? fptr((*g_pyr)[j][s]) : nullptr;
+            }
+            job.term_weight = cfg.mode == PLB_PHOTO_MIN_REPROJ ? 1.0f : 1.0f / (float)(entries * job.n_src);
+            job.mode = cfg.mode; job.flags = cfg.flags; job.clip_loss = cfg.clip_loss;
+        }
+        const size_t nbytes = plb_photo_workspace_bytes(&a);
+        S.ws_photo = workspace(0, nbytes, dev, st);
+        a.workspace = S.ws_photo.data_ptr();
+        a.workspace_bytes = (size_t)S.ws_photo.numel();
+        check(plb_photo_loss(&a, st), "plb_photo_loss");
+    }
+    if (cfg.do_smooth) {
+        plb_smooth_args& s = S.s;
+        s = plb_smooth_args();
+        s.B = (int)B;
+        s.n_scales = (int)S.pyr[0].size();
+        for (int k = 0; k < s.n_scales; ++k) {
+            const Tensor& d = S.pyr[0][k];
+            s.disp[k] = d.data_ptr<float>();
+            s.dh[k] = (int)d.size(-2); s.dw[k] = (int)d.size(-1);
+            s.g_disp[k] = (want_grad && g_pyr) ? fptr((*g_pyr)[0][k]) : nullptr;
+        }
+        s.accumulate = cfg.do_photo ? 1 : 0;
+        s.input_is_depth = cfg.input_kind;
+        s.disp_a = cfg.disp_a; s.disp_b = cfg.disp_b; s.scale_decay = cfg.scale_decay;
+        s.head_alpha = cfg.head_alpha; s.head_beta = cfg.head_beta;
+        s.want_grad = want_grad ? 1 : 0;
+        s.loss = out + 1;
+        s.upstream = up1;
+        if (skip) { s.skip_if_unit[0] = up0; s.skip_if_unit[1] = up1; }
+        const size_t nbytes = plb_smooth_workspace_bytes(&s);
+        S.ws_smooth = workspace(1, nbytes, dev, st);
+        s.workspace = S.ws_smooth.data_ptr();
+        s.workspace_bytes = (size_t)S.ws_smooth.numel();
+        check(plb_smooth_loss(&s, st), "plb_smooth_loss");
+    }
+    S.have_args = true;
+}
+
+std::vector<std::vector<Tensor>> alloc_like(const std::vector<std::vector<Tensor>>& pyr, bool do_photo) {
+    std::vector<std::vector<Tensor>> g(pyr.size());
+    for (size_t j = 0; j < pyr.size(); ++j)
+        for (auto& d : pyr[j])   // without the photometric part only frame 0 is written: the others are zero
+            g[j].push_back((!do_photo && j > 0) ? torch::zeros_like(d) : torch::empty_like(d));
+    return g;
+}
+
+// inputs: tgt, poses, K, ref_0 .. ref_{n-1}, disparity tensors frame-major
+struct FusedLoss : public torch::autograd::Function<FusedLoss> {
+    static variable_list forward(AutogradContext* ctx, at::TensorList inputs, c10::intrusive_ptr<State> S) {
+        const Cfg& cfg = S->cfg;
+        const int n_in = (int)inputs.size();
+        for (const Tensor& t : inputs)
+            TORCH_CHECK(t.is_cuda(), "plb200 ops need CUDA tensors (no CPU fallback); got a ", t.device().type(), " tensor");
+        const int cur = c10::cuda::current_device();
+        for (const Tensor& t : inputs) {
+            TORCH_CHECK(t.device().index() == cur, "plb200 ops launch on the current device (cuda:", cur, ") but got a tensor on ",
+                        t.device(), "; wrap the call in `with torch.cuda.device(t.device):`");
+        }
+        S->tgt = f32c(inputs[0]);
+        S->poses = f32c(inputs[1]);
+        {
+            const Tensor& K = inputs[2];
+            S->K = (K.scalar_type() == torch::kFloat64 || K.scalar_type() == torch::kFloat32 ? K : K.to(torch::kFloat64)).contiguous();
+        }
+        for (int i = 0; i < cfg.n_src; ++i) S->refs.push_back(f32c(inputs[3 + i]));
+        int k = 3 + cfg.n_src;
+        for (int64_t n : cfg.scales) {
+            std::vector<Tensor> fr;
+            for (int64_t q = 0; q < n; ++q) fr.push_back(f32c(inputs[k++]));
+            S->pyr.push_back(std::move(fr));
+        }
+        TORCH_CHECK(k == n_in, "fused_losses: expected ", k, " tensors, got ", n_in);
+        TORCH_CHECK((int)S->need.size() == n_in, "fused_losses: internal (need)");
+        (void)ctx;
+        bool img_grad = S->need[0];
+        for (int i = 0; i < cfg.n_src; ++i) img_grad = img_grad || S->need[3 + i];
+        bool any_grad = img_grad || S->need[1];
+        for (int i = 3 + cfg.n_src; i < n_in; ++i) any_grad = any_grad || S->need[i];
+        const bool fused = any_grad && cfg.fused_backward && !img_grad;
+        const bool both = cfg.do_photo && cfg.do_smooth;
+        auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(S->tgt.device());
+        Tensor out = both ? torch::empty({2}, fopt) : torch::zeros({2}, fopt);
+        if (fused) {
+            S->g_pyr = alloc_like(S->pyr, cfg.do_photo);
+            S->g_poses = cfg.do_photo ? torch::empty_like(S->poses) : torch::zeros_like(S->poses);
+        }
+        launch_loss(*S, fused, fused ? &S->g_pyr : nullptr, S->g_poses, Tensor(), nullptr, out.data_ptr<float>(), nullptr,
+                    nullptr, false);
+        S->fused = fused; S->img_grad = img_grad;
+        ctx->saved_data["state"] = c10::IValue::make_capsule(c10::intrusive_ptr<torch::CustomClassHolder>(S));
+        return {out[0], out[1]};
+    }
+
+    static variable_list backward(AutogradContext* ctx, variable_list grads) {
+        auto S = c10::static_intrusive_pointer_cast<State>(ctx->saved_data["state"].toCapsule());
+        const Cfg& cfg = S->cfg;
+        auto fopt = torch::TensorOptions().dtype(torch::kFloat32).device(S->tgt.device());
+        c10::cuda::CUDAGuard guard(S->tgt.device());
+        Tensor up[2];
+        const bool active[2] = {cfg.do_photo, cfg.do_smooth};
+        for (int i = 0; i < 2; ++i) {
+            if (!active[i]) continue;
+            up[i] = grads[i].defined() ? grads[i].detach().to(torch::kFloat32).reshape({}).contiguous() : torch::zeros({}, fopt);
+        }
+        const float* up0 = up[0].defined() ? up[0].data_ptr<float>() : nullptr;
+        const float* up1 = up[1].defined() ? up[1].data_ptr<float>() : nullptr;
+        std::vector<std::vector<Tensor>> g_pyr;
+        Tensor g_poses, g_tgt;
+        std::vector<Tensor> g_refs;
+        bool skip;
+        if (S->fused && !S->used) {
+            // first backward: the buffers written by the forward launch are handed to autograd
+            skip = true;
+            S->used = true;
+            g_pyr = std::move(S->g_pyr);
+            g_poses = std::move(S->g_poses);
+        } else {
+            skip = false;
+            g_pyr = alloc_like(S->pyr, cfg.do_photo);
+            g_poses = cfg.do_photo ? torch::empty_like(S->poses) : torch::zeros_like(S->poses);
+            if (S->img_grad) {
+                g_tgt = torch::zeros_like(S->tgt);
+                for (auto& r : S->refs) g_refs.push_back(torch::zeros_like(r));
+            }
+        }
+        Tensor scratch = torch::empty({2}, fopt);
+        cudaStream_t st = c10::cuda::getCurrentCUDAStream(S->tgt.device().index()).stream();
+        if (skip && S->have_args && st == S->st) {
+            // the SAME launches again (same buffers, same stream, same workspaces) behind the device-side guard
+            if (cfg.do_photo) {
+                S->a.want_grad = 1;
+                S->a.loss = scratch.data_ptr<float>(); S->a.upstream = up0;
+                S->a.skip_if_unit[0] = up0; S->a.skip_if_unit[1] = up1;
+                check(plb_photo_loss(&S->a, st), "plb_photo_loss");
+            }
+            if (cfg.do_smooth) {
+                S->s.want_grad = 1;
+                S->s.loss = scratch.data_ptr<float>() + 1; S->s.upstream = up1;
+                S->s.skip_if_unit[0] = up0; S->s.skip_if_unit[1] = up1;
+                check(plb_smooth_loss(&S->s, st), "plb_smooth_loss");
+            }
+        } else {
+            launch_loss(*S, true, &g_pyr, g_poses, g_tgt, S->img_grad ? &g_refs : nullptr, scratch.data_ptr<float>(), up0, up1, skip);
+        }
+        S->have_args = false;
+        // the gradient buffers leave with autograd (AccumulateGrad adopts a buffer nobody else holds)
+        const std::vector<bool>& need = S->need;
+        variable_list res;
+        res.reserve(need.size() + 1);
+        res.push_back(need[0] ? g_tgt : Tensor());
+        res.push_back(need[1] ? g_poses : Tensor());
+        res.push_back(Tensor());
+        for (int i = 0; i < cfg.n_src; ++i) res.push_back((need[3 + i] && !g_refs.empty()) ? g_refs[i] : Tensor());
+        size_t k = 3 + cfg.n_src;
+        for (auto& fr : g_pyr)
+            for (auto& g : fr) { res.push_back(need[k] ? std::move(g) : Tensor()); ++k; }
+        res.push_back(Tensor());       // the State argument
+        return res;
+    }
+};
+
+std::vector<Tensor> fused_losses(std::vector<Tensor> inputs, int64_t n_src, std::vector<int64_t> scales, int64_t input_kind,
+                                 bool do_photo, bool do_smooth, int64_t rotation_mode, bool fused_backward, double disp_a,
+                                 double disp_b, double scale_decay, int64_t mode, int64_t flags, double head_alpha,
+                                 double head_beta, bool deterministic, double clip_loss, int64_t sm_limit) {
+    auto S = c10::make_intrusive<State>();
+    Cfg& c = S->cfg;
+    c.n_src = (int)n_src; c.scales = std::move(scales); c.input_kind = (int)input_kind;
+    c.do_photo = do_photo; c.do_smooth = do_smooth; c.rotation_mode = (int)rotation_mode; c.fused_backward = fused_backward;
+    c.disp_a = (float)disp_a; c.disp_b = (float)disp_b; c.scale_decay = (float)scale_decay;
+    c.mode = (int)mode; c.flags = (uint32_t)flags; c.head_alpha = (float)head_alpha; c.head_beta = (float)head_beta;
+    c.deterministic = deterministic; c.clip_loss = (float)clip_loss; c.sm_limit = (int)sm_limit;
+    // which inputs want a gradient (asked here: grad mode is switched off inside forward())
+    const bool grad_on = at::GradMode::is_enabled();
+    for (const Tensor& t : inputs) S->need.push_back(grad_on && t.defined() && t.requires_grad());
+    return FusedLoss::apply(at::TensorList(inputs), S);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.doc() = "torch C++ binding of libplb200.so's fused loss (Losses.forward + backward)";
+    m.def("fused_losses", &fused_losses, "fused photometric + smoothness loss with autograd (C ABI: plb_photo_loss, plb_smooth_loss)");
+    m.def("version", []() { return std::string(plb_version()); });
+}

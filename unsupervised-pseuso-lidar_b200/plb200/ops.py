@@ -319,10 +319,22 @@ class FusedLossFn(torch.autograd.Function):
         return tuple(grads)
 
 
-def fused_losses(tgt, refs, pyramids, poses, K, **cfg_kw):
-    """pyramids: list[frame] of list[scale] of [B,1,h,w].  Returns (loss_mam, loss_smooth)."""
+def fused_losses(tgt, refs, pyramids, poses, K, binding=None, **cfg_kw):
+    """pyramids: list[frame] of list[scale] of [B,1,h,w].  Returns (loss_mam, loss_smooth).
+    binding: "torch" = the C++ torch binding (csrc/torch_binding.cpp: autograd node and argument structs in C++),
+    "ctypes" = FusedLossFn above; None = the C++ one when it is built.  Same C ABI, same kernels, same results."""
     cfg = LossConfig(len(refs), [len(p) for p in pyramids], **cfg_kw)
     flat = [d for p in pyramids for d in p]
+    from . import _tb
+    if binding == "torch" and _tb.mod is None:
+        raise RuntimeError("the torch C++ binding is not built (plb200/build.py --torch)")
+    if binding != "ctypes" and _tb.mod is not None:
+        head = cfg.disp_head or (0.0, 0.0)
+        out = _tb.mod.fused_losses([tgt, poses, K, *refs, *flat], cfg.n_src, cfg.scales_per_frame, cfg.input_kind,
+                                   cfg.do_photo, cfg.do_smooth, cfg.rotation_mode, cfg.fused_backward, cfg.disp_a,
+                                   cfg.disp_b, cfg.scale_decay, cfg.mode, cfg.flags, head[0], head[1],
+                                   cfg.deterministic, cfg.clip_loss or 0.0, _sm_limit)
+        return out[0], out[1]
     return FusedLossFn.apply(cfg, tgt, poses, K, *refs, *flat)
 
 
