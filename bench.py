@@ -483,6 +483,7 @@ def run_ours(args, cfg):
         if world == 1 and not args.no_cloud:
             cloud = time_cloud(dev)
             cloud["frac"] = cloud["achieved_gbs"] / peak
+            cloud["f32_pointcloud2"]["frac"] = cloud["f32_pointcloud2"]["achieved_gbs"] / peak
             velo = time_velo(dev)
             velo["frac"] = velo["achieved_gbs"] / peak
         line = {
@@ -568,32 +569,64 @@ def time_photo_kernel(criterion, gpu_sets, cfg, dev, iters):
 
 
 def time_cloud(dev, B=32, H=375, W=1242, iters=20):
-    """Config C4 (BASELINE.json configs[3]): depth -> pseudo-LiDAR back-projection, fp64 parity layout.
-    Returns Mpix/s, kept points, and the HBM fraction on the algorithmic bytes of SURVEY.md section 8(d):
-    4 B/px read + 32 B per kept point."""
+    """Config C4 (BASELINE.json configs[3]): depth -> pseudo-LiDAR back-projection.  The headline numbers are the fp64
+    x,y,z,0 parity layout; `f32` is the PointCloud2 wire layout the reference publishes (PseudoLidarPipeline.py:51-54,
+    16 B per point) written by the same kernel; `e2e` is project_batch with HOST buffers: pinned depth in, counts and
+    only the kept rows of the cloud out.  HBM fraction on the algorithmic bytes of SURVEY.md section 8(d): 4 B/px read
+    + 32 (16) B per kept point."""
     import tempfile
     from plb200 import synth
     from utils.PseudoLiDAR import PseudoLiDAR
     with tempfile.TemporaryDirectory() as d:
         pl = PseudoLiDAR(synth.write_kitti_calib(d), 0, device=dev)
     sets = [synth.make_depth_images(B, H, W, seed=40 + k).to(dev) for k in range(3)]   # 3 x 60 MB in, 3 x 477 MB out > L2
-    outs = [pl.project_batch(s) for s in sets]
-    torch.cuda.synchronize()
-    kept = int(outs[0]["count"].sum())
     st = torch.cuda.current_stream()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    del outs
-    e0.record(st)
-    for i in range(iters):
-        pl.project_batch(sets[i % len(sets)])
-    e1.record(st)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
     px = B * H * W
-    abytes = 4.0 * px + 32.0 * kept
-    return {"workload": "c4: %dx%d depth -> pseudo-LiDAR, batch %d, f64 x,y,z,0 parity layout" % (H, W, B),
-            "ms": ms, "mpix_s": px / 1e6 / (ms / 1e3), "kept_points": kept, "algorithmic_bytes": abytes,
-            "achieved_gbs": abytes / (ms / 1e3) / 1e9}
+    res = {}
+    for layout, want, bpp in (("f64", dict(want_f64=True), 32.0), ("f32", dict(want_f64=False, want_f32=True), 16.0)):
+        outs = [pl.project_batch(s, **want) for s in sets]
+        torch.cuda.synchronize()
+        kept = int(outs[0]["count"].sum())
+        del outs
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for i in range(iters):
+            pl.project_batch(sets[i % len(sets)], **want)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        abytes = 4.0 * px + bpp * kept
+        res[layout] = {"ms": ms, "mpix_s": px / 1e6 / (ms / 1e3), "kept_points": kept, "algorithmic_bytes": abytes,
+                       "achieved_gbs": abytes / (ms / 1e3) / 1e9}
+    # end to end with host buffers (fp64 parity layout): H2D of the depth batch, the two launches, D2H of the counts
+    # (the output size is data dependent: one sync) and of the kept rows of every image
+    host_in = [s.cpu().pin_memory() for s in sets]
+    host_out = torch.empty(B * H * W, 4, dtype=torch.float64).pin_memory()
+    dbuf = torch.empty_like(sets[0])
+
+    def e2e_once(i):
+        dbuf.copy_(host_in[i % len(host_in)], non_blocking=True)
+        r = pl.project_batch(dbuf)
+        counts = r["count"].cpu()
+        o = 0
+        for b in range(B):
+            n = int(counts[b])
+            host_out[o:o + n].copy_(r["cloud_f64"][b, :n], non_blocking=True)
+            o += n
+        torch.cuda.synchronize()
+        return o
+    e2e_once(0)
+    t0 = time.perf_counter()
+    n_e2e = 5
+    for i in range(n_e2e):
+        rows = e2e_once(i)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    out = {"workload": "c4: %dx%d depth -> pseudo-LiDAR, batch %d, f64 x,y,z,0 parity layout" % (H, W, B)}
+    out.update(res["f64"])
+    out["f32_pointcloud2"] = res["f32"]
+    out["e2e"] = {"ms": e2e_ms, "mpix_s": px / 1e6 / (e2e_ms / 1e3), "h2d_bytes": 4 * px, "d2h_bytes": 32 * rows + 4 * B,
+                  "note": "pinned host depth in, counts + kept rows (f64) out, wall clock incl. the count sync"}
+    return out
 
 
 def time_velo(dev, B=32, N=123577, H=375, W=1242, iters=20):

@@ -53,6 +53,7 @@ def _check_grad(ours, golden, exact, what):
     same formulas: a bilinear sample that fp32 rounding puts on the other side of a pixel boundary
     (measured: e32 = 1.3e-4 on the pose gradients of live_b4_s4_32x64, <= 1e-5 elsewhere)."""
     e32 = rel_err(golden, exact)
+    print(what, "rel err vs fp64: ours %.2e, golden (fp32 reference) %.2e" % (rel_err(ours, exact), e32))
     assert rel_err(ours, exact) < max(GRAD_TOL, 2 * e32), (what, e32)
     assert rel_err(ours, golden) < max(GRAD_TOL, 2 * e32), (what, e32)
 
@@ -123,6 +124,7 @@ def test_oracle_parity_odd_shapes(B, H, W, S, regime, noise):
 
     def check(ours, r32, r64, what):
         e32 = rel_err(r32, r64)
+        print(what, "rel err vs fp64: ours %.2e, fp32 reference %.2e" % (rel_err(ours, r64), e32))
         assert rel_err(ours, r64) < max(GRAD_TOL, 3 * e32), (what, e32)
         assert rel_err(ours, r32) < max(GRAD_TOL, 4 * e32), (what, e32)
 
@@ -136,6 +138,7 @@ def test_oracle_parity_odd_shapes(B, H, W, S, regime, noise):
         scale = float(r64.abs().max())
         bad_ours = int(((ours.double() - r64).abs() > GRAD_TOL * scale).sum())
         bad_ref = int(((r32.double() - r64).abs() > GRAD_TOL * scale).sum())
+        print(what, "%d of %d elements beyond 1e-4 of the map's scale (fp32 reference: %d)" % (bad_ours, r64.numel(), bad_ref))
         # one flipped sample touches up to 4 elements of a low-resolution map: allow 4 flips
         assert bad_ours <= max(16, int(5e-4 * r64.numel())) + 4 * bad_ref, (what, bad_ours, bad_ref, r64.numel())
         # the elements that agree must make the norm agree too

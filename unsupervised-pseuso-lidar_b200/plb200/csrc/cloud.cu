@@ -7,12 +7,15 @@
 // (cloud_x >= 0 & cloud_z < 1) are bit-identical to the reference's.
 //
 // Order-preserving compaction in two launches with no inter-block waiting:
-//   (1) per-tile valid counts.  cloud_x and cloud_z are affine in the depth, so validity (cloud_x >= 0 & cloud_z < 1)
-//       costs two fp64 FMAs per coordinate whenever the value is further than 1e-8 from its threshold; only the rare
-//       borderline pixel runs the exact chain - the mask stays bit-identical to the reference's;
-//   (2) every tile sums the counts of the tiles before it, compacts (pixel, depth) of its valid pixels in shared
-//       memory and evaluates the kept points densely, one per thread, at their final row-major rank;
-//       [0::sparsity] keeps ranks divisible by `sparsity`.  Integer prefix sums: bitwise repeatable.
+//   (1) validity of every pixel, ONE WARP per 1024-pixel tile (eight 128-bit loads per lane in flight, no shared
+//       memory, no block barrier): cloud_x and cloud_z are affine in the depth, so validity (cloud_x >= 0 &
+//       cloud_z < 1) costs two fp64 FMAs per coordinate whenever the value is further than 1e-8 from its threshold;
+//       only the rare borderline pixel runs the exact chain - the mask stays bit-identical to the reference's.  Out:
+//       the tile's count and its 1024 validity bits (32 words, one per lane);
+//   (2) every tile sums the counts of the tiles before it, reads its validity bits back (the test is not repeated),
+//       compacts (pixel, depth) of its valid pixels in shared memory and evaluates the kept points densely, one per
+//       thread, at their final row-major rank; [0::sparsity] keeps ranks divisible by `sparsity`.  Integer prefix
+//       sums: bitwise repeatable.
 #include "common.cuh"
 
 namespace plb {
@@ -44,6 +47,22 @@ __device__ __forceinline__ void cloud_point(const CloudConst& cc, int col, int r
     const double y = __dadd_rn(EXACT ? __ddiv_rn(ny, cc.f_v) : div_const(ny, cc.f_v, cc.rf_v), cc.b_y);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        double acc = __dmul_rn(x, cc.Ti[k * 4 + 0]);
+        acc = __fma_rn(y, cc.Ti[k * 4 + 1], acc);
+        acc = __fma_rn(d, cc.Ti[k * 4 + 2], acc);
+        acc = __fma_rn(1.0, cc.Ti[k * 4 + 3], acc);
+        o[k] = acc;
+    }
+}
+
+// x, y, z only (the caller knows the 4th row of T_inv is zero and checks that the point is finite)
+__device__ __forceinline__ void cloud_point3(const CloudConst& cc, int col, int row, float depth, double (&o)[4]) {
+    const double d = (double)depth;
+    const double nx = __dmul_rn(__dsub_rn((double)col, cc.c_u), d), ny = __dmul_rn(__dsub_rn((double)row, cc.c_v), d);
+    const double x = __dadd_rn(div_const(nx, cc.f_u, cc.rf_u), cc.b_x);
+    const double y = __dadd_rn(div_const(ny, cc.f_v, cc.rf_v), cc.b_y);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
         double acc = __dmul_rn(x, cc.Ti[k * 4 + 0]);
         acc = __fma_rn(y, cc.Ti[k * 4 + 1], acc);
         acc = __fma_rn(d, cc.Ti[k * 4 + 2], acc);
@@ -113,30 +132,42 @@ __device__ __forceinline__ unsigned cloud_mask(const CloudConst& cc, const Cloud
     return vmask;
 }
 
-// launch 1: valid points per tile
-__global__ void __launch_bounds__(CL_THREADS)
-cloud_count_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) {
-    const int b = blockIdx.y, blk = blockIdx.x, tiles = gridDim.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int npx = a.H * a.W;
+// Workspace: int32 counts [B][tiles], then uint32 validity words [B][tiles][32]: bit 4 * it + k of word `lane` is
+// pixel tile * 1024 + it * 128 + lane * 4 + k - i.e. the four pixels thread t = it * 32 + lane of launch 2 owns.
+__host__ __device__ inline size_t cloud_words_offset(int B, int tiles) {
+    return ((size_t)B * tiles * sizeof(int32_t) + 255) / 256 * 256;
+}
+
+// launch 1: validity bits and valid points per tile; one warp per tile
+constexpr int CC_WARPS = 4;
+__global__ void __launch_bounds__(CC_WARPS * 32)
+cloud_count_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h, int tiles) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * CC_WARPS + (threadIdx.x >> 5);
+    if (blk >= tiles) return;
+    const int npx = a.H * a.W, W = a.W;
     const CloudConst cc = cloud_const(a, h);
     const float* depth = a.depth + (size_t)b * npx;
-    __shared__ int s_warp[CL_THREADS / 32];
-    const int p0 = blk * CL_TILE + tid * CL_ITEMS;
-    float dv[CL_ITEMS];
-    cloud_load(depth, (size_t)b * npx, p0, npx, dv);
-    const int row0 = p0 / a.W;
-    int mine = __popc(cloud_mask(cc, h, a.W, p0, npx, row0, p0 - row0 * a.W, dv));
+    const int pbase = blk * CL_TILE + lane * CL_ITEMS;
+    constexpr int NIT = CL_TILE / 128;
+    float dv[NIT][CL_ITEMS];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) cloud_load(depth, (size_t)b * npx, pbase + it * 128, npx, dv[it]);
+    int row = pbase / W, col = pbase - row * W;
+    unsigned word = 0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int p0 = pbase + it * 128;
+        if (p0 < npx) word |= cloud_mask(cc, h, W, p0, npx, row, col, dv[it]) << (4 * it);
+        col += 128;
+        while (col >= W) { col -= W; ++row; }
+    }
+    int mine = __popc(word);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if (lane == 0) s_warp[warp] = mine;
-    __syncthreads();
-    if (tid == 0) {
-        int total = 0;
-#pragma unroll
-        for (int w = 0; w < CL_THREADS / 32; ++w) total += s_warp[w];
-        ((int32_t*)a.workspace)[(size_t)b * tiles + blk] = total;
-    }
+    if (lane == 0) ((int32_t*)a.workspace)[(size_t)b * tiles + blk] = mine;
+    uint32_t* words = (uint32_t*)((char*)a.workspace + cloud_words_offset(a.B, tiles));
+    words[((size_t)b * tiles + blk) * 32 + lane] = word;
 }
 
 // launch 2: every tile sums the counts of the tiles before it (a few hundred L2-resident integers: cheaper than a
@@ -152,7 +183,7 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     const CloudConst cc = cloud_const(a, h);
     const float* depth = a.depth + (size_t)b * npx;
     __shared__ int s_warp[CL_THREADS / 32], s_pre[CL_THREADS / 32];
-    __shared__ int s_pix[CL_TILE], s_row[CL_TILE];
+    __shared__ int s_pix[CL_TILE];
     __shared__ float s_dep[CL_TILE];
 
     const int p0 = blk * CL_TILE + tid * CL_ITEMS;
@@ -167,8 +198,9 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) s_pre[warp] = part;
     }
-    const int row0 = p0 / a.W, col0 = p0 - row0 * a.W;
-    const unsigned vmask = cloud_mask(cc, h, a.W, p0, npx, row0, col0, dv);
+    // this thread's four validity bits, as launch 1 decided them
+    const uint32_t* words = (const uint32_t*)((const char*)a.workspace + cloud_words_offset(a.B, tiles));
+    const unsigned vmask = (__ldg(words + ((size_t)b * tiles + blk) * 32 + lane) >> (4 * warp)) & 15u;
     const int mine = __popc(vmask);
     // inclusive scan of `mine` across the warp, then across warps
     int incl = mine;
@@ -202,25 +234,35 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     }
     if (n_keep == 0) return;
     {
-        int row = row0, col = col0;
         int r = warp_off + incl - mine;     // local rank of this thread's first valid point
 #pragma unroll
-        for (int k = 0; k < CL_ITEMS; ++k) {
-            if ((vmask >> k) & 1u) { s_pix[r] = p0 + k; s_row[r] = row; s_dep[r] = dv[k]; ++r; }
-            if (++col == a.W) { col = 0; ++row; }
-        }
+        for (int k = 0; k < CL_ITEMS; ++k)
+            if ((vmask >> k) & 1u) { s_pix[r] = p0 + k; s_dep[r] = dv[k]; ++r; }
     }
     __syncthreads();
+    // the homogeneous row of T_inv is all zeros in the reference (zeros_like of a 4x4, PseudoLiDAR.py:43): the 4th
+    // output column is then exactly 0 for every finite point
+    const bool w_zero = a.Tinv[12] == 0.0 && a.Tinv[13] == 0.0 && a.Tinv[14] == 0.0 && a.Tinv[15] == 0.0;
+    const int tile_row0 = (blk * CL_TILE) / a.W;
     const size_t out0 = (size_t)b * npx + (sp == 1 ? (size_t)base : (size_t)(base + r_first) / sp);   // first output row of the tile
     for (int j = tid; j < n_keep; j += CL_THREADS) {
         const int r = r_first + j * sp;
-        const int pix = s_pix[r], row = s_row[r], col = pix - row * a.W;
+        const int pix = s_pix[r];
+        // row of the pixel: a tile spans at most CL_TILE / W + 2 rows - a few compares instead of a division
+        int row = tile_row0, col = pix - tile_row0 * a.W;
+        while (col >= a.W) { col -= a.W; ++row; }
         const float d = s_dep[r];
         double o[4];
         // the reference's operation order with constant-divisor divisions; a coordinate within 1e-9 of its
         // threshold (or huge) is re-evaluated with IEEE divisions, as the values always were
-        cloud_point<false>(cc, col, row, d, o);
-        const bool safe = fabs(o[0]) > 1e-9 && fabs(o[2] - 1.0) > 1e-9 && fabs(o[0]) < 1e12 && fabs(o[2]) < 1e12;
+        if (w_zero) {
+            cloud_point3(cc, col, row, d, o);
+            o[3] = 0.0;
+        } else {
+            cloud_point<false>(cc, col, row, d, o);
+        }
+        const bool safe = fabs(o[0]) > 1e-9 && fabs(o[2] - 1.0) > 1e-9 && fabs(o[0]) < 1e12 && fabs(o[2]) < 1e12 &&
+                          fabs(o[1]) < 1e12;
         if (!safe) cloud_point<true>(cc, col, row, d, o);
         const size_t pos = out0 + j;
         if (a.cloud_f64 != nullptr) {
@@ -237,7 +279,8 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
 static inline int cloud_blocks(const plb_cloud_args* a) { return (a->H * a->W + CL_TILE - 1) / CL_TILE; }
 
 size_t cloud_workspace_bytes(const plb_cloud_args* a) {
-    return ((size_t)a->B * cloud_blocks(a) * sizeof(int32_t) + 255) / 256 * 256;
+    const int tiles = cloud_blocks(a);
+    return cloud_words_offset(a->B, tiles) + ((size_t)a->B * tiles * 32 * sizeof(uint32_t) + 255) / 256 * 256;
 }
 
 int cloud_launch(const plb_cloud_args* a, cudaStream_t st) {
@@ -261,7 +304,7 @@ int cloud_launch(const plb_cloud_args* a, cudaStream_t st) {
         h.a2x = T2[0] / f_u; h.a2y = T2[1] / f_v; h.a2c = T2[2] - c_u * h.a2x - c_v * h.a2y;
         h.c2 = h.b_x * T2[0] + h.b_y * T2[1] + T2[3];
     }
-    cloud_count_kernel<<<grid, CL_THREADS, 0, st>>>(*a, h);
+    cloud_count_kernel<<<dim3((tiles + CC_WARPS - 1) / CC_WARPS, a->B), CC_WARPS * 32, 0, st>>>(*a, h, tiles);
     ++g_launches;
     PLB_CHECK_LAUNCH();
     cloud_write_kernel<<<grid, CL_THREADS, 0, st>>>(*a, h);
