@@ -42,6 +42,9 @@ WORKLOADS = {
     # BASELINE.json configs[1] read literally: the dormant SSIM + per-pixel min-reprojection + automask
     # composition (losses.py:12-84,94-96,154-162) at 4 scales, one direction
     "c2min": dict(B=12, H=192, W=640, n_src=2, n_scales=4, variant="min"),
+    # ... with every photometric map clamped at mean + 0.5 std of the whole map, as the reference's
+    # compute_photometric_loss does (losses.py:79-82): a grid-wide dependency, i.e. a statistics pass first
+    "c2minclip": dict(B=12, H=192, W=640, n_src=2, n_scales=4, variant="minclip"),
 }
 
 
@@ -50,7 +53,9 @@ def workload_name(wl, cfg):
         wl, cfg["H"], cfg["W"], cfg["B"], cfg["n_src"], cfg["n_scales"],
         {"live": "reference-live Losses.forward (mode='min', which the reference computes as a MEAN over sources, losses.py:226-228; 2 directions, L1 + 2nd-order smoothness)",
          "dir0": "single-direction L1",
-         "min": "single-direction SSIM+L1 min-reprojection + automask (dormant path)"}[cfg["variant"]])
+         "min": "single-direction SSIM+L1 min-reprojection + automask (dormant path)",
+         "minclip": "single-direction SSIM+L1 min-reprojection + automask with the mean + 0.5 std clip of every map (dormant path, "
+                    "losses.py:79-82)"}[cfg["variant"]])
 
 
 def algorithmic_bytes_per_px(cfg):
@@ -178,8 +183,9 @@ def oracle_step(cfg, inp):
         sum(loss).backward()
         return loss[0].detach() + loss[1].detach()
     depths = O.disp_to_depth(disp)
-    if cfg["variant"] == "min":
-        loss = O.min_reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[0], poses, inp["intrinsics"])
+    if cfg["variant"] in ("min", "minclip"):
+        loss = O.min_reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[0], poses, inp["intrinsics"],
+                                       clip_loss=0.5 if cfg["variant"] == "minclip" else None)
     else:
         loss = O.reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[:1], poses, inp["intrinsics"])
     loss.backward()
@@ -285,10 +291,10 @@ def step_fn(criterion, g, cfg):
     if cfg["variant"] == "live":
         loss = criterion.forward(g["tgt"], g["ref_imgs"], disp, poses, g["intrinsics"], None)
         total = loss[0] + loss[1]
-    elif cfg["variant"] == "min":
+    elif cfg["variant"] in ("min", "minclip"):
         from plb200 import ops, _lib
         mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp[:1], poses, g["intrinsics"], do_smooth=False,
-                                  mode=_lib.PHOTO_MIN_REPROJ)
+                                  mode=_lib.PHOTO_MIN_REPROJ, clip_loss=0.5 if cfg["variant"] == "minclip" else None)
         total = mam
     else:
         from plb200 import ops
@@ -425,6 +431,12 @@ def run_ours(args, cfg):
         ems, hms = time_eager(criterion, gpu_sets, cfg, dev, max(20, min(args.steps, 100)))
         eager_step = {"value": px_per_step / 1e6 / (ems / 1e3), "unit": UNIT, "ms_per_step": ems, "host_ms_per_step": hms,
                       "note": "same step issued eagerly through Losses.forward / backward (no CUDA graph), device-resident inputs"}
+        if cfg["variant"] == "live":
+            cms, chms = time_captured(criterion, gpu_sets, dev, max(20, min(args.steps, 100)))
+            eager_step["captured"] = {"value": px_per_step / 1e6 / (cms / 1e3), "unit": UNIT, "ms_per_step": cms,
+                                      "host_ms_per_step": chms,
+                                      "note": "Losses.capture(): the public graphed step, fresh inputs copied into its static "
+                                              "buffers (device to device) every step"}
 
     if world > 1:
         import torch.distributed as dist
@@ -464,7 +476,7 @@ def run_ours(args, cfg):
         if world == 1 and not args.no_cloud:
             # the other photometric compositions on the same frames (kernel-only, same method as `roofline`)
             others = {}
-            for name in ("headline", "headline64", "c2min", "c2"):
+            for name in ("headline", "headline64", "c2min", "c2minclip", "c2"):
                 if name == args.workload:
                     continue
                 ocfg = WORKLOADS[name]
@@ -534,7 +546,8 @@ def time_photo_kernel(criterion, gpu_sets, cfg, dev, iters):
         pyr = g["disparity"] if cfg["variant"] == "live" else g["disparity"][:1]
         from plb200 import _lib
         lcfg = ops.LossConfig(cfg["n_src"], [len(p) for p in pyr], do_smooth=False,
-                              mode=_lib.PHOTO_MIN_REPROJ if cfg["variant"] == "min" else _lib.PHOTO_L1_MEAN)
+                              mode=_lib.PHOTO_MIN_REPROJ if cfg["variant"] in ("min", "minclip") else _lib.PHOTO_L1_MEAN,
+                              clip_loss=0.5 if cfg["variant"] == "minclip" else None)
         g_pyr = [[torch.empty_like(d) for d in p] for p in pyr]
         g_poses = torch.zeros_like(g["poses"])
         out = torch.zeros(2, device=dev)
@@ -763,6 +776,30 @@ def time_eager(criterion, gpu_sets, cfg, dev, iters):
     e0.record()
     for i in range(iters):
         step_fn(criterion, gpu_sets[i % len(gpu_sets)], cfg)
+    e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / iters
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, host_ms
+
+
+def time_captured(criterion, gpu_sets, dev, iters):
+    """`Losses.capture()` (plb200/graphed.py): the step a trainer gets when it graphs the loss tail - inputs that live
+    in other buffers (here: the rotating input sets) are copied into the captured step's static buffers, then one
+    graph launch."""
+    g0 = gpu_sets[0]
+    step = criterion.capture(g0["tgt"], g0["ref_imgs"], g0["disparity"], g0["poses"], g0["intrinsics"])
+
+    def one(i):
+        g = gpu_sets[i % len(gpu_sets)]
+        step(g["tgt"], g["ref_imgs"], g["disparity"], g["poses"], g["intrinsics"])
+    for i in range(5):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(iters):
+        one(i)
     e1.record()
     host_ms = (time.perf_counter() - t0) * 1e3 / iters
     torch.cuda.synchronize()

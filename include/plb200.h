@@ -115,7 +115,9 @@ typedef struct plb_photo_args {
                                   given one equals 1, the launch returns at once (the gradients
                                   written by the forward pass with unit upstream are then already
                                   exact) - see DESIGN.md                                          */
-    void* workspace;           /* plb_photo_workspace_bytes() bytes, zero-filled ONCE by the caller */
+    void* workspace;           /* plb_photo_workspace_bytes() bytes, zero-filled ONCE by the caller; it cleans up
+                                  after itself, and the library clears it when a later call brings a different
+                                  layout (another batch / image size / mode / set of gradients)         */
     size_t workspace_bytes;
     plb_photo_job jobs[PLB_MAX_JOBS];
 } plb_photo_args;

@@ -286,3 +286,26 @@ def test_torch_binding_backward_twice_and_errors():
     assert torch.equal(g1, p.grad)
     with pytest.raises(RuntimeError):
         ops.fused_losses(inp["tgt"], [r.to(dev) for r in inp["ref_imgs"]], disp, p, inp["intrinsics"].to(dev), binding="torch")
+
+
+def test_captured_step_equals_eager():
+    """`Losses.capture()` (CUDA graph of forward + backward over static buffers) returns bitwise what the eager calls
+    return, for the inputs it was captured with and for new inputs copied in at replay."""
+    from losses import Losses
+    from plb200 import synth
+    dev = _dev()
+    sets = [synth.to_device(synth.make_photo_inputs(3, 96, 320, n_src=2, n_scales=4, seed=s, n_depth_frames=2), dev) for s in (5, 6)]
+    crit = Losses()
+    step = crit.capture(sets[0]["tgt"], sets[0]["ref_imgs"], sets[0]["disparity"], sets[0]["poses"], sets[0]["intrinsics"])
+    for k in (0, 1, 0):
+        g = sets[k]
+        loss, grads = step(g["tgt"], g["ref_imgs"], g["disparity"], g["poses"], g["intrinsics"])
+        disp = [[d.detach().clone().requires_grad_(True) for d in fr] for fr in g["disparity"]]
+        p = g["poses"].detach().clone().requires_grad_(True)
+        ref = crit.forward(g["tgt"], g["ref_imgs"], disp, p, g["intrinsics"], None)
+        (ref[0] + ref[1]).backward()
+        assert torch.equal(loss[0], ref[0].detach()) and torch.equal(loss[1], ref[1].detach())
+        assert torch.equal(grads.poses, p.grad)
+        for fr_c, fr_e in zip(grads.disparity, disp):
+            for gc, de in zip(fr_c, fr_e):
+                assert torch.equal(gc, de.grad)

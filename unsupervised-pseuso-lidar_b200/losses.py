@@ -56,6 +56,14 @@ class Losses:
 
     __call__ = forward
 
+    def capture(self, tgt_img, ref_imgs, disparity, poses, intrinsics, warmup=2):
+        """`forward` + `sum(loss).backward()` (`trainer.py:312` + `:264`) captured as ONE CUDA graph over static
+        copies of the arguments (plb200/graphed.py): `step = criterion.capture(...)`, then per training step
+        `loss, grads = step(tgt, ref_imgs, disparity, poses, intrinsics)`.  Same kernels, bitwise the same results;
+        the host cost of a step drops from ~170 us of autograd + launch issue to one graph launch."""
+        from plb200.graphed import CapturedLossStep
+        return CapturedLossStep(self, tgt_img, ref_imgs, disparity, poses, intrinsics, warmup=warmup)
+
     def reprojection_loss(self, tgt, refs, depths, poses, intrinsics, mode='min'):
         """`losses.py:183-240`; `depths` are depth (not disparity) pyramids per frame.
         mode 'min' is the mean the reference computes (`:226-228`)."""

@@ -27,6 +27,8 @@
 // each (job, image) pair, runs the pose chain and adds the loss: no atomics on the results, bitwise repeatable, and
 // no fence / ticket traffic in the main kernel.
 #include "photo_common.cuh"
+#include <mutex>
+#include <unordered_map>
 
 namespace plb {
 
@@ -62,27 +64,6 @@ __device__ __forceinline__ void dbg_stamp(int slot) {
 // is scale invariant) and (cx, cy, ze) = D * A + p3', this equals -(g_cam . p3') / D - the analytically cancelled
 // form, free of the ~W-sized cancellation the chain-rule form carries, and A need not stay live across the loads.
 // ---------------------------------------------------------------------------------------------
-template <int NS> struct Vec;
-template <> struct Vec<1> { typedef float T; };
-template <> struct Vec<2> { typedef float2 T; };
-
-__device__ __forceinline__ float v_fma(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ float2 v_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float v_mul(float a, float b) { return a * b; }
-__device__ __forceinline__ float2 v_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float v_add(float a, float b) { return a + b; }
-__device__ __forceinline__ float2 v_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float v_sub(float a, float b) { return a - b; }
-__device__ __forceinline__ float2 v_sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
-__device__ __forceinline__ void v_bc(float& v, float s) { v = s; }
-__device__ __forceinline__ void v_bc(float2& v, float s) { v = make_float2(s, s); }
-__device__ __forceinline__ float v_get(float v, int) { return v; }
-__device__ __forceinline__ float v_get(float2 v, int k) { return k == 0 ? v.x : v.y; }
-__device__ __forceinline__ void v_set(float& v, int, float s) { v = s; }
-__device__ __forceinline__ void v_set(float2& v, int k, float s) { if (k == 0) v.x = s; else v.y = s; }
-__device__ __forceinline__ float v_hsum(float v) { return v; }
-__device__ __forceinline__ float v_hsum(float2 v) { return v.x + v.y; }
-
 // where the constants of a combo live: T2 table `tab` for a packed combo, Q[k0] for a single sample
 struct ComboRef { int tab, k0; };
 
@@ -1697,6 +1678,8 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     PhotoLaunch p;
     p.a = *a;
     p.L = photo_layout(*a);
+    rc = photo_workspace_prepare(*a, p.L, st);
+    if (rc != PLB_OK) return rc;
     bool img_grad = false, low = false, lowfast = false;
     for (int j = 0; j < a->n_jobs; ++j) {
         if (a->jobs[j].g_tgt) img_grad = true;
@@ -1847,5 +1830,28 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
 }
 
 size_t photo_workspace_bytes(const plb_photo_args* a) { return photo_layout(*a).total; }
+
+// The workspace cleans up after itself for ONE layout: tickets go back to zero, the fixed-point accumulators of the
+// deterministic mode are re-zeroed by their conversion kernel, everything else is written before it is read.  A call
+// with a DIFFERENT layout (another batch, image size, mode, set of gradients) finds the regions it expects to be zero
+// somewhere else - possibly under the records or statistics an earlier call left - so the library remembers the
+// layout every workspace pointer was last used with and clears the buffer when it changes (the first use of a pointer
+// trusts the caller's zero fill).
+int photo_workspace_prepare(const plb_photo_args& a, const PhotoLayout& L, cudaStream_t st) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    mix(L.tickets); mix(L.records); mix(L.lossrec); mix(L.ws_pose); mix(L.ws_loss); mix(L.gup); mix(L.pairs); mix(L.ylow);
+    for (int j = 0; j < PLB_MAX_JOBS; ++j)
+        for (int s = 0; s < PLB_MAX_SCALES; ++s) mix(L.ylow_off[j][s]);
+    mix(L.pm_thr); mix(L.pm_stat); mix(L.detacc); mix((uint64_t)L.det_n); mix(L.total);
+    static std::mutex mu;
+    static std::unordered_map<const void*, uint64_t> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = seen.find(a.workspace);
+    if (it == seen.end()) { seen.emplace(a.workspace, h); return PLB_OK; }
+    if (it->second == h) return PLB_OK;
+    it->second = h;
+    return (int)cudaMemsetAsync(a.workspace, 0, L.total, st);
+}
 
 }  // namespace plb

@@ -5,6 +5,30 @@
 
 namespace plb {
 
+// Packed fp32 helpers: the two halves of a float2 ride Blackwell's packed pipe (FFMA2 / FADD2 / FMUL2), each half
+// rounded exactly like the scalar operation.
+template <int NS> struct Vec;
+template <> struct Vec<1> { typedef float T; };
+template <> struct Vec<2> { typedef float2 T; };
+
+__device__ __forceinline__ float v_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float2 v_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float v_mul(float a, float b) { return a * b; }
+__device__ __forceinline__ float2 v_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float v_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 v_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float v_sub(float a, float b) { return a - b; }
+__device__ __forceinline__ float2 v_sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+__device__ __forceinline__ void v_bc(float& v, float s) { v = s; }
+__device__ __forceinline__ void v_bc(float2& v, float s) { v = make_float2(s, s); }
+__device__ __forceinline__ float v_get(float v, int) { return v; }
+__device__ __forceinline__ float v_get(float2 v, int k) { return k == 0 ? v.x : v.y; }
+__device__ __forceinline__ void v_set(float& v, int, float s) { v = s; }
+__device__ __forceinline__ void v_set(float2& v, int k, float s) { if (k == 0) v.x = s; else v.y = s; }
+__device__ __forceinline__ float v_hsum(float v) { return v; }
+__device__ __forceinline__ float v_hsum(float2 v) { return v.x + v.y; }
+
+
 // Threads per block of the fused L1 kernel (tuned on B200, profiles/README.md): 4 x 160 threads per SM = 5 warps per
 // scheduler, the most that 96 registers per thread allow (a scheduler's quarter of the register file holds
 // 16384 / (32 x 96) = 5.3 warps; 3 x 192 leaves two schedulers a warp short).
@@ -264,5 +288,7 @@ int photo_upsample_T_launch(const PhotoLaunch& p, cudaStream_t st);   // photo.c
 // fixed-point accumulators (PhotoLayout::detacc) -> the caller's buffers; `unit`: value of one accumulator count
 int photo_det_convert_launch(const plb_photo_args& a, const PhotoLayout& L, float unit, cudaStream_t st);   // photo.cu
 int photo_min_launch(const plb_photo_args* a, cudaStream_t st);       // photo_min.cu
+// clears the workspace when the layout it was last used with differs from this call's (photo.cu)
+int photo_workspace_prepare(const plb_photo_args& a, const PhotoLayout& L, cudaStream_t st);
 
 }  // namespace plb

@@ -85,6 +85,18 @@ __device__ __forceinline__ void pm_project(const float4 Pa, const float4 Pb, con
 
 __device__ __forceinline__ void pm_taps(const float* __restrict__ cb, int plane, int W, const MinProj& q,
                                         float (&v)[3][4]) {
+    // one vote of the lanes that are here: every footprint inside the source (the common case) -> plain loads, six row
+    // pointers and immediate offsets instead of twelve predicated loads with their own address arithmetic
+    if (__all_sync(__activemask(), q.mask == 15u)) {
+        const float* __restrict__ p0 = cb + q.o00;
+        const float* __restrict__ p1 = p0 + W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            v[c][0] = __ldg(p0 + c * plane); v[c][1] = __ldg(p0 + c * plane + 1);
+            v[c][2] = __ldg(p1 + c * plane); v[c][3] = __ldg(p1 + c * plane + 1);
+        }
+        return;
+    }
     const bool mnw = q.mask & 1u, mne = q.mask & 2u, msw = q.mask & 4u, mse = q.mask & 8u;
     const int o00 = q.o00, o01 = o00 + W;
 #pragma unroll
@@ -121,12 +133,18 @@ __device__ __forceinline__ float pm_depth(const plb_photo_args& a, const PairCon
     return ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
 }
 
-// Shared memory of one block (dynamic: ~55 KB, three blocks per SM).
+// Shared memory of one block (dynamic: ~70 KB with two sources, three blocks per SM).  Sources live in PAIRS - the two
+// halves of a float2 - so that stage 2 runs both on the packed fp32 pipe with one 64-bit load per value; the target is
+// stored twice (t, t) for the same reason.
+constexpr int PM_NT = PM_TW * PM_TH;        // tile pixels = threads
+template <int NSMAX, int VAR>
 struct __align__(16) PminSmem {
+    static constexpr bool kImg = VAR == PM_VAR_IMG, kStats = VAR == PM_VAR_STATS;
+    static constexpr int kState = kStats ? 1 : PM_NT, kImgState = kImg ? PM_NT : 1, kStat = kStats ? PM_MAXMAPS : 1;
     float4 coef[3][PM_N1];                  // per channel, the min-source term: d rp / d x_q = ca + cb x_q + cc y_q (+ cl at the centre)
     PairConst pc;
-    float T[3][PM_N2];                      // target, tile + 2 (reflected at the border)
-    float X[PLB_MAX_SRC][3][PM_N2];         // warped (or, for the automask pass, raw) sources
+    float2 T2[3][PM_N2];                    // target (t, t), tile + 2 (reflected at the border)
+    float2 X2[NSMAX / 2][3][PM_N2];         // warped (or, for the automask pass, raw) sources (2g, 2g + 1)
     float aut[3][PM_N1];                    // min_i photo(src_i, tgt) per channel
     float val[3][PM_N1];                    // min_i rp_i per channel
     signed char src[3][PM_N1];              // argmin_i
@@ -135,100 +153,127 @@ struct __align__(16) PminSmem {
     float red[PH_NREC + 3];
     float part4[4][64];
     float thr[PM_MAXMAPS];                  // clip thresholds (3e38: no clip)
-    float da[3][PM_N1];                     // IMG: constant term of d rp / d y_q (the target's side of SSIM)
-    double stat[PM_THREADS / 32][PM_MAXMAPS][2];   // STATS: per-warp (sum, sum of squares) of every map
+    // sampler state of the tile pixels, left by stage 1 for stage 3 (no second projection / tap gather):
+    // d warped_c / d px, d warped_c / d py, (1/z, px, py) - zero where no tap is inside the source - and the depth
+    float sdx[NSMAX][3][kState], sdy[NSMAX][3][kState], sgeo[NSMAX][3][kState], sD[kState];
+    float sfx[NSMAX][kImgState], sfy[NSMAX][kImgState];      // IMG: bilinear fractions, first tap and tap mask
+    int so00[NSMAX][kImgState];
+    unsigned smask[NSMAX][kImgState];
+    float da[3][kImg ? PM_N1 : 1];          // IMG: constant term of d rp / d y_q (the target's side of SSIM)
+    double stat[PM_THREADS / 32][kStat][2]; // STATS: per-warp (sum, sum of squares) of every map
     int flag;
 };
 
 // photometric value of one (pixel, channel) from its 3x3 window sums, and the coefficients of its
 // derivative w.r.t. the predicted image at window position q:
 //   d rp / d x_q = ca + cb * x_q + cc * y_q   (+ cl at the centre)
+// evaluated for the two sources of a pair at once: every arithmetic step is one packed instruction (the target's
+// sums ride along in both halves), only compares / clamps / the reciprocal seed are per half.
 struct Photo { float rp, ca, cb, cc, cl, da; };
-__device__ __forceinline__ Photo photo_from_sums(float sx, float sxx, float sxy, float sy, float syy, float xc, float yc,
-                                                 float C1, float C2, bool no_ssim) {
+struct Photo2 { float2 rp, ca, cb, cc, cl, da; };
+__device__ __forceinline__ float2 f2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ Photo photo_half(const Photo2& t, int q) {
     Photo r;
-    const float diff = xc - yc;
-    const float sg = (diff > 0.0f ? 1.0f : 0.0f) - (diff < 0.0f ? 1.0f : 0.0f);
+    r.rp = v_get(t.rp, q); r.ca = v_get(t.ca, q); r.cb = v_get(t.cb, q);
+    r.cc = v_get(t.cc, q); r.cl = v_get(t.cl, q); r.da = v_get(t.da, q);
+    return r;
+}
+template <bool WANT_DA>
+__device__ __forceinline__ Photo2 photo_from_sums2(float2 sx, float2 sxx, float2 sxy, float2 sy, float2 syy, float2 xc,
+                                                   float2 yc, float C1, float C2, bool no_ssim) {
+    Photo2 r;
+    const float2 diff = v_sub(xc, yc);
+    float2 sg;
+    sg.x = (diff.x > 0.0f ? 1.0f : 0.0f) - (diff.x < 0.0f ? 1.0f : 0.0f);
+    sg.y = (diff.y > 0.0f ? 1.0f : 0.0f) - (diff.y < 0.0f ? 1.0f : 0.0f);
+    const float2 ad = make_float2(fabsf(diff.x), fabsf(diff.y));
     if (no_ssim) {
-        r.rp = fabsf(diff); r.ca = r.cb = r.cc = r.da = 0.0f; r.cl = sg;
+        r.rp = ad; r.ca = r.cb = r.cc = r.da = f2(0.0f); r.cl = sg;
         return r;
     }
-    const float i9 = 1.0f / 9.0f;
-    const float mux = sx * i9, muy = sy * i9;
-    const float mxx = mux * mux, myy = muy * muy, mxy = mux * muy;
-    const float sigx = fmaf(sxx, i9, -mxx), sigy = fmaf(syy, i9, -myy), sigxy = fmaf(sxy, i9, -mxy);
-    const float N1 = fmaf(2.0f, mxy, C1), N2 = fmaf(2.0f, sigxy, C2);
-    const float D1 = mxx + myy + C1, D2 = sigx + sigy + C2;
-    const float iD = rcp_nr(D1 * D2);                    // one reciprocal for both denominators
-    const float iD1 = D2 * iD, iD2 = D1 * iD;
-    const float ssim = (N1 * N2) * iD;
-    const float h = (1.0f - ssim) * 0.5f;
-    r.rp = fmaf(0.85f, fminf(fmaxf(h, 0.0f), 1.0f), 0.15f * fabsf(diff));
+    const float2 i9 = f2(1.0f / 9.0f), neg1 = f2(-1.0f);
+    const float2 mux = v_mul(sx, i9), muy = v_mul(sy, i9);
+    const float2 nmux = v_mul(mux, neg1), nmuy = v_mul(muy, neg1);
+    const float2 nmxx = v_mul(nmux, mux), nmyy = v_mul(nmuy, muy), nmxy = v_mul(nmux, muy);   // -mu_x^2, -mu_y^2, -mu_x mu_y
+    const float2 sigx = v_fma(sxx, i9, nmxx), sigy = v_fma(syy, i9, nmyy), sigxy = v_fma(sxy, i9, nmxy);
+    const float2 c1 = f2(C1), c2 = f2(C2);
+    const float2 N1 = v_fma(nmxy, f2(-2.0f), c1), N2 = v_fma(sigxy, f2(2.0f), c2);
+    const float2 D1 = v_fma(v_add(nmxx, nmyy), neg1, c1), D2 = v_add(v_add(sigx, sigy), c2);
+    const float2 nDD = v_mul(v_mul(D1, neg1), D2);
+    float2 iD;                                           // one reciprocal for both denominators
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iD.x) : "f"(-nDD.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iD.y) : "f"(-nDD.y));
+    iD = v_mul(iD, v_fma(nDD, iD, f2(2.0f)));            // Newton step
+    const float2 iD1 = v_mul(D2, iD), iD2 = v_mul(D1, iD);
+    const float2 ssim = v_mul(v_mul(N1, N2), iD);
+    const float2 h = v_mul(v_fma(ssim, neg1, f2(1.0f)), f2(0.5f));
+    const float2 hc = make_float2(fminf(fmaxf(h.x, 0.0f), 1.0f), fminf(fmaxf(h.y, 0.0f), 1.0f));
+    r.rp = v_fma(f2(0.85f), hc, v_mul(f2(0.15f), ad));
     // d ssim / d x_q = (2/9) { [mu_y (N2 - N1)]/(D1 D2) - ssim mu_x (1/D1 - 1/D2) }  +  x_q (-(2/9) ssim / D2)
     //                  + y_q ((2/9) N1 / (D1 D2));   d rp / d x_q = -0.425 * (that) inside the clamp
-    const float k = (h > 0.0f && h < 1.0f) ? (-0.425f * 2.0f * i9) : 0.0f;
-    r.ca = k * (muy * (N2 - N1) * iD - ssim * mux * (iD1 - iD2));
+    const float kk = -0.425f * 2.0f * (1.0f / 9.0f);
+    const float2 k = make_float2((h.x > 0.0f && h.x < 1.0f) ? kk : 0.0f, (h.y > 0.0f && h.y < 1.0f) ? kk : 0.0f);
+    const float2 dN = v_mul(v_sub(N2, N1), iD), ndI = v_sub(iD2, iD1);
+    r.ca = v_mul(k, v_fma(v_mul(ssim, mux), ndI, v_mul(muy, dN)));
     // (SSIM is symmetric in x and y: d ssim / d y_q has the same x_q / y_q coefficients swapped and this constant)
-    r.da = k * (mux * (N2 - N1) * iD - ssim * muy * (iD1 - iD2));
-    r.cb = k * (-ssim * iD2);
-    r.cc = k * (N1 * iD);
-    r.cl = 0.15f * sg;
+    r.da = WANT_DA ? v_mul(k, v_fma(v_mul(ssim, muy), ndI, v_mul(mux, dN))) : f2(0.0f);
+    r.cb = v_mul(v_mul(k, neg1), v_mul(ssim, iD2));
+    r.cc = v_mul(k, v_mul(N1, iD));
+    r.cl = v_mul(f2(0.15f), sg);
     return r;
 }
 
 // Stage 2 work item = (channel, column of tile + 1, group of 5 rows): 3 x 34 x 2 = 204 threads.  The
-// thread walks DOWN its column keeping the last three horizontal 3-sums of y, y^2 and, per source, x,
-// x^2, x y in registers (separable box filter: 3 shared loads per source and row instead of 18), and
-// emits one photometric term per row: min over the NS sources of this call.
-//   MODE 0: first sources of the scale: write val / src / coef;  MODE 1: later sources: update when smaller;
+// thread walks DOWN its column keeping the last three horizontal 3-sums of y, y^2 and, for the source pair, x,
+// x^2, x y in registers (separable box filter: 3 shared loads per row for BOTH sources instead of 18 each), and
+// emits one photometric term per row: min over the sources of the pair.
+//   MODE 0: first pair of the scale: write val / src / coef;  MODE 1: second pair: update when smaller;
 //   MODE 2 / 3: the same for the automask reference (raw sources), value only.
 constexpr int PM_S2_ITEMS = 3 * PM_W1 * 2;
-template <int NS, int MODE, int VAR>
-__device__ __forceinline__ void pm_stage2(PminSmem& S, int i0, int map0, int tid, int tx0, int ty0, int H, int W, float C1,
+template <int MODE, int VAR, class SM>
+__device__ __forceinline__ void pm_stage2(SM& S, int g, int n_here, int map0, int tid, int tx0, int ty0, int H, int W, float C1,
                                           float C2, bool no_ssim) {
-    float st[NS][2];
+    const int i0 = 2 * g;
+    float st[2][2];
 #pragma unroll
-    for (int q = 0; q < NS; ++q) st[q][0] = st[q][1] = 0.0f;
+    for (int q = 0; q < 2; ++q) st[q][0] = st[q][1] = 0.0f;
     if (tid < PM_S2_ITEMS) {
         const int ch = tid / (2 * PM_W1), r = tid - ch * (2 * PM_W1);
         const int grp = r / PM_W1, col = r - grp * PM_W1;
-        const float* __restrict__ T = S.T[ch];
+        const float2* __restrict__ T = S.T2[ch];
+        const float2* __restrict__ X = S.X2[g][ch];
         int k = (5 * grp) * PM_W2 + col;        // tile + 2 index of the window's top-left corner
-        float hy[3], hyy[3], hx[NS][3], hxx[NS][3], hxy[NS][3];
-        float yc = 0.0f, xc[NS];
-        float thr[NS];
+        float2 hy[3], hyy[3], hx[3], hxx[3], hxy[3];
+        float2 yc = f2(0.0f), xc = f2(0.0f);
+        float thr[2];
 #pragma unroll
-        for (int q = 0; q < NS; ++q) thr[q] = S.thr[map0 + q];
+        for (int q = 0; q < 2; ++q) thr[q] = S.thr[map0 + q];
         const int gx = tx0 + col - 1;
         const bool colin = gx >= 0 && gx < W;
 #pragma unroll
         for (int rr = 0; rr < 7; ++rr, k += PM_W2) {
             const int slot = rr % 3;
-            const float y0 = T[k], y1 = T[k + 1], y2 = T[k + 2];
-            hy[slot] = (y0 + y1) + y2;
-            hyy[slot] = fmaf(y2, y2, fmaf(y1, y1, y0 * y0));
-            float xn[NS];
-#pragma unroll
-            for (int q = 0; q < NS; ++q) {
-                const float* __restrict__ X = S.X[i0 + q][ch];
-                const float x0 = X[k], x1 = X[k + 1], x2 = X[k + 2];
-                hx[q][slot] = (x0 + x1) + x2;
-                hxx[q][slot] = fmaf(x2, x2, fmaf(x1, x1, x0 * x0));
-                hxy[q][slot] = fmaf(x2, y2, fmaf(x1, y1, x0 * y0));
-                xn[q] = x1;
-            }
+            const float2 y0 = T[k], y1 = T[k + 1], y2 = T[k + 2];
+            const float2 x0 = X[k], x1 = X[k + 1], x2 = X[k + 2];
+            hy[slot] = v_add(v_add(y0, y1), y2);
+            hyy[slot] = v_fma(y2, y2, v_fma(y1, y1, v_mul(y0, y0)));
+            hx[slot] = v_add(v_add(x0, x1), x2);
+            hxx[slot] = v_fma(x2, x2, v_fma(x1, x1, v_mul(x0, x0)));
+            hxy[slot] = v_fma(x2, y2, v_fma(x1, y1, v_mul(x0, y0)));
             if (rr >= 2) {
                 const int o = 5 * grp + rr - 2;            // row of tile + 1
                 const int p1 = o * PM_W1 + col;
                 const int gy = ty0 + o - 1;
                 const bool in = colin && gy >= 0 && gy < H;
-                const float sy = (hy[0] + hy[1]) + hy[2], syy = (hyy[0] + hyy[1]) + hyy[2];
+                const Photo2 t2 = photo_from_sums2<VAR == PM_VAR_IMG>(
+                    v_add(v_add(hx[0], hx[1]), hx[2]), v_add(v_add(hxx[0], hxx[1]), hxx[2]), v_add(v_add(hxy[0], hxy[1]), hxy[2]),
+                    v_add(v_add(hy[0], hy[1]), hy[2]), v_add(v_add(hyy[0], hyy[1]), hyy[2]), xc, yc, C1, C2, no_ssim);
                 Photo m; m.rp = 3.0e38f; m.ca = m.cb = m.cc = m.cl = m.da = 0.0f;
-                int mi = 0;
+                int mi = i0;
 #pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    Photo t = photo_from_sums((hx[q][0] + hx[q][1]) + hx[q][2], (hxx[q][0] + hxx[q][1]) + hxx[q][2],
-                                              (hxy[q][0] + hxy[q][1]) + hxy[q][2], sy, syy, xc[q], yc, C1, C2, no_ssim);
+                for (int q = 0; q < 2; ++q) {
+                    if (q == 1 && n_here < 2) continue;   // (block-uniform) the pair's second half is empty
+                    Photo t = photo_half(t2, q);
                     if (VAR == PM_VAR_STATS) {
                         // the map's own statistics: every pixel of the image once (the tile's interior)
                         if (in && col >= 1 && col <= PM_TW && o >= 1 && o <= PM_TH) { st[q][0] += t.rp; st[q][1] = fmaf(t.rp, t.rp, st[q][1]); }
@@ -252,15 +297,15 @@ __device__ __forceinline__ void pm_stage2(PminSmem& S, int i0, int map0, int tid
                 }
             }
             yc = y1;
-#pragma unroll
-            for (int q = 0; q < NS; ++q) xc[q] = xn[q];
+            xc = x1;
         }
     }
     if (VAR == PM_VAR_STATS) {
         // warp butterfly (fixed order), then this warp's own slot: no atomics, repeatable
         const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-        for (int q = 0; q < NS; ++q) {
+        for (int q = 0; q < 2; ++q) {
+            if (q == 1 && n_here < 2) continue;
             double a = (double)st[q][0], b = (double)st[q][1];
 #pragma unroll
             for (int k = 16; k > 0; k >>= 1) {
@@ -273,16 +318,14 @@ __device__ __forceinline__ void pm_stage2(PminSmem& S, int i0, int map0, int tid
 }
 
 // MODE0 = 0: the warped sources of a scale (maps map0 + i); MODE0 = 2: the raw sources (automask reference)
-template <int MODE0, int VAR>
-__device__ __forceinline__ void pm_stage2_all(PminSmem& S, int n_src, int map0, int tid, int tx0, int ty0, int H, int W,
+template <int MODE0, int VAR, int NSMAX, class SM>
+__device__ __forceinline__ void pm_stage2_all(SM& S, int n_src, int map0, int tid, int tx0, int ty0, int H, int W,
                                               float C1, float C2, bool no_ssim) {
     // sources two at a time (they share the target's window sums); block-uniform control flow
-    if (n_src >= 2) pm_stage2<2, MODE0, VAR>(S, 0, map0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
-    else pm_stage2<1, MODE0, VAR>(S, 0, map0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
-    if (n_src > 2) {
+    pm_stage2<MODE0, VAR>(S, 0, min(n_src, 2), map0, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+    if (NSMAX > 2 && n_src > 2) {
         __syncthreads();
-        if (n_src == 4) pm_stage2<2, MODE0 + 1, VAR>(S, 2, map0 + 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
-        else pm_stage2<1, MODE0 + 1, VAR>(S, 2, map0 + 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
+        pm_stage2<MODE0 + 1, VAR>(S, NSMAX > 2 ? 1 : 0, n_src - 2, map0 + 2, tid, tx0, ty0, H, W, C1, C2, no_ssim);
     }
 }
 
@@ -307,7 +350,8 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     const bool no_ssim = job.flags & PLB_PHOTO_NO_SSIM, automask = !(job.flags & PLB_PHOTO_NO_AUTOMASK);
 
     extern __shared__ __align__(16) unsigned char pm_smem[];
-    PminSmem& S = *reinterpret_cast<PminSmem*>(pm_smem);
+    typedef PminSmem<NSMAX, VAR> Smem;
+    Smem& S = *reinterpret_cast<Smem*>(pm_smem);
     PairConst& pc = S.pc;
 
     // ---- prologue: K^-1, P per source, base pointers of image b ------------------------------------
@@ -355,7 +399,7 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     }
     for (int k = tid; k < (PM_THREADS / 32) * (PH_NREC + 3); k += PM_THREADS) (&S.rec[0][0])[k] = 0.0f;
     if (STATS)
-        for (int k = tid; k < (PM_THREADS / 32) * PM_MAXMAPS * 2; k += PM_THREADS) (&S.stat[0][0][0])[k] = 0.0;
+        for (int k = tid; k < (PM_THREADS / 32) * Smem::kStat * 2; k += PM_THREADS) (&S.stat[0][0][0])[k] = 0.0;
     __syncthreads();
     const int n_src = pc.n_src, n_scales = pc.n_scales;
     const float w_e = pc.w_e / (float)n_scales;        // scales are averaged
@@ -368,23 +412,32 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
         const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
         const int o = gy * W + gx;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) S.T[c][k] = __ldg(pc.tgt + (o + c * plane));
-        if (automask)
-            for (int i = 0; i < n_src; ++i)
+        for (int c = 0; c < 3; ++c) S.T2[c][k] = f2(__ldg(pc.tgt + (o + c * plane)));
+        if (automask) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) S.X[i][c][k] = __ldg(pc.src[i] + (o + c * plane));
+            for (int g = 0; g < NSMAX / 2; ++g) {
+                if (2 * g >= n_src) continue;
+                const bool two = 2 * g + 1 < n_src;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    S.X2[g][c][k] = make_float2(__ldg(pc.src[2 * g] + (o + c * plane)),
+                                                two ? __ldg(pc.src[2 * g + 1] + (o + c * plane)) : 0.0f);
+            }
+        }
     }
     __syncthreads();
-    if (automask) pm_stage2_all<2, VAR>(S, n_src, PLB_MAX_SCALES * PLB_MAX_SRC, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
+    if (automask) pm_stage2_all<2, VAR, NSMAX>(S, n_src, PLB_MAX_SCALES * PLB_MAX_SRC, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
     __syncthreads();
 
-    float acc[NSMAX][12];
+    // pose sums of this thread's pixel over the scales: sum h_r = sum g_cam[r] * D and sum g_cam[r] per source (the
+    // pixel's ray is the same at every scale: it multiplies the sums once, at the end)
+    float acc[NSMAX][6];
     float lsum = 0.0f;
     float gta[3] = {0.0f, 0.0f, 0.0f};                 // IMG: d loss / d target of this thread's pixel, all scales
 #pragma unroll
     for (int i = 0; i < NSMAX; ++i)
 #pragma unroll
-        for (int k = 0; k < 12; ++k) acc[i][k] = 0.0f;
+        for (int k = 0; k < 6; ++k) acc[i][k] = 0.0f;
 
     // this thread's tile pixel
     const int qx = tx0 + lane, qy = ty0 + warp;
@@ -394,7 +447,8 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
 #pragma unroll 1
     for (int s = 0; s < n_scales; ++s) {
         const bool full = pc.dh[s] == H && pc.dw[s] == W;
-        // ---- (1) warp tile + 2 halo of every source into shared memory ---------------------------
+        // ---- (1) warp tile + 2 halo of every source into shared memory; the tile's own pixels also leave the
+        //      derivatives of the sampler (stage 3 needs no second projection / gather) ---------------
         for (int k = tid; k < PM_N2; k += PM_THREADS) {
             const int ly = k / PM_W2, lx = k - ly * PM_W2;
             const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
@@ -403,24 +457,45 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
             const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
             const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
             const float rz = fmaf(pc.kinv[7], yf, pc.kinv[6] * xf) + pc.kinv[8];
+            const bool own = GRAD && !STATS && lx >= 2 && lx < 2 + PM_TW && ly >= 2 && ly < 2 + PM_TH;
+            const int q = own ? (ly - 2) * PM_TW + (lx - 2) : 0;
+            if (own) S.sD[q] = D;
 #pragma unroll
-            for (int i = 0; i < NSMAX; ++i) {
-                if (i < n_src) {
-                    MinProj q;
-                    pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
-                    float v[3][4];
-                    pm_taps(pc.src[i], plane, W, q, v);
+            for (int g = 0; g < NSMAX / 2; ++g) {
+                if (2 * g >= n_src) continue;
+                float w[2][3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float top = fmaf(q.fx, v[c][1] - v[c][0], v[c][0]), bot = fmaf(q.fx, v[c][3] - v[c][2], v[c][2]);
-                        S.X[i][c][k] = fmaf(q.fy, bot - top, top);
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int i = 2 * g + hh;
+                    w[hh][0] = w[hh][1] = w[hh][2] = 0.0f;
+                    if (i < n_src) {
+                        MinProj pq;
+                        pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, pq);
+                        float v[3][4];
+                        pm_taps(pc.src[i], plane, W, pq, v);
+                        const bool use = pq.mask != 0u;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float dA = v[c][1] - v[c][0], dB = v[c][3] - v[c][2];
+                            const float top = fmaf(pq.fx, dA, v[c][0]), bot = fmaf(pq.fx, dB, v[c][2]);
+                            const float dV = bot - top;
+                            w[hh][c] = fmaf(pq.fy, dV, top);
+                            if (own) { S.sdx[i][c][q] = fmaf(pq.fy, dB - dA, dA); S.sdy[i][c][q] = dV; }
+                        }
+                        if (own) {
+                            // (the selects also keep the inf / NaN of a degenerate z out of the sums)
+                            S.sgeo[i][0][q] = use ? pq.inv : 0.0f; S.sgeo[i][1][q] = use ? pq.px : 0.0f; S.sgeo[i][2][q] = use ? pq.py : 0.0f;
+                            if (IMG) { S.sfx[i][q] = pq.fx; S.sfy[i][q] = pq.fy; S.so00[i][q] = pq.o00; S.smask[i][q] = pq.mask; }
+                        }
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) S.X2[g][c][k] = make_float2(w[0][c], w[1][c]);
             }
         }
         __syncthreads();
         // ---- (2) photometric mix and min over sources per channel (separable, sliding) ------------
-        pm_stage2_all<0, VAR>(S, n_src, s * PLB_MAX_SRC, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
+        pm_stage2_all<0, VAR, NSMAX>(S, n_src, s * PLB_MAX_SRC, tid, tx0, ty0, H, W, p.C1, p.C2, no_ssim);
         __syncthreads();
         if (STATS) continue;                              // the statistics pass ends here
         // ---- (2b) automask, max over channels on tile + 1 ------------------------------------------
@@ -448,13 +523,17 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
         __syncthreads();
         // ---- (3) gradient of the tile pixels ------------------------------------------------------
         if (GRAD) {
-            float gD = 0.0f, D = 0.0f;
             if (qin) {
-                // d loss / d warped_i(q, c): the selected terms of the 3x3 neighbours p, by (source, channel)
-                float e[NSMAX][3];
+                // d loss / d warped_i(q, c) = the selected terms of the 3x3 neighbours p; each neighbour selects ONE
+                // (source, channel), so its term goes straight through that channel's sampler derivative into
+                // (G_x, G_y) of that source
+                float Gx[NSMAX], Gy[NSMAX];
+                float e[IMG ? NSMAX : 1][3];
                 float gt[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int i = 0; i < NSMAX; ++i) e[i][0] = e[i][1] = e[i][2] = 0.0f;
+                for (int i = 0; i < NSMAX; ++i) Gx[i] = Gy[i] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < (IMG ? NSMAX : 1); ++i) e[i][0] = e[i][1] = e[i][2] = 0.0f;
 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
@@ -463,7 +542,7 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
                         const int sel = S.sel[pk1];
                         const int sc = max(sel, 0), c = sc & 3, i = sc >> 2;
                         const float4 cf = S.coef[c][pk1];
-                        const float xq = S.X[i][c][qk2], tq = S.T[c][qk2];
+                        const float xq = reinterpret_cast<const float*>(&S.X2[i >> 1][c][qk2])[i & 1], tq = S.T2[c][qk2].x;
                         float g = fmaf(cf.y, xq, fmaf(cf.z, tq, cf.x));
                         float gy_ = 0.0f;
                         if (IMG) gy_ = fmaf(cf.y, tq, fmaf(cf.z, xq, S.da[c][pk1]));
@@ -476,11 +555,18 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
                             gy_ *= mx * my;
                         }
                         if (dx == 0 && dy == 0) { g += cf.w; gy_ -= cf.w; }
+                        g = sel >= 0 ? g : 0.0f;
+                        const float gdx = g * S.sdx[i][c][tid], gdy = g * S.sdy[i][c][tid];
 #pragma unroll
-                        for (int ii = 0; ii < NSMAX; ++ii)
-#pragma unroll
-                            for (int cc = 0; cc < 3; ++cc) e[ii][cc] += (sel == cc + 4 * ii) ? g : 0.0f;
+                        for (int ii = 0; ii < NSMAX; ++ii) {
+                            Gx[ii] += (i == ii) ? gdx : 0.0f;
+                            Gy[ii] += (i == ii) ? gdy : 0.0f;
+                        }
                         if (IMG) {
+#pragma unroll
+                            for (int ii = 0; ii < NSMAX; ++ii)
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) e[IMG ? ii : 0][cc] += (sel == cc + 4 * ii) ? g : 0.0f;
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) gt[cc] += (sel >= 0 && c == cc) ? gy_ : 0.0f;
                         }
@@ -489,56 +575,49 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) gta[cc] = fmaf(w_e, gt[cc], gta[cc]);
                 }
-                D = pm_depth<HEAD>(a, pc, s, full, qx, qy, W);
+                const float D = S.sD[tid];
                 const float xf = (float)qx, yf = (float)qy;
                 const float rx = fmaf(pc.kinv[1], yf, pc.kinv[0] * xf) + pc.kinv[2];
                 const float ry = fmaf(pc.kinv[4], yf, pc.kinv[3] * xf) + pc.kinv[5];
                 const float rz = fmaf(pc.kinv[7], yf, pc.kinv[6] * xf) + pc.kinv[8];
+                float gD = 0.0f;
 #pragma unroll
                 for (int i = 0; i < NSMAX; ++i) {
-                    if (i < n_src && (e[i][0] != 0.0f || e[i][1] != 0.0f || e[i][2] != 0.0f)) {
-                        MinProj q;
-                        pm_project(pc.P[i][0], pc.P[i][1], pc.P[i][2], rx, ry, rz, D, H, W, q);
-                        float v[3][4];
-                        pm_taps(pc.src[i], plane, W, q, v);
-                        float Gx = 0.0f, Gy = 0.0f;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float dA = v[c][1] - v[c][0], dB = v[c][3] - v[c][2];
-                            const float top = fmaf(q.fx, dA, v[c][0]), bot = fmaf(q.fx, dB, v[c][2]);
-                            Gx = fmaf(e[i][c], fmaf(q.fy, dB - dA, dA), Gx);
-                            Gy = fmaf(e[i][c], bot - top, Gy);
-                        }
-                        const bool use = q.mask != 0u;
-                        const float gi = use ? w_e * q.inv : 0.0f;
-                        const float gcx = Gx * gi, gcy = Gy * gi;
-                        const float gcz = use ? -(gcx * q.px + gcy * q.py) : 0.0f;
-                        gD += fmaf(gcx, q.Ax, fmaf(gcy, q.Ay, gcz * q.Az));
-                        const float hx = gcx * D, hy = gcy * D, hz = gcz * D;
-                        acc[i][0] = fmaf(hx, rx, acc[i][0]); acc[i][1] = fmaf(hx, ry, acc[i][1]); acc[i][2] = fmaf(hx, rz, acc[i][2]); acc[i][3] += gcx;
-                        acc[i][4] = fmaf(hy, rx, acc[i][4]); acc[i][5] = fmaf(hy, ry, acc[i][5]); acc[i][6] = fmaf(hy, rz, acc[i][6]); acc[i][7] += gcy;
-                        acc[i][8] = fmaf(hz, rx, acc[i][8]); acc[i][9] = fmaf(hz, ry, acc[i][9]); acc[i][10] = fmaf(hz, rz, acc[i][10]); acc[i][11] += gcz;
+                    if (i < n_src) {
+                        const float4 Pa = pc.P[i][0], Pb = pc.P[i][1], Pc = pc.P[i][2];
+                        const float Ax = fmaf(Pa.z, rz, fmaf(Pa.y, ry, Pa.x * rx));
+                        const float Ay = fmaf(Pb.z, rz, fmaf(Pb.y, ry, Pb.x * rx));
+                        const float Az = fmaf(Pc.z, rz, fmaf(Pc.y, ry, Pc.x * rx));
+                        const float gi = w_e * S.sgeo[i][0][tid];
+                        const float gcx = Gx[i] * gi, gcy = Gy[i] * gi;
+                        const float gcz = -(gcx * S.sgeo[i][1][tid] + gcy * S.sgeo[i][2][tid]);
+                        gD += fmaf(gcx, Ax, fmaf(gcy, Ay, gcz * Az));
+                        acc[i][0] = fmaf(gcx, D, acc[i][0]); acc[i][1] = fmaf(gcy, D, acc[i][1]); acc[i][2] = fmaf(gcz, D, acc[i][2]);
+                        acc[i][3] += gcx; acc[i][4] += gcy; acc[i][5] += gcz;
                         if (IMG && pc.g_src[i] != nullptr) {
                             // d loss / d source: e scattered through the bilinear weights (zero-padded taps get nothing)
-                            const float wnw = (1.0f - q.fx) * (1.0f - q.fy), wne = q.fx * (1.0f - q.fy);
-                            const float wsw = (1.0f - q.fx) * q.fy, wse = q.fx * q.fy;
+                            const float fx = S.sfx[i][tid], fy = S.sfy[i][tid];
+                            const int o00 = S.so00[i][tid];
+                            const unsigned mask = S.smask[i][tid];
+                            const float wnw = (1.0f - fx) * (1.0f - fy), wne = fx * (1.0f - fy);
+                            const float wsw = (1.0f - fx) * fy, wse = fx * fy;
                             const float m = p.det ? PM_DET_ONE : w_e;
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
-                                const float ec = m * e[i][c];
+                                const float ec = m * e[IMG ? i : 0][c];
                                 if (ec == 0.0f) continue;
                                 if (p.det) {
-                                    unsigned long long* g = reinterpret_cast<unsigned long long*>(pc.g_src[i]) + (q.o00 + c * plane);
-                                    if (q.mask & 1u) atomicAdd(g, (unsigned long long)__float2ll_rn(wnw * ec));
-                                    if (q.mask & 2u) atomicAdd(g + 1, (unsigned long long)__float2ll_rn(wne * ec));
-                                    if (q.mask & 4u) atomicAdd(g + W, (unsigned long long)__float2ll_rn(wsw * ec));
-                                    if (q.mask & 8u) atomicAdd(g + W + 1, (unsigned long long)__float2ll_rn(wse * ec));
+                                    unsigned long long* g = reinterpret_cast<unsigned long long*>(pc.g_src[i]) + (o00 + c * plane);
+                                    if (mask & 1u) atomicAdd(g, (unsigned long long)__float2ll_rn(wnw * ec));
+                                    if (mask & 2u) atomicAdd(g + 1, (unsigned long long)__float2ll_rn(wne * ec));
+                                    if (mask & 4u) atomicAdd(g + W, (unsigned long long)__float2ll_rn(wsw * ec));
+                                    if (mask & 8u) atomicAdd(g + W + 1, (unsigned long long)__float2ll_rn(wse * ec));
                                 } else {
-                                    float* g = pc.g_src[i] + (q.o00 + c * plane);
-                                    if (q.mask & 1u) atomicAdd(g, wnw * ec);
-                                    if (q.mask & 2u) atomicAdd(g + 1, wne * ec);
-                                    if (q.mask & 4u) atomicAdd(g + W, wsw * ec);
-                                    if (q.mask & 8u) atomicAdd(g + W + 1, wse * ec);
+                                    float* g = pc.g_src[i] + (o00 + c * plane);
+                                    if (mask & 1u) atomicAdd(g, wnw * ec);
+                                    if (mask & 2u) atomicAdd(g + 1, wne * ec);
+                                    if (mask & 4u) atomicAdd(g + W, wsw * ec);
+                                    if (mask & 8u) atomicAdd(g + W + 1, wse * ec);
                                 }
                             }
                         }
@@ -574,11 +653,16 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     }
 
     // ---- block record: warp butterflies, fixed-order sum over warps --------------------------------
+    const float rxq = fmaf(pc.kinv[1], (float)qy, pc.kinv[0] * (float)qx) + pc.kinv[2];
+    const float ryq = fmaf(pc.kinv[4], (float)qy, pc.kinv[3] * (float)qx) + pc.kinv[5];
+    const float rzq = fmaf(pc.kinv[7], (float)qy, pc.kinv[6] * (float)qx) + pc.kinv[8];
 #pragma unroll
     for (int i = 0; i < NSMAX; ++i) {
         float v[16];
 #pragma unroll
-        for (int k = 0; k < 12; ++k) v[k] = acc[i][k];
+        for (int r = 0; r < 3; ++r) {
+            v[4 * r] = acc[i][r] * rxq; v[4 * r + 1] = acc[i][r] * ryq; v[4 * r + 2] = acc[i][r] * rzq; v[4 * r + 3] = acc[i][3 + r];
+        }
         v[12] = (i == 0) ? lsum : 0.0f;
         v[13] = v[14] = v[15] = 0.0f;
         int which;
@@ -685,11 +769,11 @@ static int pm_launch_variant(const PminLaunch& p, dim3 grid, cudaStream_t st) {
     const int dev = current_device();
     if (!attr_set[dev]) {                                    // per device: a process may drive several GPUs
         const cudaError_t e = cudaFuncSetAttribute(photo_min_kernel<GRAD, NSMAX, HEAD, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)sizeof(PminSmem));
+                                                   (int)sizeof(PminSmem<NSMAX, VAR>));
         if (e != cudaSuccess) return (int)e;
         attr_set[dev] = true;
     }
-    photo_min_kernel<GRAD, NSMAX, HEAD, VAR><<<grid, PM_THREADS, sizeof(PminSmem), st>>>(p);
+    photo_min_kernel<GRAD, NSMAX, HEAD, VAR><<<grid, PM_THREADS, sizeof(PminSmem<NSMAX, VAR>), st>>>(p);
     return PLB_OK;
 }
 
@@ -705,6 +789,8 @@ int photo_min_launch(const plb_photo_args* a, cudaStream_t st) {
     PminLaunch p;
     p.a = *a;
     p.L = photo_layout(*a);
+    rc = photo_workspace_prepare(*a, p.L, st);
+    if (rc != PLB_OK) return rc;
     p.tiles_x = (a->W + PM_TW - 1) / PM_TW;
     p.tiles = photo_min_tiles(*a);
     p.w_e = job.term_weight / ((float)a->B * (float)a->H * (float)a->W);
