@@ -172,6 +172,7 @@ struct __align__(16) PminSmem {
 struct Photo { float rp, ca, cb, cc, cl, da; };
 struct Photo2 { float2 rp, ca, cb, cc, cl, da; };
 __device__ __forceinline__ float2 f2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 v_neg(float2 v) { return make_float2(-v.x, -v.y); }
 __device__ __forceinline__ Photo photo_half(const Photo2& t, int q) {
     Photo r;
     r.rp = v_get(t.rp, q); r.ca = v_get(t.ca, q); r.cb = v_get(t.cb, q);
@@ -182,7 +183,7 @@ template <bool WANT_DA>
 __device__ __forceinline__ Photo2 photo_from_sums2(float2 sx, float2 sxx, float2 sxy, float2 sy, float2 syy, float2 xc,
                                                    float2 yc, float C1, float C2, bool no_ssim) {
     Photo2 r;
-    const float2 diff = v_sub(xc, yc);
+    const float2 diff = v_add(xc, v_neg(yc));
     float2 sg;
     sg.x = (diff.x > 0.0f ? 1.0f : 0.0f) - (diff.x < 0.0f ? 1.0f : 0.0f);
     sg.y = (diff.y > 0.0f ? 1.0f : 0.0f) - (diff.y < 0.0f ? 1.0f : 0.0f);
@@ -191,33 +192,33 @@ __device__ __forceinline__ Photo2 photo_from_sums2(float2 sx, float2 sxx, float2
         r.rp = ad; r.ca = r.cb = r.cc = r.da = f2(0.0f); r.cl = sg;
         return r;
     }
-    const float2 i9 = f2(1.0f / 9.0f), neg1 = f2(-1.0f);
+    // (negations are operand modifiers of the packed instructions: free)
+    const float2 i9 = f2(1.0f / 9.0f);
     const float2 mux = v_mul(sx, i9), muy = v_mul(sy, i9);
-    const float2 nmux = v_mul(mux, neg1), nmuy = v_mul(muy, neg1);
-    const float2 nmxx = v_mul(nmux, mux), nmyy = v_mul(nmuy, muy), nmxy = v_mul(nmux, muy);   // -mu_x^2, -mu_y^2, -mu_x mu_y
-    const float2 sigx = v_fma(sxx, i9, nmxx), sigy = v_fma(syy, i9, nmyy), sigxy = v_fma(sxy, i9, nmxy);
+    const float2 mxx = v_mul(mux, mux), myy = v_mul(muy, muy), mxy = v_mul(mux, muy);
+    const float2 sigx = v_fma(sxx, i9, v_neg(mxx)), sigy = v_fma(syy, i9, v_neg(myy)), sigxy = v_fma(sxy, i9, v_neg(mxy));
     const float2 c1 = f2(C1), c2 = f2(C2);
-    const float2 N1 = v_fma(nmxy, f2(-2.0f), c1), N2 = v_fma(sigxy, f2(2.0f), c2);
-    const float2 D1 = v_fma(v_add(nmxx, nmyy), neg1, c1), D2 = v_add(v_add(sigx, sigy), c2);
-    const float2 nDD = v_mul(v_mul(D1, neg1), D2);
+    const float2 N1 = v_fma(f2(2.0f), mxy, c1), N2 = v_fma(f2(2.0f), sigxy, c2);
+    const float2 D1 = v_add(v_add(mxx, myy), c1), D2 = v_add(v_add(sigx, sigy), c2);
+    const float2 DD = v_mul(D1, D2);
     float2 iD;                                           // one reciprocal for both denominators
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iD.x) : "f"(-nDD.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iD.y) : "f"(-nDD.y));
-    iD = v_mul(iD, v_fma(nDD, iD, f2(2.0f)));            // Newton step
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iD.x) : "f"(DD.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iD.y) : "f"(DD.y));
+    iD = v_mul(iD, v_fma(v_neg(DD), iD, f2(2.0f)));      // Newton step
     const float2 iD1 = v_mul(D2, iD), iD2 = v_mul(D1, iD);
     const float2 ssim = v_mul(v_mul(N1, N2), iD);
-    const float2 h = v_mul(v_fma(ssim, neg1, f2(1.0f)), f2(0.5f));
+    const float2 h = v_fma(ssim, f2(-0.5f), f2(0.5f));   // (1 - ssim) / 2
     const float2 hc = make_float2(fminf(fmaxf(h.x, 0.0f), 1.0f), fminf(fmaxf(h.y, 0.0f), 1.0f));
     r.rp = v_fma(f2(0.85f), hc, v_mul(f2(0.15f), ad));
     // d ssim / d x_q = (2/9) { [mu_y (N2 - N1)]/(D1 D2) - ssim mu_x (1/D1 - 1/D2) }  +  x_q (-(2/9) ssim / D2)
     //                  + y_q ((2/9) N1 / (D1 D2));   d rp / d x_q = -0.425 * (that) inside the clamp
     const float kk = -0.425f * 2.0f * (1.0f / 9.0f);
     const float2 k = make_float2((h.x > 0.0f && h.x < 1.0f) ? kk : 0.0f, (h.y > 0.0f && h.y < 1.0f) ? kk : 0.0f);
-    const float2 dN = v_mul(v_sub(N2, N1), iD), ndI = v_sub(iD2, iD1);
+    const float2 dN = v_mul(v_add(N2, v_neg(N1)), iD), ndI = v_add(iD2, v_neg(iD1));
     r.ca = v_mul(k, v_fma(v_mul(ssim, mux), ndI, v_mul(muy, dN)));
     // (SSIM is symmetric in x and y: d ssim / d y_q has the same x_q / y_q coefficients swapped and this constant)
     r.da = WANT_DA ? v_mul(k, v_fma(v_mul(ssim, muy), ndI, v_mul(mux, dN))) : f2(0.0f);
-    r.cb = v_mul(v_mul(k, neg1), v_mul(ssim, iD2));
+    r.cb = v_mul(v_neg(k), v_mul(ssim, iD2));
     r.cc = v_mul(k, v_mul(N1, iD));
     r.cl = v_mul(f2(0.15f), sg);
     return r;
@@ -268,20 +269,31 @@ __device__ __forceinline__ void pm_stage2(SM& S, int g, int n_here, int map0, in
                 const Photo2 t2 = photo_from_sums2<VAR == PM_VAR_IMG>(
                     v_add(v_add(hx[0], hx[1]), hx[2]), v_add(v_add(hxx[0], hxx[1]), hxx[2]), v_add(v_add(hxy[0], hxy[1]), hxy[2]),
                     v_add(v_add(hy[0], hy[1]), hy[2]), v_add(v_add(hyy[0], hyy[1]), hyy[2]), xc, yc, C1, C2, no_ssim);
-                Photo m; m.rp = 3.0e38f; m.ca = m.cb = m.cc = m.cl = m.da = 0.0f;
+                Photo m;
                 int mi = i0;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    if (q == 1 && n_here < 2) continue;   // (block-uniform) the pair's second half is empty
-                    Photo t = photo_half(t2, q);
-                    if (VAR == PM_VAR_STATS) {
-                        // the map's own statistics: every pixel of the image once (the tile's interior)
-                        if (in && col >= 1 && col <= PM_TW && o >= 1 && o <= PM_TH) { st[q][0] += t.rp; st[q][1] = fmaf(t.rp, t.rp, st[q][1]); }
-                    } else if (t.rp > thr[q]) {
-                        // torch.clamp(max=thr): the value is the threshold and no gradient passes (losses.py:82)
-                        t.rp = thr[q]; t.ca = t.cb = t.cc = t.cl = t.da = 0.0f;
+                if (VAR == PM_VAR_STATS) {
+                    // the map's own statistics: every pixel of the image once (the tile's interior)
+                    if (in && col >= 1 && col <= PM_TW && o >= 1 && o <= PM_TH) {
+                        st[0][0] += t2.rp.x; st[0][1] = fmaf(t2.rp.x, t2.rp.x, st[0][1]);
+                        st[1][0] += t2.rp.y; st[1][1] = fmaf(t2.rp.y, t2.rp.y, st[1][1]);
                     }
-                    if (t.rp < m.rp) { m = t; mi = i0 + q; }
+                    m.rp = 0.0f; m.ca = m.cb = m.cc = m.cl = m.da = 0.0f;
+                } else {
+                    // torch.clamp(max=thr): a clamped value is the threshold and passes no gradient (losses.py:82); then
+                    // the smaller of the two halves (first one on ties, a NaN never wins) - one select per field
+                    const bool c0 = t2.rp.x > thr[0], c1 = t2.rp.y > thr[1];
+                    const float r0 = c0 ? thr[0] : t2.rp.x, r1 = c1 ? thr[1] : t2.rp.y;
+                    const bool take0 = r0 < 3.0e38f;
+                    const float base = take0 ? r0 : 3.0e38f;
+                    const bool take1 = n_here >= 2 && r1 < base;
+                    const bool dead = take1 ? c1 : (c0 || !take0);      // the chosen term carries no gradient
+                    m.rp = take1 ? r1 : base;
+                    mi = take1 ? i0 + 1 : i0;
+                    m.ca = dead ? 0.0f : (take1 ? t2.ca.y : t2.ca.x);
+                    m.cb = dead ? 0.0f : (take1 ? t2.cb.y : t2.cb.x);
+                    m.cc = dead ? 0.0f : (take1 ? t2.cc.y : t2.cc.x);
+                    m.cl = dead ? 0.0f : (take1 ? t2.cl.y : t2.cl.x);
+                    m.da = dead ? 0.0f : (take1 ? t2.da.y : t2.da.x);
                 }
                 if (VAR == PM_VAR_STATS) {
                 } else if (MODE >= 2) {
