@@ -36,6 +36,9 @@ WORKLOADS = {
     "c2": dict(B=12, H=192, W=640, n_src=2, n_scales=4, variant="live"),
     "c3": dict(B=8, H=320, W=1024, n_src=3, n_scales=4, variant="live"),
     "c5": dict(B=64, H=192, W=640, n_src=2, n_scales=4, variant="live"),
+    # BASELINE.json configs[4] as worded: 4 scales + EDGE-AWARE smoothness (a term the reference does not have: its own
+    # smoothness is the 2nd-order one of c5) - the live photometric composition + plb_edge_smooth_loss on the target's pyramid
+    "c5e": dict(B=64, H=192, W=640, n_src=2, n_scales=4, variant="live_edge"),
     "headline": dict(B=12, H=192, W=640, n_src=2, n_scales=1, variant="dir0"),
     # the same single-direction kernel at the per-GPU batch of BASELINE.json configs[4] (fixed launch costs amortised)
     "headline64": dict(B=64, H=192, W=640, n_src=2, n_scales=1, variant="dir0"),
@@ -51,7 +54,9 @@ WORKLOADS = {
 def workload_name(wl, cfg):
     return "%s: %dx%d batch %d/GPU, 1 target + %d source frames, %d-scale %s loss fwd+bwd" % (
         wl, cfg["H"], cfg["W"], cfg["B"], cfg["n_src"], cfg["n_scales"],
-        {"live": "reference-live Losses.forward (mode='min', which the reference computes as a MEAN over sources, losses.py:226-228; 2 directions, L1 + 2nd-order smoothness)",
+        {"live_edge": "reference-live photometric term (mode='min' = mean over sources, 2 directions, L1) + edge-aware "
+                      "1st-order smoothness of the target's disparity pyramid (monodepth2 form; not in the reference)",
+         "live": "reference-live Losses.forward (mode='min', which the reference computes as a MEAN over sources, losses.py:226-228; 2 directions, L1 + 2nd-order smoothness)",
          "dir0": "single-direction L1",
          "min": "single-direction SSIM+L1 min-reprojection + automask (dormant path)",
          "minclip": "single-direction SSIM+L1 min-reprojection + automask with the mean + 0.5 std clip of every map (dormant path, "
@@ -66,7 +71,7 @@ def algorithmic_bytes_per_px(cfg):
         reads = 12.0 + 12.0 * n_src + pyr
         return 2.0 * reads + pyr
     total = direction(cfg["n_src"])
-    if cfg["variant"] == "live":
+    if cfg["variant"] in ("live", "live_edge"):
         total += direction(1)
     return total   # "min": same streams as one direction (the automask re-reads the sources it already holds)
 
@@ -183,6 +188,11 @@ def oracle_step(cfg, inp):
         sum(loss).backward()
         return loss[0].detach() + loss[1].detach()
     depths = O.disp_to_depth(disp)
+    if cfg["variant"] == "live_edge":
+        loss = O.reprojection_loss(inp["tgt"], inp["ref_imgs"], depths, poses, inp["intrinsics"]) + \
+            O.edge_aware_smooth_loss(disp[0], inp["tgt"])
+        loss.backward()
+        return loss.detach()
     if cfg["variant"] in ("min", "minclip"):
         loss = O.min_reprojection_loss(inp["tgt"], inp["ref_imgs"], depths[0], poses, inp["intrinsics"],
                                        clip_loss=0.5 if cfg["variant"] == "minclip" else None)
@@ -205,7 +215,7 @@ def cpu_reference_run(cfg, steps, warmup, budget_s=25.0):
     Bs = min(CPU_ARM_MAX_BATCH, cfg["B"])
     n_src = cfg["n_src"]
     inp = synth.make_photo_inputs(Bs, cfg["H"], cfg["W"], n_src=n_src, n_scales=cfg["n_scales"], seed=1234,
-                                  n_depth_frames=2 if cfg["variant"] == "live" else 1)
+                                  n_depth_frames=2 if cfg["variant"] in ("live", "live_edge") else 1)
     t_start = time.perf_counter()
     n_warm = max(1, min(warmup, 2))
     for _ in range(n_warm):
@@ -273,7 +283,7 @@ def make_sets(cfg, n_sets, seed, dev):
     sets = []
     for k in range(n_sets):
         inp = synth.make_photo_inputs(cfg["B"], cfg["H"], cfg["W"], n_src=cfg["n_src"], n_scales=cfg["n_scales"],
-                                      seed=seed + 17 * k, n_depth_frames=2 if cfg["variant"] == "live" else 1)
+                                      seed=seed + 17 * k, n_depth_frames=2 if cfg["variant"] in ("live", "live_edge") else 1)
         sets.append(inp)
     return sets
 
@@ -291,6 +301,10 @@ def step_fn(criterion, g, cfg):
     if cfg["variant"] == "live":
         loss = criterion.forward(g["tgt"], g["ref_imgs"], disp, poses, g["intrinsics"], None)
         total = loss[0] + loss[1]
+    elif cfg["variant"] == "live_edge":
+        from plb200 import ops
+        mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp, poses, g["intrinsics"], do_smooth=False, deterministic=True)
+        total = mam + criterion.edge_aware_smooth_loss(disp[0], g["tgt"])
     elif cfg["variant"] in ("min", "minclip"):
         from plb200 import ops, _lib
         mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp[:1], poses, g["intrinsics"], do_smooth=False,
@@ -543,7 +557,7 @@ def time_photo_kernel(criterion, gpu_sets, cfg, dev, iters):
     # launch only the fused photometric kernel (forward + unit-upstream gradients)
     calls = []
     for g in gpu_sets:
-        pyr = g["disparity"] if cfg["variant"] == "live" else g["disparity"][:1]
+        pyr = g["disparity"] if cfg["variant"] in ("live", "live_edge") else g["disparity"][:1]
         from plb200 import _lib
         lcfg = ops.LossConfig(cfg["n_src"], [len(p) for p in pyr], do_smooth=False,
                               mode=_lib.PHOTO_MIN_REPROJ if cfg["variant"] in ("min", "minclip") else _lib.PHOTO_L1_MEAN,

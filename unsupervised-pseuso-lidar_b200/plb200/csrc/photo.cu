@@ -1692,6 +1692,8 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
     if (head && img_grad) return PLB_EINVAL;       // image gradients: disparity / depth inputs only
     p.strips = (a->W + 31) / 32;
     p.n_pairs = a->n_jobs * a->B;
+    int max_src = 0;
+    for (int j = 0; j < a->n_jobs; ++j) max_src = a->jobs[j].n_src > max_src ? a->jobs[j].n_src : max_src;
     long long wsum = 0, pair_w_min = 1LL << 62;
     int usum = 0;
     for (int j = 0; j < PLB_MAX_JOBS; ++j) {
@@ -1716,7 +1718,9 @@ int photo_l1_launch(const plb_photo_args* a, cudaStream_t st) {
                 int w = cb.kind == PH_KIND_SINGLE ? PH_W_ODD : PH_W_PAIR;
                 if (photo_scale_mode(*a, j, cb.s0) != PH_SM_FULL) w += PH_W_LOW;
                 if (cb.kind == PH_KIND_SCALEPAIR) {
-                    w += PH_W_SPAIR;
+                    // (measured, profiles/README.md: with at most two sources per job a scale pair is cheaper relative
+                    // to a source pair than in the three- / four-source kernel variants)
+                    w += max_src <= 2 ? PH_W_SPAIR2 : PH_W_SPAIR;
                     if (photo_scale_mode(*a, j, cb.s1) != PH_SM_FULL) w += PH_W_LOW;
                 }
                 p.combo_w[j][c] = w;

@@ -61,6 +61,9 @@ constexpr int PH_REC_ID = 63;
 #ifndef PH_W_SPAIR
 #define PH_W_SPAIR 14              // ... and a scale pair (two gradient maps instead of one)
 #endif
+#ifndef PH_W_SPAIR2
+#define PH_W_SPAIR2 8              // ... the same when no job has more than two sources (c2 187 -> 180 us, c5 950 -> 891 us)
+#endif
 #ifndef PH_GRID_MULT
 #define PH_GRID_MULT 1            // blocks launched per resident block slot
 #endif
