@@ -15,6 +15,8 @@ and write into `step.inputs` directly.
 """
 import torch
 
+from . import ops
+
 
 class GradBuffers:
     def __init__(self, disparity, poses):
@@ -54,27 +56,34 @@ class CapturedLossStep:
             for d in fr:
                 d.grad = None
         i["poses"].grad = None
-        loss = self.criterion.forward(i["tgt"], i["ref_imgs"], i["disparity"], i["poses"], i["intrinsics"], None)
-        (loss[0] + loss[1]).backward()
+        # the step owns its backward call, so the upstream gradient of both losses is exactly 1: no guarded relaunch
+        with ops.unit_upstream():
+            loss = self.criterion.forward(i["tgt"], i["ref_imgs"], i["disparity"], i["poses"], i["intrinsics"], None)
+            total = loss[0] + loss[1]
+            total.backward()
+        self.total = total.detach()
         return [l.detach() for l in loss]
 
     def __call__(self, tgt=None, ref_imgs=None, disparity=None, poses=None, intrinsics=None):
-        """Replay; any argument given is first copied into its static buffer (same shapes as at capture)."""
+        """Replay; any argument given is first copied into its static buffer (same shapes as at capture) - all of them
+        in ONE multi-tensor copy, so the host cost does not grow with the number of pyramid levels."""
         i = self.inputs
-        with torch.no_grad():
-            if tgt is not None:
-                i["tgt"].copy_(tgt)
-            if ref_imgs is not None:
-                for dst, src in zip(i["ref_imgs"], ref_imgs):
-                    dst.copy_(src)
-            if disparity is not None:
-                for dfr, sfr in zip(i["disparity"], disparity):
-                    sfr = sfr if isinstance(sfr, (list, tuple)) else [sfr]
-                    for dst, src in zip(dfr, sfr):
-                        dst.copy_(src)
-            if poses is not None:
-                i["poses"].copy_(poses)
-            if intrinsics is not None:
-                i["intrinsics"].copy_(intrinsics)
+        dst, src = [], []
+        if tgt is not None:
+            dst.append(i["tgt"]); src.append(tgt)
+        if ref_imgs is not None:
+            dst += list(i["ref_imgs"]); src += list(ref_imgs)
+        if disparity is not None:
+            for dfr, sfr in zip(i["disparity"], disparity):
+                dst += list(dfr); src += list(sfr if isinstance(sfr, (list, tuple)) else [sfr])
+        if poses is not None:
+            dst.append(i["poses"]); src.append(poses)
+        if intrinsics is not None:
+            dst.append(i["intrinsics"]); src.append(intrinsics)
+        if dst:
+            if len(dst) != len(src):
+                raise ValueError("arguments do not match the captured step's inputs")
+            with torch.no_grad():
+                torch._foreach_copy_(dst, [s_.detach() for s_ in src])
         self.graph.replay()
         return self.loss, self.grads

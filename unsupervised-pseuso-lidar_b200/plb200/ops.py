@@ -212,6 +212,32 @@ def _launch_loss(cfg, tgt, refs, poses, K, pyr, want_grad, g_pyr, g_poses, g_tgt
             (ws_photo if cfg.do_photo else None, ws_smooth if cfg.do_smooth else None))
 
 
+_unit_upstream = False
+
+
+class unit_upstream:
+    """Context: the caller vouches that every upstream gradient of the fused losses evaluated inside is exactly 1 - a
+    step that calls `(loss[0] + loss[1]).backward()` itself (plb200/graphed.py).  The gradients written by the forward
+    launch then stand, and backward issues no guarded relaunch (five launches that would exit at once)."""
+
+    def __enter__(self):
+        global _unit_upstream
+        self._old = _unit_upstream
+        _unit_upstream = True
+        from . import _tb
+        if _tb.mod is not None and hasattr(_tb.mod, "set_unit_upstream"):
+            _tb.mod.set_unit_upstream(True)
+        return self
+
+    def __exit__(self, *exc):
+        global _unit_upstream
+        _unit_upstream = self._old
+        from . import _tb
+        if _tb.mod is not None and hasattr(_tb.mod, "set_unit_upstream"):
+            _tb.mod.set_unit_upstream(self._old)
+        return False
+
+
 def _relaunch_guarded(args, up, scratch):
     """The backward pass of a fused forward: the SAME launches again (same buffers, same stream) with the real
     upstream scalars behind the device-side "all upstream == 1" guard.  The argument structs of the forward call
@@ -299,7 +325,9 @@ class FusedLossFn(torch.autograd.Function):
                 g_refs = [torch.zeros_like(r) for r in refs]
         scratch = torch.empty(2, dtype=torch.float32, device=dev)
         args, ctx.args = getattr(ctx, "args", None), None
-        if not (skip and args is not None and _relaunch_guarded(args, up, scratch)):
+        if skip and _unit_upstream:
+            pass                                            # ops.unit_upstream(): the forward launch's gradients stand
+        elif not (skip and args is not None and _relaunch_guarded(args, up, scratch)):
             _launch_loss(cfg, tgt, refs, poses, K, pyr, True, g_pyr, g_poses, g_tgt, g_refs, scratch, up, skip)
         # the gradient buffers leave with autograd: holding on to them would make AccumulateGrad CLONE every one of
         # them into .grad (a device copy per tensor) instead of adopting the buffer
