@@ -81,6 +81,10 @@ struct CloudHost {
     double rf_u, rf_v, b_x, b_y;
     double a0x, a0y, a0c, c0;          // cloud_x = d * (col * a0x + row * a0y + a0c) + c0
     double a2x, a2y, a2c, c2;          // cloud_z likewise
+    // the same affine forms in fp32 with a rigorous error bound: a pixel whose |value| exceeds m * |d| + t is decided
+    // by the fp32 sign (two FFMAs per coordinate, no float -> double conversion), every other pixel takes the fp64 test
+    float fa0x, fa0y, fa0c, fc0, fm0, ft0;
+    float fa2x, fa2y, fa2c, fc2, fm2, ft2;     // fc2 = c2 - 1: the test is cloud_z - 1 < 0
 };
 
 __device__ __forceinline__ bool cloud_valid(const CloudConst& cc, const CloudHost& h, int col, int row, double A0, double A2,
@@ -120,11 +124,26 @@ __device__ __forceinline__ void cloud_load(const float* depth, size_t img_off, i
 // validity bits of this thread's CL_ITEMS consecutive pixels
 __device__ __forceinline__ unsigned cloud_mask(const CloudConst& cc, const CloudHost& h, int W, int p0, int npx,
                                                int row, int col, const float (&dv)[CL_ITEMS]) {
-    double A0 = __fma_rn((double)col, h.a0x, __fma_rn((double)row, h.a0y, h.a0c));
-    double A2 = __fma_rn((double)col, h.a2x, __fma_rn((double)row, h.a2y, h.a2c));
     unsigned vmask = 0;
     if (p0 + CL_ITEMS <= npx && col + CL_ITEMS <= W) {
-        // all four pixels exist and share a row (all but ~0.4 % of the calls): no per-pixel bound or wrap logic
+        // all four pixels exist and share a row (all but ~0.4 % of the calls): no per-pixel bound or wrap logic.
+        // fp32 first: |fp32 value - exact value| <= 4 u (Amax |d| + |c|) (inputs rounded once, two FMAs for A, one for the
+        // value); the host passes m = 16 u Amax, t = 16 u |c| + 1e-6, so a value beyond m |d| + t has the exact sign and
+        // lies further than the fp64 test's own margin from its threshold.  NaN / inf / |d| >= 1e5 fail the comparison.
+        const float r0 = fmaf((float)row, h.fa0y, h.fa0c), r2 = fmaf((float)row, h.fa2y, h.fa2c);
+        bool all_dec = true;
+        unsigned fmask = 0;
+#pragma unroll
+        for (int k = 0; k < CL_ITEMS; ++k) {
+            const float d = dv[k], ad = fabsf(d), xc = (float)(col + k);
+            const float v0 = fmaf(d, fmaf(xc, h.fa0x, r0), h.fc0), v2 = fmaf(d, fmaf(xc, h.fa2x, r2), h.fc2);
+            const bool dec = fabsf(v0) > fmaf(h.fm0, ad, h.ft0) && fabsf(v2) > fmaf(h.fm2, ad, h.ft2) && ad < 1.0e5f;
+            all_dec = all_dec && dec;
+            if (v0 >= 0.0f && v2 < 0.0f) fmask |= 1u << k;
+        }
+        if (all_dec) return fmask;
+        double A0 = __fma_rn((double)col, h.a0x, __fma_rn((double)row, h.a0y, h.a0c));
+        double A2 = __fma_rn((double)col, h.a2x, __fma_rn((double)row, h.a2y, h.a2c));
 #pragma unroll
         for (int k = 0; k < CL_ITEMS; ++k) {
             if (cloud_valid(cc, h, col + k, row, A0, A2, dv[k])) vmask |= 1u << k;
@@ -132,6 +151,8 @@ __device__ __forceinline__ unsigned cloud_mask(const CloudConst& cc, const Cloud
         }
         return vmask;
     }
+    double A0 = __fma_rn((double)col, h.a0x, __fma_rn((double)row, h.a0y, h.a0c));
+    double A2 = __fma_rn((double)col, h.a2x, __fma_rn((double)row, h.a2y, h.a2c));
 #pragma unroll
     for (int k = 0; k < CL_ITEMS; ++k) {
         if (p0 + k < npx && cloud_valid(cc, h, col, row, A0, A2, dv[k])) vmask |= 1u << k;
@@ -266,17 +287,17 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
         while (col >= a.W) { col -= a.W; ++row; }
         const float d = s_dep[r];
         double o[4];
-        // the reference's operation order with constant-divisor divisions; a coordinate within 1e-9 of its
-        // threshold (or huge) is re-evaluated with IEEE divisions, as the values always were
+        // the reference's operation order with constant-divisor divisions
         if (w_zero) {
             cloud_point3(cc, col, row, d, o);
             o[3] = 0.0;
         } else {
             cloud_point<false>(cc, col, row, d, o);
         }
-        const bool safe = fabs(o[0]) > 1e-9 && fabs(o[2] - 1.0) > 1e-9 && fabs(o[0]) < 1e12 && fabs(o[2]) < 1e12 &&
-                          fabs(o[1]) < 1e12;
-        if (!safe) cloud_point<true>(cc, col, row, d, o);
+        // (an infinite depth can be a kept point under odd calibrations: the constant-divisor division turns it into NaN
+        // where the IEEE division gives inf.  One fp32 compare instead of range checks on the fp64 results: for a
+        // finite depth the quotients are finite and the correction step is exact)
+        if (!(fabsf(d) < 1.0e30f)) cloud_point<true>(cc, col, row, d, o);
         const size_t pos = out0 + j;
         if (a.cloud_f64 != nullptr) {
             double2* q = reinterpret_cast<double2*>(a.cloud_f64 + pos * 4);
@@ -316,6 +337,13 @@ int cloud_launch(const plb_cloud_args* a, cudaStream_t st) {
         h.c0 = h.b_x * T0[0] + h.b_y * T0[1] + T0[3];
         h.a2x = T2[0] / f_u; h.a2y = T2[1] / f_v; h.a2c = T2[2] - c_u * h.a2x - c_v * h.a2y;
         h.c2 = h.b_x * T2[0] + h.b_y * T2[1] + T2[3];
+        const double u = 1.0 / 16777216.0;          // 2^-24
+        const double amax0 = fabs(h.a0x) * a->W + fabs(h.a0y) * a->H + fabs(h.a0c);
+        const double amax2 = fabs(h.a2x) * a->W + fabs(h.a2y) * a->H + fabs(h.a2c);
+        h.fa0x = (float)h.a0x; h.fa0y = (float)h.a0y; h.fa0c = (float)h.a0c; h.fc0 = (float)h.c0;
+        h.fa2x = (float)h.a2x; h.fa2y = (float)h.a2y; h.fa2c = (float)h.a2c; h.fc2 = (float)(h.c2 - 1.0);
+        h.fm0 = (float)(16.0 * u * amax0 * 1.0001); h.ft0 = (float)(16.0 * u * fabs(h.c0) + 1e-6);
+        h.fm2 = (float)(16.0 * u * amax2 * 1.0001); h.ft2 = (float)(16.0 * u * fabs(h.c2 - 1.0) + 1e-6);
     }
     cloud_count_kernel<<<dim3((tiles + CC_WARPS - 1) / CC_WARPS, a->B), CC_WARPS * 32, 0, st>>>(*a, h, tiles);
     ++g_launches;
