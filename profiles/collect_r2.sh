@@ -12,7 +12,7 @@ python profiles/trace_step.py headline 40 > $O/r2_timeline_headline.txt 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
 $NCU -k regex:photo_l1 -s 2 -c 1 -o $O/r2_photo_l1_c2 python profiles/prof_photo.py c2 4 > $O/r2_ncu_a.log 2>&1
 $NCU -k regex:photo_l1\|photo_finalize -s 4 -c 2 -o $O/r2_photo_l1_headline python profiles/prof_photo.py headline 4 > $O/r2_ncu_b.log 2>&1
-$NCU -k regex:upsample\|smooth -s 4 -c 2 -o $O/r2_aux_c2 python profiles/prof_photo.py c2 4 > $O/r2_ncu_c.log 2>&1
+$NCU -k regex:lowres_merge\|smooth -s 4 -c 2 -o $O/r2_aux_c2 python profiles/prof_photo.py c2 4 > $O/r2_ncu_c.log 2>&1
 $NCU -k regex:photo_min -s 2 -c 1 -o $O/r2_photo_min_c2min python profiles/prof_photo.py c2min 4 > $O/r2_ncu_d.log 2>&1
 $NCU -k regex:cloud_ -s 4 -c 2 -o $O/r2_cloud python profiles/prof_cloud.py > $O/r2_ncu_e.log 2>&1
 python profiles/kbench.py headline headline64 c1 c2 c3 c5 c2min > $O/r2_kbench.txt 2>&1
