@@ -168,8 +168,10 @@ __device__ __forceinline__ unsigned cloud_mask(const CloudConst& cc, const Cloud
 
 // Workspace: int32 counts [B][tiles], then uint32 validity words [B][tiles][32]: bit 4 * it + k of word `lane` is
 // pixel tile * 1024 + it * 128 + lane * 4 + k - i.e. the four pixels thread t = it * 32 + lane of launch 2 owns.
+// (the per-image count rows are padded to a multiple of four tiles: 16-byte loads of the counts)
+__host__ __device__ inline int cloud_tiles_pad(int tiles) { return (tiles + 3) & ~3; }
 __host__ __device__ inline size_t cloud_words_offset(int B, int tiles) {
-    return ((size_t)B * tiles * sizeof(int32_t) + 255) / 256 * 256;
+    return ((size_t)B * cloud_tiles_pad(tiles) * sizeof(int32_t) + 255) / 256 * 256;
 }
 
 // launch 1: validity bits and valid points per tile; one warp per tile
@@ -183,23 +185,33 @@ cloud_count_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h, 
     const CloudConst cc = cloud_const(a, h);
     const float* depth = a.depth + (size_t)b * npx;
     const int pbase = blk * CL_TILE + lane * CL_ITEMS;
-    constexpr int NIT = CL_TILE / 128;
-    float dv[NIT][CL_ITEMS];
+    // ONE copy of the mask code, iterated (an unrolled tile is ~1000 instructions = 16 KB that every warp walks once:
+    // the 6 KB L0 instruction cache never hits); three 128-bit loads per lane stay in flight ahead of the evaluation
+    constexpr int NIT = CL_TILE / 128, AHEAD = 3;
+    float ring[AHEAD][CL_ITEMS];
 #pragma unroll
-    for (int it = 0; it < NIT; ++it) cloud_load(depth, (size_t)b * npx, pbase + it * 128, npx, dv[it]);
+    for (int it = 0; it < AHEAD; ++it) cloud_load(depth, (size_t)b * npx, pbase + it * 128, npx, ring[it]);
     int row = pbase / W, col = pbase - row * W;
     unsigned word = 0;
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < NIT; ++it) {
+        float nxt[CL_ITEMS];
+        cloud_load(depth, (size_t)b * npx, pbase + (it + AHEAD) * 128, npx, nxt);      // zeros beyond the image
         const int p0 = pbase + it * 128;
-        if (p0 < npx) word |= cloud_mask(cc, h, W, p0, npx, row, col, dv[it]) << (4 * it);
+        if (p0 < npx) word |= cloud_mask(cc, h, W, p0, npx, row, col, ring[0]) << (4 * it);
         col += 128;
         while (col >= W) { col -= W; ++row; }
+#pragma unroll
+        for (int k = 0; k < CL_ITEMS; ++k) {
+#pragma unroll
+            for (int r = 0; r + 1 < AHEAD; ++r) ring[r][k] = ring[r + 1][k];
+            ring[AHEAD - 1][k] = nxt[k];
+        }
     }
     int mine = __popc(word);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if (lane == 0) ((int32_t*)a.workspace)[(size_t)b * tiles + blk] = mine;
+    if (lane == 0) ((int32_t*)a.workspace)[(size_t)b * cloud_tiles_pad(tiles) + blk] = mine;
     uint32_t* words = (uint32_t*)((char*)a.workspace + cloud_words_offset(a.B, tiles));
     words[((size_t)b * tiles + blk) * 32 + lane] = word;
 }
@@ -225,7 +237,7 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     cloud_load(depth, (size_t)b * npx, p0, npx, dv);
     // exclusive prefix of this tile: counts of tiles [0, blk) of image b, fixed order (integers)
     {
-        const int32_t* counts = (const int32_t*)a.workspace + (size_t)b * tiles;
+        const int32_t* counts = (const int32_t*)a.workspace + (size_t)b * cloud_tiles_pad(tiles);
         int part = 0;
         for (int k = tid; k < blk; k += CL_THREADS) part += __ldg(counts + k);
 #pragma unroll
@@ -310,6 +322,138 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
     }
 }
 
+// launch 2 without decimation (sparsity 0 / 1, the reference's default): no compaction through shared memory, no
+// block at all.  A warp owns 1024 / CD_WPT consecutive pixels and walks them 32 at a time, ONE pixel per lane, in a
+// rolled loop (one copy of the fp64 chain in the instruction cache, its constants hoisted): the pixel's validity bit
+// comes from the word of the lane that owned it in launch 1 (one shuffle), its output row is the tile's base (the counts
+// of the tiles before it: 16-byte loads of the padded count row) + the valid pixels of the tile before the warp's chunk
+// (one popc + warp reduction of the words) + its rank in the ballot.  Valid lanes run the exact chain in place and
+// write rows that are consecutive across the warp.  No shared memory, no barrier, no per-point row / column
+// reconstruction; depths are loaded CD_AHEAD steps ahead.
+// v, as a value the compiler cannot trace back to the constant bank (blockIdx.z is 0: the grid is two-dimensional)
+__device__ __forceinline__ double pin_reg(double v) { return __longlong_as_double(__double_as_longlong(v) ^ (long long)blockIdx.z); }
+constexpr int CD_WPT = 1;                         // warps per 1024-pixel tile
+constexpr int CD_WARPS = 4;                       // warps per block
+constexpr int CD_GROUPS = 8 / CD_WPT;             // 128-pixel groups of launch 1 per warp (4 validity bits of every word each)
+
+// F64 / F32: which cloud layouts are written; AUX: the call also wants the index and / or the validity mask
+template <bool F64, bool F32, bool AUX>
+__global__ void __launch_bounds__(CD_WARPS * 32)
+cloud_write_direct_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h, int tiles) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * CD_WARPS + (threadIdx.x >> 5);
+    const int blk = gw / CD_WPT, part = gw - blk * CD_WPT;
+    if (blk >= tiles) return;
+    const int npx = a.H * a.W, W = a.W;
+    const int chunk = blk * CL_TILE + part * (128 * CD_GROUPS);
+    const float* dp = a.depth + (size_t)b * npx + chunk + lane;          // this lane's pixel of the current step
+    int p = chunk + lane;
+    float ring[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) ring[s] = p + 32 * s < npx ? __ldg(dp + 32 * s) : 0.0f;
+    const uint32_t* words = (const uint32_t*)((const char*)a.workspace + cloud_words_offset(a.B, tiles));
+    const unsigned word = __ldg(words + ((size_t)b * tiles + blk) * 32 + lane);
+    int base = 0;
+    {
+        const int4* c4 = reinterpret_cast<const int4*>((const int32_t*)a.workspace + (size_t)b * cloud_tiles_pad(tiles));
+        for (int k = lane; 4 * k < blk; k += 32) {
+            const int4 c = __ldg(c4 + k);
+            const int left = blk - 4 * k;
+            base += c.x + (left > 1 ? c.y : 0) + (left > 2 ? c.z : 0) + (left > 3 ? c.w : 0);
+        }
+        base = __reduce_add_sync(0xffffffffu, base);
+    }
+    const int below = __reduce_add_sync(0xffffffffu, __popc(word & ((1u << (4 * CD_GROUPS * part)) - 1u)));
+    if (blk == tiles - 1 && part == CD_WPT - 1) {
+        const int total = __reduce_add_sync(0xffffffffu, __popc(word));
+        if (lane == 0 && a.count != nullptr) a.count[b] = base + total;
+    }
+    if (chunk >= npx) return;
+    // the chain's constants live in registers for the whole loop (left to itself the compiler re-loads each one from
+    // the constant bank inside the divergent block: ~14 uniform loads per step)
+    CloudConst cc = cloud_const(a, h);
+    cc.c_u = pin_reg(cc.c_u); cc.c_v = pin_reg(cc.c_v); cc.f_u = pin_reg(cc.f_u); cc.f_v = pin_reg(cc.f_v);
+    cc.b_x = pin_reg(cc.b_x); cc.b_y = pin_reg(cc.b_y); cc.rf_u = pin_reg(cc.rf_u); cc.rf_v = pin_reg(cc.rf_v);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cc.Ti[k] = pin_reg(cc.Ti[k]);
+    const bool w_zero = a.Tinv[12] == 0.0 && a.Tinv[13] == 0.0 && a.Tinv[14] == 0.0 && a.Tinv[15] == 0.0;
+    unsigned mine = word >> (4 * CD_GROUPS * part);            // bits 4 g + k: pixel 128 g + 4 lane + k of the chunk
+    const unsigned lt = (1u << lane) - 1u;
+    const int src = lane >> 2;
+    int orow = base + below;                                  // output row (within image b) of the step's first valid pixel
+    double* const o64 = F64 ? a.cloud_f64 + (size_t)b * npx * 4 : nullptr;
+    float4* const o32 = F32 ? reinterpret_cast<float4*>(a.cloud_f32) + (size_t)b * npx : nullptr;
+    int32_t* const oidx = AUX && a.index != nullptr ? a.index + (size_t)b * npx : nullptr;
+    uint8_t* const oval = AUX && a.valid != nullptr ? a.valid + (size_t)b * npx : nullptr;
+    int row = chunk / W, col = chunk - row * W + lane;
+#pragma unroll 1
+    for (int g = 0; g < CD_GROUPS; ++g) {
+        // the next group's four depths, all issued here: they land while this group's four steps run (the copy into
+        // `ring` at the end of the group must not wait for a load issued one step earlier)
+        float nxt[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) nxt[s] = (g + 1 < CD_GROUPS && p + 128 + 32 * s < npx) ? __ldg(dp + 128 + 32 * s) : 0.0f;
+        // pixel p = chunk + 128 g + 32 s + lane of step s: its bit sits with lane 8 s + lane / 4 of launch 1
+        bool odd = false;                                     // a depth the constant-divisor chain cannot take (inf / huge / NaN)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) odd = odd || !(fabsf(ring[s]) < 1.0e30f);
+        if (w_zero && !__any_sync(0xffffffffu, odd)) {
+            // the common case, ONE basic block for the four steps: every lane runs the chain (the warp would anyway),
+            // only the stores are predicated - the four independent chains interleave
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const float d = ring[s];
+                if (col >= W) { col -= W; ++row; }            // W >= 32 (host dispatch): one wrap per step at most
+                const bool v = (__shfl_sync(0xffffffffu, mine, 8 * s + src) >> (lane & 3)) & 1u;
+                const unsigned ball = __ballot_sync(0xffffffffu, v);
+                if (AUX && oval != nullptr && p < npx) oval[p] = v;
+                const int r = orow + __popc(ball & lt);
+                double o[4];
+                cloud_point3(cc, col, row, d, o);
+                if (v) {
+                    if (F64) {
+                        double2* q = reinterpret_cast<double2*>(o64) + (size_t)r * 2;
+                        __stcs(q, make_double2(o[0], o[1]));
+                        __stcs(q + 1, make_double2(o[2], 0.0));
+                    }
+                    if (F32) __stcs(o32 + r, make_float4((float)o[0], (float)o[1], (float)o[2], 0.0f));
+                    if (AUX && oidx != nullptr) oidx[r] = p;
+                }
+                orow += __popc(ball);
+                col += 32; p += 32;
+            }
+        } else {
+#pragma unroll 1
+            for (int s = 0; s < 4; ++s) {
+                const float d = s == 0 ? ring[0] : s == 1 ? ring[1] : s == 2 ? ring[2] : ring[3];
+                while (col >= W) { col -= W; ++row; }
+                const bool v = (__shfl_sync(0xffffffffu, mine, 8 * s + src) >> (lane & 3)) & 1u;
+                const unsigned ball = __ballot_sync(0xffffffffu, v);
+                if (AUX && oval != nullptr && p < npx) oval[p] = v;
+                if (v) {
+                    const int r = orow + __popc(ball & lt);
+                    double o[4];
+                    cloud_point<false>(cc, col, row, d, o);
+                    if (!(fabsf(d) < 1.0e30f)) cloud_point<true>(cc, col, row, d, o);      // see cloud_write_kernel
+                    if (F64) {
+                        double2* q = reinterpret_cast<double2*>(o64) + (size_t)r * 2;
+                        __stcs(q, make_double2(o[0], o[1]));
+                        __stcs(q + 1, make_double2(o[2], o[3]));
+                    }
+                    if (F32) __stcs(o32 + r, make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]));
+                    if (AUX && oidx != nullptr) oidx[r] = p;
+                }
+                orow += __popc(ball);
+                col += 32; p += 32;
+            }
+        }
+        dp += 128;
+        mine >>= 4;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) ring[s] = nxt[s];
+    }
+}
+
 static inline int cloud_blocks(const plb_cloud_args* a) { return (a->H * a->W + CL_TILE - 1) / CL_TILE; }
 
 size_t cloud_workspace_bytes(const plb_cloud_args* a) {
@@ -348,7 +492,19 @@ int cloud_launch(const plb_cloud_args* a, cudaStream_t st) {
     cloud_count_kernel<<<dim3((tiles + CC_WARPS - 1) / CC_WARPS, a->B), CC_WARPS * 32, 0, st>>>(*a, h, tiles);
     ++g_launches;
     PLB_CHECK_LAUNCH();
-    cloud_write_kernel<<<grid, CL_THREADS, 0, st>>>(*a, h);
+    if (a->sparsity <= 1 && a->W >= 32) {
+        const dim3 dgrid((tiles * CD_WPT + CD_WARPS - 1) / CD_WARPS, a->B);
+        const bool f64 = a->cloud_f64 != nullptr, f32 = a->cloud_f32 != nullptr, aux = a->index != nullptr || a->valid != nullptr;
+#define PLB_CLOUD_DIRECT(A, B_, C) cloud_write_direct_kernel<A, B_, C><<<dgrid, CD_WARPS * 32, 0, st>>>(*a, h, tiles)
+        if (f64 && !f32 && !aux) PLB_CLOUD_DIRECT(true, false, false);
+        else if (!f64 && f32 && !aux) PLB_CLOUD_DIRECT(false, true, false);
+        else if (f64 && !f32) PLB_CLOUD_DIRECT(true, false, true);
+        else if (!f64 && f32) PLB_CLOUD_DIRECT(false, true, true);
+        else if (f64 && f32) PLB_CLOUD_DIRECT(true, true, true);
+        else PLB_CLOUD_DIRECT(false, false, true);
+#undef PLB_CLOUD_DIRECT
+    }
+    else cloud_write_kernel<<<grid, CL_THREADS, 0, st>>>(*a, h);
     ++g_launches;
     PLB_CHECK_LAUNCH();
     return PLB_OK;
