@@ -71,6 +71,36 @@ __device__ __forceinline__ void cloud_point3(const CloudConst& cc, int col, int 
     }
 }
 
+// streaming stores under a predicate (no branch in the instruction stream)
+__device__ __forceinline__ void st_cs_f64x4_if(bool p, void* q, double a, double b, double c, double d) {   // 32-byte aligned
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.cs.v4.f64 [%1], {%2, %3, %4, %5}; }"
+                 :: "r"((unsigned)p), "l"(q), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void st_cs_f32x4_if(bool p, void* q, float a, float b, float c, float d) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.cs.v4.f32 [%1], {%2, %3, %4, %5}; }"
+                 :: "r"((unsigned)p), "l"(q), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// (double)i for 0 <= i < 2^31 without the conversion unit: the bits (0x43300000, i) are 2^52 + i exactly, and the
+// subtraction is exact - one DADD on the fp64 pipe instead of an I2F.F64 on the (16x narrower) XU pipe
+__device__ __forceinline__ double int_as_double_exact(int i) {
+    return __dsub_rn(__hiloint2double(0x43300000, i), 4503599627370496.0);
+}
+// the same chain with the column / row already in fp64
+__device__ __forceinline__ void cloud_point3d(const CloudConst& cc, double dcol, double drow, double d, double (&o)[4]) {
+    const double nx = __dmul_rn(__dsub_rn(dcol, cc.c_u), d), ny = __dmul_rn(__dsub_rn(drow, cc.c_v), d);
+    const double x = __dadd_rn(div_const(nx, cc.f_u, cc.rf_u), cc.b_x);
+    const double y = __dadd_rn(div_const(ny, cc.f_v, cc.rf_v), cc.b_y);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double acc = __dmul_rn(x, cc.Ti[k * 4 + 0]);
+        acc = __fma_rn(y, cc.Ti[k * 4 + 1], acc);
+        acc = __fma_rn(d, cc.Ti[k * 4 + 2], acc);
+        acc = __fma_rn(1.0, cc.Ti[k * 4 + 3], acc);
+        o[k] = acc;
+    }
+}
+
 // Validity of one pixel (cloud_x >= 0 & cloud_z < 1), bit-identical to the reference's and identical in the
 // count and the write launch.  cloud_x and cloud_z are affine in the depth, cloud_k = d * A_k(col, row) + C_k, with
 // A_k affine in (col, row): the host folds the calibration into eight doubles (CloudHost) and a pixel costs two FMAs
@@ -334,11 +364,14 @@ cloud_write_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h) 
 __device__ __forceinline__ double pin_reg(double v) { return __longlong_as_double(__double_as_longlong(v) ^ (long long)blockIdx.z); }
 constexpr int CD_WPT = 1;                         // warps per 1024-pixel tile
 constexpr int CD_WARPS = 4;                       // warps per block
+#ifndef CD_MINB
+#define CD_MINB 5                                 // resident blocks per SM the register allocation aims for
+#endif
 constexpr int CD_GROUPS = 8 / CD_WPT;             // 128-pixel groups of launch 1 per warp (4 validity bits of every word each)
 
 // F64 / F32: which cloud layouts are written; AUX: the call also wants the index and / or the validity mask
 template <bool F64, bool F32, bool AUX>
-__global__ void __launch_bounds__(CD_WARPS * 32)
+__global__ void __launch_bounds__(CD_WARPS * 32, CD_MINB)
 cloud_write_direct_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h, int tiles) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * CD_WARPS + (threadIdx.x >> 5);
@@ -351,6 +384,9 @@ cloud_write_direct_kernel(const __grid_constant__ plb_cloud_args a, const CloudH
     float ring[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) ring[s] = p + 32 * s < npx ? __ldg(dp + 32 * s) : 0.0f;
+    // the rest of the warp's depths on their way into L2 (one 128-byte line per lane: the loads a group ahead of their
+    // use then pay an L2 hit, not a DRAM round trip under load)
+    if (chunk + 32 * lane < npx) prefetch_l2(a.depth + (size_t)b * npx + chunk + 32 * lane);
     const uint32_t* words = (const uint32_t*)((const char*)a.workspace + cloud_words_offset(a.B, tiles));
     const unsigned word = __ldg(words + ((size_t)b * tiles + blk) * 32 + lane);
     int base = 0;
@@ -400,26 +436,26 @@ cloud_write_direct_kernel(const __grid_constant__ plb_cloud_args a, const CloudH
         if (w_zero && !__any_sync(0xffffffffu, odd)) {
             // the common case, ONE basic block for the four steps: every lane runs the chain (the warp would anyway),
             // only the stores are predicated - the four independent chains interleave
+            unsigned own[4], ball[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) own[s] = __shfl_sync(0xffffffffu, mine, 8 * s + src);      // four shuffles in flight
+#pragma unroll
+            for (int s = 0; s < 4; ++s) ball[s] = __ballot_sync(0xffffffffu, (own[s] >> (lane & 3)) & 1u);
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const float d = ring[s];
                 if (col >= W) { col -= W; ++row; }            // W >= 32 (host dispatch): one wrap per step at most
-                const bool v = (__shfl_sync(0xffffffffu, mine, 8 * s + src) >> (lane & 3)) & 1u;
-                const unsigned ball = __ballot_sync(0xffffffffu, v);
+                const bool v = (ball[s] >> lane) & 1u;
                 if (AUX && oval != nullptr && p < npx) oval[p] = v;
-                const int r = orow + __popc(ball & lt);
+                const int r = orow + __popc(ball[s] & lt);
                 double o[4];
-                cloud_point3(cc, col, row, d, o);
-                if (v) {
-                    if (F64) {
-                        double2* q = reinterpret_cast<double2*>(o64) + (size_t)r * 2;
-                        __stcs(q, make_double2(o[0], o[1]));
-                        __stcs(q + 1, make_double2(o[2], 0.0));
-                    }
-                    if (F32) __stcs(o32 + r, make_float4((float)o[0], (float)o[1], (float)o[2], 0.0f));
-                    if (AUX && oidx != nullptr) oidx[r] = p;
-                }
-                orow += __popc(ball);
+                cloud_point3d(cc, int_as_double_exact(col), int_as_double_exact(row), (double)d, o);
+                // PREDICATED stores, not a branch: behind `if (v)` the compiler sinks the whole chain into the divergent
+                // block and the four steps run one after the other, each at the full latency of its dependent chain
+                if (F64) st_cs_f64x4_if(v, o64 + (size_t)r * 4, o[0], o[1], o[2], 0.0);     // one 256-bit store: a whole sector
+                if (F32) st_cs_f32x4_if(v, o32 + r, (float)o[0], (float)o[1], (float)o[2], 0.0f);
+                if (AUX && oidx != nullptr && v) oidx[r] = p;
+                orow = __shfl_sync(0xffffffffu, r + (v ? 1 : 0), 31);      // rows after this step (no second popc: XU pipe)
                 col += 32; p += 32;
             }
         } else {
