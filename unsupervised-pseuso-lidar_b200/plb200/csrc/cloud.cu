@@ -151,6 +151,26 @@ __device__ __forceinline__ void cloud_load(const float* depth, size_t img_off, i
     }
 }
 
+// the same with the image's alignment class decided once per warp (`al` = 4 / 2 / 1 floats: p0 is a multiple of 4, so
+// the class depends on the image offset only) and a limit that also ends the tile
+__device__ __forceinline__ void cloud_load_al(const float* depth, int al, int p0, int lim, float (&dv)[CL_ITEMS]) {
+    if (p0 + CL_ITEMS <= lim) {
+        if (al == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(depth + p0));
+            dv[0] = q.x; dv[1] = q.y; dv[2] = q.z; dv[3] = q.w;
+        } else if (al == 2) {
+            const float2 q0 = __ldg(reinterpret_cast<const float2*>(depth + p0)), q1 = __ldg(reinterpret_cast<const float2*>(depth + p0 + 2));
+            dv[0] = q0.x; dv[1] = q0.y; dv[2] = q1.x; dv[3] = q1.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CL_ITEMS; ++k) dv[k] = __ldg(depth + p0 + k);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CL_ITEMS; ++k) dv[k] = (p0 + k < lim) ? __ldg(depth + p0 + k) : 0.0f;
+    }
+}
+
 // validity bits of this thread's CL_ITEMS consecutive pixels
 __device__ __forceinline__ unsigned cloud_mask(const CloudConst& cc, const CloudHost& h, int W, int p0, int npx,
                                                int row, int col, const float (&dv)[CL_ITEMS]) {
@@ -216,27 +236,27 @@ cloud_count_kernel(const __grid_constant__ plb_cloud_args a, const CloudHost h, 
     const float* depth = a.depth + (size_t)b * npx;
     const int pbase = blk * CL_TILE + lane * CL_ITEMS;
     // ONE copy of the mask code, iterated (an unrolled tile is ~1000 instructions = 16 KB that every warp walks once:
-    // the 6 KB L0 instruction cache never hits); three 128-bit loads per lane stay in flight ahead of the evaluation
-    constexpr int NIT = CL_TILE / 128, AHEAD = 3;
-    float ring[AHEAD][CL_ITEMS];
-#pragma unroll
-    for (int it = 0; it < AHEAD; ++it) cloud_load(depth, (size_t)b * npx, pbase + it * 128, npx, ring[it]);
+    // the 6 KB L0 instruction cache never hits).  The warp's 4 KB of depths are sent for in one instruction (one
+    // 128-byte line per lane into L2); the loop's own 128-bit loads then pay an L2 hit that the other warps cover.
+    constexpr int NIT = CL_TILE / 128;
+    if (blk * CL_TILE + 32 * lane < npx) prefetch_l2(depth + blk * CL_TILE + 32 * lane);
     int row = pbase / W, col = pbase - row * W;
     unsigned word = 0;
+    float cur[CL_ITEMS];
+    const size_t img_off = (size_t)b * npx;
+    const int al = (((uintptr_t)a.depth & 15) == 0 && (img_off & 3) == 0) ? 4 : (((uintptr_t)a.depth & 7) == 0 && (img_off & 1) == 0) ? 2 : 1;
+    const int lim = min(npx, (blk + 1) * CL_TILE);            // the tile's end: zeros beyond it
+    cloud_load_al(depth, al, pbase, lim, cur);
+    int p0 = pbase;
 #pragma unroll 1
-    for (int it = 0; it < NIT; ++it) {
+    for (int it = 0; it < NIT; ++it, p0 += 128) {
         float nxt[CL_ITEMS];
-        cloud_load(depth, (size_t)b * npx, pbase + (it + AHEAD) * 128, npx, nxt);      // zeros beyond the image
-        const int p0 = pbase + it * 128;
-        if (p0 < npx) word |= cloud_mask(cc, h, W, p0, npx, row, col, ring[0]) << (4 * it);
+        cloud_load_al(depth, al, p0 + 128, lim, nxt);
+        if (p0 < npx) word |= cloud_mask(cc, h, W, p0, npx, row, col, cur) << (4 * it);
         col += 128;
         while (col >= W) { col -= W; ++row; }
 #pragma unroll
-        for (int k = 0; k < CL_ITEMS; ++k) {
-#pragma unroll
-            for (int r = 0; r + 1 < AHEAD; ++r) ring[r][k] = ring[r + 1][k];
-            ring[AHEAD - 1][k] = nxt[k];
-        }
+        for (int k = 0; k < CL_ITEMS; ++k) cur[k] = nxt[k];
     }
     int mine = __popc(word);
 #pragma unroll
