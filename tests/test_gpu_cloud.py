@@ -42,7 +42,10 @@ def test_full_frame_golden_checksum(calib):
     assert PseudoLiDAR(calib, 10).project_PL(full.cuda()).shape[0] == int(g["full_count_sp10"])
 
 
-@pytest.mark.parametrize("B,H,W,sp", [(3, 37, 124, 0), (2, 1, 5, 0), (4, 375, 1242, 0), (2, 100, 333, 7)])
+# (3, 33, 35): an odd pixel count - the images start on 16-, 4- and 8-byte boundaries (every alignment class of the
+# count launch) and the last tile is ragged; (2, 1, 5): narrower than a warp step -> the compacting write launch
+@pytest.mark.parametrize("B,H,W,sp", [(3, 37, 124, 0), (2, 1, 5, 0), (4, 375, 1242, 0), (2, 100, 333, 7), (3, 33, 35, 0),
+                                      (2, 64, 1030, 0)])
 def test_batch_against_oracle(calib, B, H, W, sp):
     from utils.PseudoLiDAR import PseudoLiDAR
     from plb200 import synth
@@ -50,6 +53,9 @@ def test_batch_against_oracle(calib, B, H, W, sp):
     pl = PseudoLiDAR(calib, sp)
     depth = synth.make_depth_images(B, H, W, seed=5, lo=-5.0, hi=70.0)   # negatives: x<0 is masked out
     depth[0, 0, 0] = float("nan")
+    if W > 40:
+        depth[0, H // 2, 33] = float("inf")      # the write launch's exact-division path for one 128-pixel group
+        depth[B - 1, H - 1, W - 1] = 3.0e38
     res = pl.project_batch(depth, want_f64=True, want_f32=True, want_index=True, want_valid=True)
     counts = res["count"].cpu().numpy()
     for b in range(B):
