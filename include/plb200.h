@@ -325,14 +325,16 @@ typedef struct plb_prep_args {
     int32_t B;                 /* frames                                                            */
     int32_t in_h, in_w;        /* size of the decoded frames                                        */
     int32_t H, W;              /* network resolution (config: image_height, image_width)            */
-    int32_t reserved;
+    int32_t n_K;               /* intrinsics matrices in K_in / K_out: 0 = one per frame (B); a training sample has ONE
+                                  matrix for its 1 + n_src frames, so a batch of 3 B frames comes with n_K = B.
+                                  n_K > B: PLB_EINVAL                                               */
     const uint8_t* frames;     /* [B, in_h, in_w, 3] uint8 RGB, HWC as PIL decodes them             */
     float mean[3];             /* 0.485, 0.456, 0.406 in the reference                              */
     float stdev[3];            /* 0.229, 0.224, 0.225                                               */
     float* out_planar;         /* out [B,3,H,W] fp32 (the layout the networks and the loss read) or NULL */
     float* out_nhwc4;          /* out [B,H,W,4] fp32 (r,g,b,0) or NULL (at least one of the two)     */
-    const double* K_in;        /* [B,3,3] f64 intrinsics at the decoded size, or NULL               */
-    double* K_out;             /* out [B,3,3] f64: row 0 * W / in_w, row 1 * H / in_h (NULL iff K_in is NULL) */
+    const double* K_in;        /* [n_K,3,3] f64 intrinsics at the decoded size, or NULL             */
+    double* K_out;             /* out [n_K,3,3] f64: row 0 * W / in_w, row 1 * H / in_h (NULL iff K_in is NULL) */
     void* workspace;           /* plb_prep_workspace_bytes() bytes (no initialisation needed)       */
     size_t workspace_bytes;
 } plb_prep_args;

@@ -65,6 +65,10 @@ def test_argument_validation_without_gpu(L):
     assert L.lib.plb_velo_project(v, None) == -2         # no output
     w = L.WarpArgs()
     assert L.lib.plb_warp_forward(w, None) == -1
+    pr = L.PrepArgs()
+    pr.B, pr.in_h, pr.in_w, pr.H, pr.W, pr.n_K = 2, 8, 8, 4, 4, 3      # more intrinsics matrices than frames
+    pr.frames = pr.out_planar = pr.K_in = pr.K_out = pr.workspace = 1   # non-NULL: validation only, nothing is launched
+    assert L.lib.plb_prep_frames(pr, None) == -1
     with pytest.raises(L.PlbError):
         L.check(-3, "x")
 

@@ -64,3 +64,26 @@ def test_round_trip_table_and_errors():
         ops.prep_frames(torch.zeros(1, 4, 4, 3, device="cuda"), 4, 4)
     with pytest.raises(_lib.PlbError):
         ops.prep_frames(torch.zeros(1, 400, 400, 3, dtype=torch.uint8, device="cuda"), 4, 4)      # reduction > 15x
+
+
+def test_intrinsics_per_sample_not_per_frame():
+    """A batch of 3 B frames (target + two sources per sample) with ONE matrix per sample: only those B matrices are
+    read and written (plb_prep_args.n_K) - the words behind K_out stay untouched - and more matrices than frames is
+    an error, not an out-of-bounds read."""
+    from plb200 import ops
+    dev = torch.device("cuda:0")
+    B = 4
+    g = torch.Generator().manual_seed(2)
+    frames = torch.randint(0, 256, (3 * B, 40, 64, 3), dtype=torch.uint8, generator=g).to(dev)
+    K = torch.rand(B, 3, 3, dtype=torch.float64, generator=g).to(dev)
+    res = ops.prep_frames(frames, 20, 32, K=K)
+    per_frame = ops.prep_frames(frames, 20, 32, K=K.repeat(3, 1, 1))
+    torch.cuda.synchronize()
+    assert res["K"].shape == (B, 3, 3)
+    assert torch.equal(res["K"], per_frame["K"][:B]) and torch.equal(res["planar"], per_frame["planar"])
+    exp = K.clone()
+    exp[:, 0] *= 32 / 64
+    exp[:, 1] *= 20 / 40
+    assert torch.equal(res["K"], exp)
+    with pytest.raises(ValueError):
+        ops.prep_frames(frames[:2], 20, 32, K=K)

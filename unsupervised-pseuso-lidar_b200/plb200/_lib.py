@@ -186,7 +186,7 @@ class VeloArgs(C.Structure):
 class PrepArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_K", C.c_int32),
         ("frames", _fp),
         ("mean", C.c_float * 3), ("stdev", C.c_float * 3),
         ("out_planar", _fp), ("out_nhwc4", _fp),

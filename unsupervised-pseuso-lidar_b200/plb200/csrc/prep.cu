@@ -164,7 +164,7 @@ prep_resize_kernel(const __grid_constant__ PrepLaunch p) {
             reinterpret_cast<float4*>(a.out_nhwc4)[((size_t)b * a.H + Y) * a.W + X] = make_float4(o[0], o[1], o[2], 0.0f);
     }
     // intrinsics (dataloaders.py:95-98): K[0] *= W / og_w, K[1] *= H / og_h, fp64 like numpy
-    if (a.K_in != nullptr && a.K_out != nullptr && tile == 0 && tid < 9) {
+    if (a.K_in != nullptr && a.K_out != nullptr && tile == 0 && tid < 9 && b < (a.n_K > 0 ? a.n_K : a.B)) {
         const double sx = __ddiv_rn((double)a.W, (double)a.in_w), sy = __ddiv_rn((double)a.H, (double)a.in_h);
         const double v = a.K_in[(size_t)b * 9 + tid];
         a.K_out[(size_t)b * 9 + tid] = tid < 3 ? __dmul_rn(v, sx) : (tid < 6 ? __dmul_rn(v, sy) : v);
@@ -177,6 +177,7 @@ static int validate_prep(const plb_prep_args* a) {
     if (a->frames == nullptr || (a->out_planar == nullptr && a->out_nhwc4 == nullptr)) return PLB_ENULL;
     if (prep_ksize(a->in_w, a->W) > PR_KMAX || prep_ksize(a->in_h, a->H) > PR_KMAX) return PLB_EINVAL;
     if ((a->K_in == nullptr) != (a->K_out == nullptr)) return PLB_ENULL;
+    if (a->n_K < 0 || a->n_K > a->B) return PLB_EINVAL;
     if (a->B > 65535) return PLB_EINVAL;
     if (a->workspace == nullptr) return PLB_EWORKSPACE;
     return PLB_OK;

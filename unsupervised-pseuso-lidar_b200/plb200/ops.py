@@ -676,7 +676,8 @@ IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
 def prep_frames(frames, height, width, K=None, mean=IMAGENET_MEAN, std=IMAGENET_STD, want_planar=True, want_nhwc4=False,
                 out=None):
-    """frames [B,h,w,3] uint8 CUDA (decoded RGB, HWC) -> dict(planar [B,3,H,W] f32, nhwc4 [B,H,W,4] f32, K [B,3,3] f64):
+    """frames [B,h,w,3] uint8 CUDA (decoded RGB, HWC), K [n,3,3] (n <= B: one matrix per frame or per training sample)
+    -> dict(planar [B,3,H,W] f32, nhwc4 [B,H,W,4] f32, K [n,3,3] f64):
     the reference loader's transform chain and intrinsics scaling (trainer.py:97-103, dataloaders.py:32-49,95-98),
     bit-exact.  `out`: an optional preallocated [B,3,H,W] float32 tensor for the planar result.  No sync."""
     _need_cuda(frames, K)
@@ -703,9 +704,12 @@ def prep_frames(frames, height, width, K=None, mean=IMAGENET_MEAN, std=IMAGENET_
         res["nhwc4"] = torch.empty(B, a.H, a.W, 4, dtype=torch.float32, device=dev)
         a.out_nhwc4 = res["nhwc4"].data_ptr()
     if K is not None:
+        # one matrix per frame, or one per training sample (its 1 + n_src frames share it): [n,3,3] with n <= B
+        if K.dim() != 3 or tuple(K.shape[1:]) != (3, 3) or K.shape[0] < 1 or K.shape[0] > B:
+            raise ValueError("K must be [n,3,3] with 1 <= n <= %d frames, got %s" % (B, tuple(K.shape)))
         K = K.to(torch.float64).contiguous()
         res["K"] = torch.empty_like(K)
-        a.K_in, a.K_out = K.data_ptr(), res["K"].data_ptr()
+        a.K_in, a.K_out, a.n_K = K.data_ptr(), res["K"].data_ptr(), K.shape[0]
     ws = _workspace("prep", lib.plb_prep_workspace_bytes(a), dev)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     check(lib.plb_prep_frames(a, _stream()), "plb_prep_frames")
