@@ -106,3 +106,22 @@ def test_torch_binding_loads_and_refuses_cpu_tensors(L):
     for binding in ("torch", "ctypes"):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             ops.fused_losses(inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"], binding=binding)
+
+
+def test_ops_reject_mismatched_shapes(L):
+    """The kernels see pointers, not extents: shapes the reference's torch ops would reject are rejected on the host
+    (checked before the device check, so this runs without a GPU)."""
+    import torch
+    from plb200 import ops, synth
+    inp = synth.make_photo_inputs(2, 8, 16, n_src=2, n_scales=2)
+    t, r, d, p, K = inp["tgt"], inp["ref_imgs"], inp["disparity"], inp["poses"], inp["intrinsics"]
+    bad = [
+        (t, r, d, p, K[:1]),                                   # one intrinsics matrix for two samples
+        (t, r, d, p[:, :1], K),                                # fewer poses than sources
+        (t, [r[0], r[1][:1]], d, p, K),                        # a reference image of another batch
+        (t, r, [[x[:1] for x in d[0]]] + list(d[1:]), p, K),   # a disparity pyramid of another batch
+        (t[:, :1], r, d, p, K),                                # not an RGB image
+    ]
+    for args in bad:
+        with pytest.raises(ValueError):
+            ops.fused_losses(*args)

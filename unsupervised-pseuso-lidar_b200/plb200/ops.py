@@ -347,12 +347,39 @@ class FusedLossFn(torch.autograd.Function):
         return tuple(grads)
 
 
+def _check_loss_shapes(tgt, refs, pyramids, poses, K):
+    """The kernels see pointers, not extents: every shape the reference's torch ops would have rejected (or broadcast)
+    is rejected here, before a launch can read or write past a buffer."""
+    if tgt.dim() != 4 or tgt.shape[1] != 3:
+        raise ValueError("tgt must be [B,3,H,W], got %s" % (tuple(tgt.shape),))
+    B, _, H, W = tgt.shape
+    if not 1 <= len(refs) <= _lib.MAX_SRC:
+        raise ValueError("1..%d reference images, got %d" % (_lib.MAX_SRC, len(refs)))
+    for r in refs:
+        if tuple(r.shape) != tuple(tgt.shape):
+            raise ValueError("every reference image must have the target's shape %s, got %s" % (tuple(tgt.shape), tuple(r.shape)))
+    if not 1 <= len(pyramids) <= 1 + len(refs):
+        raise ValueError("1..%d disparity pyramids (target frame first), got %d" % (1 + len(refs), len(pyramids)))
+    for p in pyramids:
+        if not 1 <= len(p) <= _lib.MAX_SCALES:
+            raise ValueError("1..%d scales per pyramid, got %d" % (_lib.MAX_SCALES, len(p)))
+        for d in p:
+            if d.dim() < 3 or d.shape[0] != B or d.numel() != B * d.shape[-2] * d.shape[-1] or d.numel() == 0:
+                raise ValueError("a disparity map must be [%d,1,h,w], got %s" % (B, tuple(d.shape)))
+    n_pose = max(len(refs), len(pyramids) - 1)
+    if poses.dim() != 3 or poses.shape[0] != B or poses.shape[1] < n_pose or poses.shape[2] != 6:
+        raise ValueError("poses must be [%d,>=%d,6], got %s" % (B, n_pose, tuple(poses.shape)))
+    if tuple(K.shape) != (B, 3, 3):
+        raise ValueError("intrinsics must be [%d,3,3], got %s" % (B, tuple(K.shape)))
+
+
 def fused_losses(tgt, refs, pyramids, poses, K, binding=None, **cfg_kw):
     """pyramids: list[frame] of list[scale] of [B,1,h,w].  Returns (loss_mam, loss_smooth).
     binding: "torch" = the C++ torch binding (csrc/torch_binding.cpp: autograd node and argument structs in C++),
     "ctypes" = FusedLossFn above; None = the C++ one when it is built.  Same C ABI, same kernels, same results."""
     cfg = LossConfig(len(refs), [len(p) for p in pyramids], **cfg_kw)
     flat = [d for p in pyramids for d in p]
+    _check_loss_shapes(tgt, refs, pyramids, poses, K)
     from . import _tb
     if binding == "torch" and _tb.mod is None:
         raise RuntimeError("the torch C++ binding is not built (plb200/build.py --torch)")
@@ -374,7 +401,13 @@ class InverseWarpFn(torch.autograd.Function):
     def forward(ctx, img, depth, pose, K, pose_inv, rotation_mode):
         _need_cuda(img, depth, pose, K)
         img, depth, pose, K = _f32c(img), _f32c(depth), _f32c(pose), _kc(K)
+        if img.dim() != 4 or img.shape[1] != 3:
+            raise ValueError("img must be [B,3,H,W], got %s" % (tuple(img.shape),))
         B, _, H, W = img.shape
+        if depth.numel() != B * H * W or depth.shape[0] != B or tuple(depth.shape[-2:]) != (H, W):
+            raise ValueError("depth must be [%d,%d,%d], got %s" % (B, H, W, tuple(depth.shape)))
+        if pose.numel() != B * 6 or tuple(K.shape) != (B, 3, 3):
+            raise ValueError("pose must be [%d,6] and intrinsics [%d,3,3], got %s / %s" % (B, B, tuple(pose.shape), tuple(K.shape)))
         out = torch.empty_like(img)
         a = _lib.WarpArgs()
         a.B, a.H, a.W = B, H, W
@@ -564,6 +597,11 @@ class EdgeSmoothFn(torch.autograd.Function):
             raise ValueError("1..%d scales" % _lib.MAX_SCALES)
         tgt = _f32c(tgt)
         disps = [_f32c(d) for d in disps]
+        if tgt.dim() != 4 or tgt.shape[1] != 3:
+            raise ValueError("tgt must be [B,3,H,W], got %s" % (tuple(tgt.shape),))
+        for d in disps:
+            if d.dim() < 3 or d.shape[0] != tgt.shape[0] or d.numel() != tgt.shape[0] * d.shape[-2] * d.shape[-1]:
+                raise ValueError("a disparity map must be [%d,1,h,w], got %s" % (tgt.shape[0], tuple(d.shape)))
         loss = torch.empty((), dtype=torch.float32, device=tgt.device)
         # single pass: when a disparity needs a gradient the forward launch writes d loss / d disp for a unit upstream
         # (the loss is a scalar, its gradient is linear in the upstream value); backward only scales it
