@@ -652,6 +652,35 @@ def time_photo_kernel(criterion, gpu_sets, cfg, dev, iters):
     return e0.elapsed_time(e1) / (reps * per_graph)
 
 
+def _graph_replay_ms(calls, iters, dev):
+    """Each call captured in its own CUDA graph (after one eager run that built its workspaces); the graphs replayed
+    round robin, CUDA events around `iters` replays.  Returns ms per replay."""
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    graphs, keep = [], []
+    with torch.cuda.stream(side):
+        for c in calls:
+            c()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    for c in calls:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            keep.append(c())
+        graphs.append(g)
+    for g in graphs:
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        graphs[i % len(graphs)].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    del graphs, keep
+    return e0.elapsed_time(e1) / iters
+
+
 def time_cloud(dev, B=32, H=375, W=1242, iters=20):
     """Config C4 (BASELINE.json configs[3]): depth -> pseudo-LiDAR back-projection.  The headline numbers are the fp64
     x,y,z,0 parity layout; `f32` is the PointCloud2 wire layout the reference publishes (PseudoLidarPipeline.py:51-54,
@@ -672,16 +701,20 @@ def time_cloud(dev, B=32, H=375, W=1242, iters=20):
         torch.cuda.synchronize()
         kept = int(outs[0]["count"].sum())
         del outs
+        # the calls issued eagerly through the public API ...
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
         for i in range(iters):
             pl.project_batch(sets[i % len(sets)], **want)
         e1.record(st)
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
+        eager_ms = e0.elapsed_time(e1) / iters
+        # ... and the two launches replayed from one CUDA graph per input set (like `value`: the host cost of issuing a
+        # call - argument marshalling, the 477 MB output allocation - cannot hide in or add to the measurement)
+        ms = _graph_replay_ms([lambda s=s: pl.project_batch(s, **want) for s in sets], iters, dev)
         abytes = 4.0 * px + bpp * kept
         res[layout] = {"ms": ms, "mpix_s": px / 1e6 / (ms / 1e3), "kept_points": kept, "algorithmic_bytes": abytes,
-                       "achieved_gbs": abytes / (ms / 1e3) / 1e9}
+                       "achieved_gbs": abytes / (ms / 1e3) / 1e9, "eager_ms": eager_ms}
     # end to end with host buffers (fp64 parity layout): H2D of the depth batch, the two launches, D2H of the counts
     # (the output size is data dependent: one sync) and of the kept rows of every image
     host_in = [s.cpu().pin_memory() for s in sets]
@@ -705,7 +738,8 @@ def time_cloud(dev, B=32, H=375, W=1242, iters=20):
     for i in range(n_e2e):
         rows = e2e_once(i)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-    out = {"workload": "c4: %dx%d depth -> pseudo-LiDAR, batch %d, f64 x,y,z,0 parity layout" % (H, W, B)}
+    out = {"workload": "c4: %dx%d depth -> pseudo-LiDAR, batch %d, f64 x,y,z,0 parity layout" % (H, W, B),
+           "timing": "CUDA-graph replay of project_batch per input set (3 sets, > L2); eager_ms = the same calls issued eagerly"}
     out.update(res["f64"])
     out["f32_pointcloud2"] = res["f32"]
     out["e2e"] = {"ms": e2e_ms, "mpix_s": px / 1e6 / (e2e_ms / 1e3), "h2d_bytes": 4 * px, "d2h_bytes": 32 * rows + 4 * B,
@@ -733,10 +767,12 @@ def time_velo(dev, B=32, N=123577, H=375, W=1242, iters=20):
         tr.project_batch(sets[i % len(sets)])
     e1.record(st)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    eager_ms = e0.elapsed_time(e1) / iters
+    ms = _graph_replay_ms([lambda s=s: tr.project_batch(s) for s in sets], iters, dev)     # as time_cloud
     abytes = 16.0 * B * N + 8.0 * B * H * W
     return {"workload": "velodyne -> image: %d sweeps x %d points -> %dx%d f64 depth" % (B, N, H, W), "ms": ms,
-            "mpoints_s": B * N / 1e6 / (ms / 1e3), "algorithmic_bytes": abytes, "achieved_gbs": abytes / (ms / 1e3) / 1e9}
+            "mpoints_s": B * N / 1e6 / (ms / 1e3), "algorithmic_bytes": abytes, "achieved_gbs": abytes / (ms / 1e3) / 1e9,
+            "eager_ms": eager_ms, "timing": "CUDA-graph replay of project_batch per input set; eager_ms = the same calls issued eagerly"}
 
 
 def time_e2e(criterion, cpu_sets, cfg, dev, iters, barrier, frame_hw=None):
