@@ -75,3 +75,39 @@ def test_empty_cloud(calib):
     depth = -torch.ones(8, 16)
     cloud = PseudoLiDAR(calib, 0).project_PL(depth)
     assert cloud.shape == (0, 4)
+
+
+@pytest.mark.parametrize("sp", [0, 1, 4])
+def test_general_homogeneous_row(calib, sp):
+    """`plb_cloud_project` takes any 4x4: with a non-zero last row of T_inv the 4th output column is computed by the
+    same chain as x, y, z (the reference's own matrix has an all-zero row, PseudoLiDAR.py:43).  sparsity 0 / 1: the
+    direct write launch; 4: the compacting one."""
+    from utils.PseudoLiDAR import PseudoLiDAR
+    from plb200 import ops, synth
+    from oracle import restated as O
+    pl = PseudoLiDAR(calib, sp)
+    Tinv = np.array(pl.inverse_rigid_trans(pl.T), dtype=np.float64)
+    Tinv[3] = [0.25, -0.5, 0.125, 2.0]
+    depth = synth.make_depth_images(2, 48, 200, seed=9, lo=-2.0, hi=60.0)
+    res = ops.cloud_project(depth.cuda(), pl.P, Tinv, sparsity=sp)
+    counts = res["count"].cpu().numpy()
+    P = pl.P
+    for b in range(2):
+        rows, cols = depth[b].shape
+        c, r = np.meshgrid(np.arange(cols), np.arange(rows))
+        d = depth[b].numpy().astype(np.float64).reshape(-1)
+        pts = np.ones((d.size, 4))
+        pts[:, 0] = ((c.reshape(-1) - P[0, 2]) * d) / P[0, 0] + P[0, 3] / (-P[0, 0])
+        pts[:, 1] = ((r.reshape(-1) - P[1, 2]) * d) / P[1, 1] + P[1, 3] / (-P[1, 1])
+        pts[:, 2] = d
+        cloud = np.matmul(pts, Tinv.T)
+        ref = cloud[(cloud[:, 0] >= 0) & (cloud[:, 2] < 1)]
+        if sp:
+            ref = ref[0::sp]
+        n = int(counts[b])
+        assert n == ref.shape[0]
+        got = res["cloud_f64"][b, :n].cpu().numpy()
+        assert np.array_equal(got[:, :3], ref[:, :3])
+        err = np.abs(got[:, 3] - ref[:, 3]).max() if n else 0.0
+        print("4th column max abs err %.3e" % err)
+        assert err <= 1e-12 * max(1.0, np.abs(ref[:, 3]).max())
