@@ -26,6 +26,8 @@ struct EdgeLayout {
     size_t pooled[PLB_MAX_SCALES];   // float [B,3,h,w] (scales with f > 1)
     size_t part_mean;                // double [blocks]
     size_t part_loss;                // double [blocks][2]   (loss partial, sum g' d partial)
+    size_t img_inv;                  // float [PLB_MAX_SCALES][B]: 1 / (mean_hw(d) + 1e-7) of every image (normalize)
+    size_t img_c;                    // float [PLB_MAX_SCALES][B]: sum(g' d) inv^2 / (h w) of every image (normalize, want_grad)
     size_t total;
     int first_block[PLB_MAX_SCALES + 1];   // blocks of launch 1 / 2 / 3: EG_TILE pixels of one image of one scale
     int blocks_per_image[PLB_MAX_SCALES];
@@ -70,6 +72,8 @@ __host__ inline EdgeLayout edge_layout(const plb_edge_args& a) {
     L.first_block[PLB_MAX_SCALES] = nb;
     L.part_mean = off; off += ((size_t)nb * sizeof(double) + 255) / 256 * 256;
     L.part_loss = off; off += ((size_t)nb * 2 * sizeof(double) + 255) / 256 * 256;
+    L.img_inv = off; off += ((size_t)PLB_MAX_SCALES * a.B * sizeof(float) + 255) / 256 * 256;
+    L.img_c = off; off += ((size_t)PLB_MAX_SCALES * a.B * sizeof(float) + 255) / 256 * 256;
     L.total = off;
     return L;
 }
@@ -248,17 +252,44 @@ __device__ __forceinline__ double image_partial_sum(const double* parts, const E
 
 __device__ __forceinline__ float sgn1(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
 
+// Per-image scalars, ONE block per (scale, image) instead of every block of the image repeating the walk over its
+// partials (at batch 64 that was two block-wide sums + up to 240 dependent L2 loads in each of 10 240 blocks of the
+// main and the final launch): (a) after launch 1: inv = 1 / (mean + 1e-7); (b) after launch 2: the constant of the
+// normalisation's gradient, and (block 0) the loss.  Same partials, same fixed order: bitwise the same values.
+__global__ void __launch_bounds__(EG_THREADS)
+edge_mean_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    __shared__ double sh[EG_THREADS / 32];
+    const int s = blockIdx.x / a.B, b = blockIdx.x - s * a.B;
+    const int n = a.dh[s] * a.dw[s];
+    const double m = image_partial_sum((const double*)((const char*)a.workspace + L.part_mean), L, s, b, 1, 0, sh) / (double)n;
+    if (threadIdx.x == 0) ((float*)((char*)a.workspace + L.img_inv))[s * a.B + b] = 1.0f / ((float)m + 1e-7f);
+}
+
+__global__ void __launch_bounds__(EG_THREADS)
+edge_gsum_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    __shared__ double sh[EG_THREADS / 32];
+    const double* parts = (const double*)((const char*)a.workspace + L.part_loss);
+    if (blockIdx.x == 0) {
+        double v = 0.0;
+        for (int q = threadIdx.x; q < L.first_block[PLB_MAX_SCALES]; q += EG_THREADS) v += __ldcg(parts + (size_t)q * 2);
+        const double tot = block_sum(v, sh);
+        if (threadIdx.x == 0 && a.loss != nullptr) *a.loss = (float)tot;
+    }
+    if (!(a.normalize && a.want_grad)) return;
+    const int s = blockIdx.x / a.B, b = blockIdx.x - s * a.B;
+    const int n = a.dh[s] * a.dw[s];
+    const float s_inv = ((const float*)((const char*)a.workspace + L.img_inv))[s * a.B + b];
+    const double gd = image_partial_sum(parts, L, s, b, 2, 1, sh);
+    if (threadIdx.x == 0) ((float*)((char*)a.workspace + L.img_c))[s * a.B + b] = (float)(gd * (double)s_inv * (double)s_inv / (double)n);
+}
+
 // launch 2: loss partials and the unnormalised gradient
 __global__ void __launch_bounds__(EG_THREADS)
 edge_main_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
     __shared__ double sh[EG_THREADS / 32];
     const EdgeWork k = edge_work(a, L);
     const int n = k.h * k.w, w = k.w, h = k.h;
-    float inv = 1.0f;
-    if (a.normalize) {
-        const double m = image_partial_sum((const double*)((const char*)a.workspace + L.part_mean), L, k.s, k.b, 1, 0, sh) / (double)n;
-        inv = 1.0f / ((float)m + 1e-7f);
-    }
+    const float inv = a.normalize ? __ldg((const float*)((const char*)a.workspace + L.img_inv) + k.s * a.B + k.b) : 1.0f;
     const float* disp = a.disp[k.s] + (size_t)k.b * n;
     const float* img = (k.f > 1) ? (const float*)((const char*)a.workspace + L.pooled[k.s]) + (size_t)k.b * 3 * n
                                  : a.tgt + (size_t)k.b * 3 * n;
@@ -320,24 +351,14 @@ edge_main_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
     }
 }
 
-// launch 3: loss scalar (block 0) and, when normalising, g = g' inv - sum(g' d) inv^2 / (h w)
+// launch 3 (only when normalising with gradients): g = g' inv - sum(g' d) inv^2 / (h w)
 __global__ void __launch_bounds__(EG_THREADS)
 edge_final_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
-    __shared__ double sh[EG_THREADS / 32];
     const EdgeWork k = edge_work(a, L);
     const int n = k.h * k.w;
-    const double* parts = (const double*)((const char*)a.workspace + L.part_loss);
-    if (blockIdx.x == 0) {
-        double v = 0.0;
-        for (int q = threadIdx.x; q < L.first_block[PLB_MAX_SCALES]; q += EG_THREADS) v += __ldcg(parts + (size_t)q * 2);
-        const double tot = block_sum(v, sh);
-        if (threadIdx.x == 0 && a.loss != nullptr) *a.loss = (float)tot;
-    }
     if (!(a.normalize && a.want_grad && a.g_disp[k.s] != nullptr)) return;
-    const double m = image_partial_sum((const double*)((const char*)a.workspace + L.part_mean), L, k.s, k.b, 1, 0, sh) / (double)n;
-    const float s_inv = 1.0f / ((float)m + 1e-7f);
-    const double gd = image_partial_sum(parts, L, k.s, k.b, 2, 1, sh);
-    const float s_c = (float)(gd * (double)s_inv * (double)s_inv / (double)n);
+    const float s_inv = __ldg((const float*)((const char*)a.workspace + L.img_inv) + k.s * a.B + k.b);
+    const float s_c = __ldg((const float*)((const char*)a.workspace + L.img_c) + k.s * a.B + k.b);
 #pragma unroll
     for (int j = 0; j < EG_PX; ++j) {
         const int o = k.o0 + j * EG_THREADS;
@@ -382,12 +403,22 @@ int edge_launch(const plb_edge_args* a, cudaStream_t st) {
     edge_prep_kernel<<<nb, EG_THREADS, 0, st>>>(*a, L);
     ++g_launches;
     PLB_CHECK_LAUNCH();
+    if (a->normalize) {
+        edge_mean_kernel<<<a->n_scales * a->B, EG_THREADS, 0, st>>>(*a, L);
+        ++g_launches;
+        PLB_CHECK_LAUNCH();
+    }
     edge_main_kernel<<<nb, EG_THREADS, 0, st>>>(*a, L);
     ++g_launches;
     PLB_CHECK_LAUNCH();
-    edge_final_kernel<<<nb, EG_THREADS, 0, st>>>(*a, L);
+    edge_gsum_kernel<<<(a->normalize && a->want_grad) ? a->n_scales * a->B : 1, EG_THREADS, 0, st>>>(*a, L);
     ++g_launches;
     PLB_CHECK_LAUNCH();
+    if (a->normalize && a->want_grad) {
+        edge_final_kernel<<<nb, EG_THREADS, 0, st>>>(*a, L);
+        ++g_launches;
+        PLB_CHECK_LAUNCH();
+    }
     return PLB_OK;
 }
 
