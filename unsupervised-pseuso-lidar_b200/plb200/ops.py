@@ -617,7 +617,8 @@ class EdgeSmoothFn(torch.autograd.Function):
         g_disp, ctx.g_disp = ctx.g_disp, None
         g = g.detach().to(torch.float32)
         need = ctx.needs_input_grad[2:]
-        return (None, None) + tuple((gd * g if n else None) for gd, n in zip(g_disp, need))
+        scaled = torch._foreach_mul(list(g_disp), g)           # one multi-tensor launch for the whole pyramid
+        return (None, None) + tuple((gd if n else None) for gd, n in zip(scaled, need))
 
 
 def edge_aware_smooth(disps, tgt, normalize=True):
