@@ -20,6 +20,7 @@ namespace plb {
 constexpr int EG_THREADS = 256;
 constexpr int EG_PX = 4;                       // consecutive pixels per thread: the per-block work (which scale / image am
 constexpr int EG_TILE = EG_THREADS * EG_PX;    // I, image mean, block sums) is amortised over 1024 pixels
+constexpr int EV_OWN = 30 * 4;                 // edge_main_vec_kernel: columns a warp owns (lanes 1..30, four each)
 
 // Launch-time constants, computed once on the host.
 struct EdgeLayout {
@@ -28,6 +29,11 @@ struct EdgeLayout {
     size_t part_loss;                // double [blocks][2]   (loss partial, sum g' d partial)
     size_t img_inv;                  // float [PLB_MAX_SCALES][B]: 1 / (mean_hw(d) + 1e-7) of every image (normalize)
     size_t img_c;                    // float [PLB_MAX_SCALES][B]: sum(g' d) inv^2 / (h w) of every image (normalize, want_grad)
+    // edge_main_vec_kernel: one warp per (scale, image, row chunk, 120-column strip); its partials replace the block partials
+    int vec_main;                    // 1: every width is a multiple of 4 and every map 16-byte aligned
+    int v_rows;                      // rows per chunk
+    int v_first[PLB_MAX_SCALES + 1]; // first unit of every scale
+    int v_strips[PLB_MAX_SCALES], v_per_img[PLB_MAX_SCALES];
     size_t total;
     int first_block[PLB_MAX_SCALES + 1];   // blocks of launch 1 / 2 / 3: EG_TILE pixels of one image of one scale
     int blocks_per_image[PLB_MAX_SCALES];
@@ -70,8 +76,33 @@ __host__ inline EdgeLayout edge_layout(const plb_edge_args& a) {
             }
     }
     L.first_block[PLB_MAX_SCALES] = nb;
+    // vector main kernel: possible when rows are whole 128-bit packets
+    L.vec_main = 1;
+    for (int s = 0; s < a.n_scales && s < PLB_MAX_SCALES; ++s) {
+        if (a.dw[s] % 4 != 0 || a.dw[s] < 4) L.vec_main = 0;
+        if (((size_t)a.disp[s] | (size_t)a.g_disp[s] | (size_t)a.g_scratch[s]) & 15) L.vec_main = 0;
+    }
+    if (((size_t)a.tgt & 15) || (a.W & 3)) L.vec_main = 0;
+    int nv = 0;
+    L.v_rows = 16;
+    for (int rows = 16; rows >= 4; rows >>= 1) {      // chunks shrink with the batch: ~12 warps per SM or more
+        nv = 0;
+        L.v_rows = rows;
+        for (int s = 0; s < PLB_MAX_SCALES; ++s) {
+            L.v_first[s] = nv;
+            L.v_strips[s] = L.v_per_img[s] = 0;
+            if (s < a.n_scales && a.dh[s] > 0 && a.dw[s] > 0) {
+                L.v_strips[s] = (a.dw[s] + EV_OWN - 1) / EV_OWN;
+                L.v_per_img[s] = L.v_strips[s] * ((a.dh[s] + rows - 1) / rows);
+                nv += L.v_per_img[s] * a.B;
+            }
+        }
+        L.v_first[PLB_MAX_SCALES] = nv;
+        if (nv >= 148 * 12) break;
+    }
+    const int n_part = L.vec_main && nv > nb ? nv : nb;          // partial records: blocks (scalar) or warps (vector)
     L.part_mean = off; off += ((size_t)nb * sizeof(double) + 255) / 256 * 256;
-    L.part_loss = off; off += ((size_t)nb * 2 * sizeof(double) + 255) / 256 * 256;
+    L.part_loss = off; off += ((size_t)n_part * 2 * sizeof(double) + 255) / 256 * 256;
     L.img_inv = off; off += ((size_t)PLB_MAX_SCALES * a.B * sizeof(float) + 255) / 256 * 256;
     L.img_c = off; off += ((size_t)PLB_MAX_SCALES * a.B * sizeof(float) + 255) / 256 * 256;
     L.total = off;
@@ -208,6 +239,52 @@ edge_pool_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
     (void)src;
 }
 
+// The same pyramid without shared memory or barriers, for images whose width is a multiple of 32 and height of 16 and
+// factors up to 16 (the KITTI pyramids): a warp owns 32 x 16 pixels, every lane a 4 x 4 patch (four 128-bit loads per
+// channel) - levels 1 and 2 are sums inside the lane, levels 3 and 4 two butterfly shuffles each (lane bits: 0 -> x + 4,
+// 1 -> y + 4, 2 -> x + 8, 3 -> y + 8, 4 -> x + 16).  Same pairings as edge_pool_kernel - (a + b) + (c + d) of the
+// 2 x 2 children at every level - so the pooled images are bitwise the same.  (The tiled kernel spent 60 instructions
+// per input value and ten barriers per 12 KB tile: 74 us for the 94 MB of a 64-image batch.)
+__global__ void __launch_bounds__(EG_THREADS)
+edge_pool_fast_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.z;
+    const int X0 = blockIdx.x * 64 + (warp & 1) * 32, Y0 = blockIdx.y * 64 + (warp >> 1) * 16;
+    if (X0 >= a.W || Y0 >= a.H) return;
+    const int x = X0 + 4 * ((lane & 1) + ((lane >> 2) & 1) * 2 + ((lane >> 4) & 1) * 4);
+    const int y = Y0 + 4 * (((lane >> 1) & 1) + ((lane >> 3) & 1) * 2);
+    float* out[5];
+    int ow[5], oh[5];
+#pragma unroll
+    for (int l = 1; l <= 4; ++l) {
+        const int sidx = L.level_scale[l];
+        out[l] = sidx >= 0 ? (float*)((char*)a.workspace + L.pooled[sidx]) : nullptr;
+        ow[l] = sidx >= 0 ? a.dw[sidx] : 0;
+        oh[l] = sidx >= 0 ? a.dh[sidx] : 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* src = a.tgt + ((size_t)(b * 3 + c) * a.H + y) * a.W + x;
+        float4 r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)i * a.W));
+        const float s00 = (r[0].x + r[0].y) + (r[1].x + r[1].y), s01 = (r[0].z + r[0].w) + (r[1].z + r[1].w);
+        const float s10 = (r[2].x + r[2].y) + (r[3].x + r[3].y), s11 = (r[2].z + r[2].w) + (r[3].z + r[3].w);
+        const float q = (s00 + s01) + (s10 + s11);
+        float e = q + __shfl_xor_sync(0xffffffffu, q, 1);
+        e = e + __shfl_xor_sync(0xffffffffu, e, 2);
+        float h = e + __shfl_xor_sync(0xffffffffu, e, 4);
+        h = h + __shfl_xor_sync(0xffffffffu, h, 8);
+        if (out[1] != nullptr) {
+            float* d = out[1] + ((size_t)(b * 3 + c) * oh[1] + (y >> 1)) * ow[1] + (x >> 1);
+            *reinterpret_cast<float2*>(d) = make_float2(s00 * 0.25f, s01 * 0.25f);
+            *reinterpret_cast<float2*>(d + ow[1]) = make_float2(s10 * 0.25f, s11 * 0.25f);
+        }
+        if (out[2] != nullptr) out[2][((size_t)(b * 3 + c) * oh[2] + (y >> 2)) * ow[2] + (x >> 2)] = q * (1.0f / 16.0f);
+        if (out[3] != nullptr && (lane & 3) == 0) out[3][((size_t)(b * 3 + c) * oh[3] + (y >> 3)) * ow[3] + (x >> 3)] = e * (1.0f / 64.0f);
+        if (out[4] != nullptr && (lane & 15) == 0) out[4][((size_t)(b * 3 + c) * oh[4] + (y >> 4)) * ow[4] + (x >> 4)] = h * (1.0f / 256.0f);
+    }
+}
+
 // launch 1: pooled target images of the low scales + per-block disparity sums
 __global__ void __launch_bounds__(EG_THREADS)
 edge_prep_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
@@ -219,6 +296,17 @@ edge_prep_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
     const bool vec = (a.W & 3) == 0 && ((size_t)a.tgt & 15) == 0;
     float* pooled = (float*)((char*)a.workspace + L.pooled[k.s]);
     const float inv = 1.0f / (float)(k.f * k.f);
+    if ((k.f == 1 || L.tile_pooled[k.s]) && (n & 3) == 0 && ((size_t)a.disp[k.s] & 15) == 0) {
+        // nothing to pool here: the block only sums its 1024 disparities - one 128-bit load per thread
+        const int o = (k.o0 - (int)threadIdx.x) + 4 * (int)threadIdx.x;
+        if (o < n) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(disp + o));
+            dsum = (v.x + v.y) + (v.z + v.w);
+        }
+        const double tot = block_sum((double)dsum, sh);
+        if (threadIdx.x == 0) ((double*)((char*)a.workspace + L.part_mean))[blockIdx.x] = tot;
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < EG_PX; ++j) {
         const int o = k.o0 + j * EG_THREADS;
@@ -242,12 +330,14 @@ edge_prep_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
 // sum of the block partials of image b at scale s, by the whole block (thread t takes partials t, t + 256, ... in
 // order, then the fixed-order block sum): every thread gets the result.  (One thread walking the partials alone
 // cost 100+ us PER BLOCK - a dependent L2 load each.)
+__device__ __forceinline__ double range_partial_sum(const double* parts, int first, int count, int stride, int offset, double* sh) {
+    double m = 0.0;
+    for (int q = threadIdx.x; q < count; q += EG_THREADS) m += __ldcg(parts + (size_t)(first + q) * stride + offset);
+    return block_sum(m, sh);
+}
 __device__ __forceinline__ double image_partial_sum(const double* parts, const EdgeLayout& L, int s, int b, int stride,
                                                     int offset, double* sh) {
-    double m = 0.0;
-    const int first = L.first_block[s] + b * L.blocks_per_image[s];
-    for (int q = threadIdx.x; q < L.blocks_per_image[s]; q += EG_THREADS) m += __ldcg(parts + (size_t)(first + q) * stride + offset);
-    return block_sum(m, sh);
+    return range_partial_sum(parts, L.first_block[s] + b * L.blocks_per_image[s], L.blocks_per_image[s], stride, offset, sh);
 }
 
 __device__ __forceinline__ float sgn1(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
@@ -271,7 +361,8 @@ edge_gsum_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
     const double* parts = (const double*)((const char*)a.workspace + L.part_loss);
     if (blockIdx.x == 0) {
         double v = 0.0;
-        for (int q = threadIdx.x; q < L.first_block[PLB_MAX_SCALES]; q += EG_THREADS) v += __ldcg(parts + (size_t)q * 2);
+        const int n_part = L.vec_main ? L.v_first[PLB_MAX_SCALES] : L.first_block[PLB_MAX_SCALES];
+        for (int q = threadIdx.x; q < n_part; q += EG_THREADS) v += __ldcg(parts + (size_t)q * 2);
         const double tot = block_sum(v, sh);
         if (threadIdx.x == 0 && a.loss != nullptr) *a.loss = (float)tot;
     }
@@ -279,7 +370,8 @@ edge_gsum_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
     const int s = blockIdx.x / a.B, b = blockIdx.x - s * a.B;
     const int n = a.dh[s] * a.dw[s];
     const float s_inv = ((const float*)((const char*)a.workspace + L.img_inv))[s * a.B + b];
-    const double gd = image_partial_sum(parts, L, s, b, 2, 1, sh);
+    const double gd = L.vec_main ? range_partial_sum(parts, L.v_first[s] + b * L.v_per_img[s], L.v_per_img[s], 2, 1, sh)
+                                 : image_partial_sum(parts, L, s, b, 2, 1, sh);
     if (threadIdx.x == 0) ((float*)((char*)a.workspace + L.img_c))[s * a.B + b] = (float)(gd * (double)s_inv * (double)s_inv / (double)n);
 }
 
@@ -351,6 +443,133 @@ edge_main_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vector form of launch 2 (every width a multiple of 4, 16-byte aligned maps - the KITTI pyramids).  The kernel above
+// evaluates each edge weight twice (once from either end: 24 image loads and four expf per pixel, 288 instructions per
+// pixel, issue-bound).  Here a warp walks DOWN a strip of 120 columns (lanes 1..30 own four adjacent columns each,
+// lanes 0 / 31 are the halo), rows y, y + 1, y + 2 in three register sets that rotate without moves: every lane
+// evaluates the x- and y-difference anchored on each of its pixels ONCE - |dd| e into the forward sum, sgn(dd) e kept
+// for the gradient of the pixel itself and (by one shuffle / one row of registers) of its +x / +y neighbour.  One
+// 128-bit load of the disparity and three of the image per four pixels, one 128-bit store; per-warp partials in
+// fixed order: bitwise repeatable.
+// ---------------------------------------------------------------------------------------------
+struct EdgeRow { float d[4], i0[4], i1[4], i2[4]; };
+
+__device__ __forceinline__ float edge_sgn(float v) {
+    return __int_as_float((__float_as_int(v) & 0x80000000) | (v != 0.0f ? 0x3f800000 : 0));
+}
+
+__global__ void __launch_bounds__(EG_THREADS)
+edge_main_vec_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = blockIdx.x * (EG_THREADS / 32) + warp;
+    if (u >= L.v_first[PLB_MAX_SCALES]) return;
+    int s = 0;
+    while (s + 1 < a.n_scales && u >= L.v_first[s + 1]) ++s;
+    const int local = u - L.v_first[s];
+    const int b = local / L.v_per_img[s], rem = local - b * L.v_per_img[s];
+    const int strips = L.v_strips[s], chunk = rem / strips, strip = rem - chunk * strips;
+    const int h = a.dh[s], w = a.dw[s], n = h * w;
+    const int x = strip * EV_OWN - 4 + 4 * lane;                  // first of this lane's four columns
+    const bool colin = x >= 0 && x < w;                           // all four (w is a multiple of 4)
+    const bool own_lane = lane >= 1 && lane <= 30 && colin;
+    const int y0 = chunk * L.v_rows, y1 = min(y0 + L.v_rows, h);
+    const int ystart = max(y0 - 1, 0), ylast = min(y1, h - 1);    // rows read: the one above (its y-term), the one below
+    const float inv = a.normalize ? __ldg((const float*)((const char*)a.workspace + L.img_inv) + s * a.B + b) : 1.0f;
+    const float* disp = a.disp[s] + (size_t)b * n + (colin ? x : 0);
+    const float* img = ((L.f[s] > 1) ? (const float*)((const char*)a.workspace + L.pooled[s]) : a.tgt) + (size_t)b * 3 * n + (colin ? x : 0);
+    const float cx = L.cx[s], cy = L.cy[s];
+    const float up = a.upstream ? __ldg(a.upstream) : 1.0f;
+    float* gout = nullptr;
+    if (a.want_grad && a.g_disp[s] != nullptr) gout = (a.normalize ? a.g_scratch[s] : a.g_disp[s]) + (size_t)b * n + (colin ? x : 0);
+    const bool rmw = !a.normalize && a.accumulate != 0;
+    bool xok[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xok[c] = colin && x + c + 1 < w;
+
+    auto load = [&](EdgeRow& r, int y) {
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f), p0 = d, p1 = d, p2 = d;
+        if (colin && y <= ylast) {
+            const size_t o = (size_t)y * w;
+            d = __ldg(reinterpret_cast<const float4*>(disp + o));
+            p0 = __ldg(reinterpret_cast<const float4*>(img + o));
+            p1 = __ldg(reinterpret_cast<const float4*>(img + n + o));
+            p2 = __ldg(reinterpret_cast<const float4*>(img + 2 * (size_t)n + o));
+        }
+        r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z; r.d[3] = d.w;
+        r.i0[0] = p0.x; r.i0[1] = p0.y; r.i0[2] = p0.z; r.i0[3] = p0.w;
+        r.i1[0] = p1.x; r.i1[1] = p1.y; r.i1[2] = p1.z; r.i1[3] = p1.w;
+        r.i2[0] = p2.x; r.i2[1] = p2.y; r.i2[2] = p2.z; r.i2[3] = p2.w;
+    };
+    float ty_up[4] = {0.f, 0.f, 0.f, 0.f};                        // sgn(ddy) * ey of the row above
+    float lsum = 0.0f, gd = 0.0f;
+
+    auto step = [&](int y, const EdgeRow& cur, const EdgeRow& nxt) {
+        // the +x neighbour of the lane's last pixel: the first pixel of the lane to the right
+        const float dR = __shfl_down_sync(0xffffffffu, cur.d[0], 1);
+        const float r0 = __shfl_down_sync(0xffffffffu, cur.i0[0], 1), r1 = __shfl_down_sync(0xffffffffu, cur.i1[0], 1),
+                    r2 = __shfl_down_sync(0xffffffffu, cur.i2[0], 1);
+        const bool yok = y + 1 < h;
+        const bool owned = own_lane && y >= y0;
+        float tx[4], ty[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float dn = c < 3 ? cur.d[c < 3 ? c + 1 : 3] : dR;
+            const float n0 = c < 3 ? cur.i0[c < 3 ? c + 1 : 3] : r0, n1 = c < 3 ? cur.i1[c < 3 ? c + 1 : 3] : r1,
+                        n2 = c < 3 ? cur.i2[c < 3 ? c + 1 : 3] : r2;
+            const float gx = fabsf(cur.i0[c] - n0) + fabsf(cur.i1[c] - n1) + fabsf(cur.i2[c] - n2);
+            const float gy = fabsf(cur.i0[c] - nxt.i0[c]) + fabsf(cur.i1[c] - nxt.i1[c]) + fabsf(cur.i2[c] - nxt.i2[c]);
+            const float ex = xok[c] ? expf(-gx * (1.0f / 3.0f)) * cx : 0.0f;
+            const float ey = (yok && colin) ? expf(-gy * (1.0f / 3.0f)) * cy : 0.0f;
+            const float d0 = cur.d[c] * inv;
+            const float ddx = d0 - dn * inv, ddy = d0 - nxt.d[c] * inv;
+            tx[c] = edge_sgn(ddx) * ex;
+            ty[c] = edge_sgn(ddy) * ey;
+            if (owned) { lsum = fmaf(fabsf(ddx), ex, lsum); lsum = fmaf(fabsf(ddy), ey, lsum); }
+        }
+        const float txL = __shfl_up_sync(0xffffffffu, tx[3], 1);  // the x-term anchored on the pixel to the left
+        if (owned && gout != nullptr) {
+            float g[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float left = c > 0 ? tx[c > 0 ? c - 1 : 0] : txL;
+                g[c] = ((tx[c] - left) + (ty[c] - ty_up[c])) * up;
+                gd = fmaf(g[c], cur.d[c], gd);
+            }
+            float4* q = reinterpret_cast<float4*>(gout + (size_t)y * w);
+            if (rmw) { const float4 o = *q; g[0] += o.x; g[1] += o.y; g[2] += o.z; g[3] += o.w; }
+            *q = make_float4(g[0], g[1], g[2], g[3]);
+        } else if (owned) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float left = c > 0 ? tx[c > 0 ? c - 1 : 0] : txL;
+                gd = fmaf(((tx[c] - left) + (ty[c] - ty_up[c])) * up, cur.d[c], gd);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ty_up[c] = ty[c];
+    };
+
+    EdgeRow A, Bq, C;
+    load(A, ystart); load(Bq, ystart + 1); load(C, ystart + 2);
+    int y = ystart;
+#pragma unroll 1
+    while (true) {
+        step(y, A, Bq); if (++y >= y1) break; load(A, y + 2);
+        step(y, Bq, C); if (++y >= y1) break; load(Bq, y + 2);
+        step(y, C, A); if (++y >= y1) break; load(C, y + 2);
+    }
+    // the warp's partials, lanes in a fixed (butterfly) order
+    double l = (double)lsum, q = (double)gd;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+        double* parts = (double*)((char*)a.workspace + L.part_loss);
+        parts[(size_t)u * 2] = l;
+        parts[(size_t)u * 2 + 1] = q;
+    }
+}
+
 // launch 3 (only when normalising with gradients): g = g' inv - sum(g' d) inv^2 / (h w)
 __global__ void __launch_bounds__(EG_THREADS)
 edge_final_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
@@ -359,6 +578,19 @@ edge_final_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant
     if (!(a.normalize && a.want_grad && a.g_disp[k.s] != nullptr)) return;
     const float s_inv = __ldg((const float*)((const char*)a.workspace + L.img_inv) + k.s * a.B + k.b);
     const float s_c = __ldg((const float*)((const char*)a.workspace + L.img_c) + k.s * a.B + k.b);
+    if ((n & 3) == 0 && (((size_t)a.g_scratch[k.s] | (size_t)a.g_disp[k.s]) & 15) == 0) {
+        // four consecutive pixels per thread: 128-bit loads and stores
+        const int o = (k.o0 - (int)threadIdx.x) + 4 * (int)threadIdx.x;
+        if (o < n) {
+            const size_t go = (size_t)k.b * n + o;
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(a.g_scratch[k.s] + go));
+            float4 g = make_float4(v.x * s_inv - s_c, v.y * s_inv - s_c, v.z * s_inv - s_c, v.w * s_inv - s_c);
+            float4* out = reinterpret_cast<float4*>(a.g_disp[k.s] + go);
+            if (a.accumulate) { const float4 w = *out; g.x += w.x; g.y += w.y; g.z += w.z; g.w += w.w; }
+            *out = g;
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < EG_PX; ++j) {
         const int o = k.o0 + j * EG_THREADS;
@@ -394,9 +626,14 @@ int edge_launch(const plb_edge_args* a, cudaStream_t st) {
     const EdgeLayout L = edge_layout(*a);
     const int nb = L.first_block[PLB_MAX_SCALES];
     if (L.any_tile_pooled) {
-        dim3 pg((a->W + EP_T - 1) / EP_T, (a->H + EP_T - 1) / EP_T, a->B);
-        if (pg.z > 65535) return PLB_EINVAL;
-        edge_pool_kernel<<<pg, EG_THREADS, 0, st>>>(*a, L);
+        if (a->B > 65535) return PLB_EINVAL;
+        const bool fast = (a->W % 32) == 0 && (a->H % 16) == 0 && L.level_scale[5] < 0 && ((size_t)a->tgt & 15) == 0;
+        if (fast) {
+            edge_pool_fast_kernel<<<dim3((a->W + 63) / 64, (a->H + 63) / 64, a->B), EG_THREADS, 0, st>>>(*a, L);
+        } else {
+            dim3 pg((a->W + EP_T - 1) / EP_T, (a->H + EP_T - 1) / EP_T, a->B);
+            edge_pool_kernel<<<pg, EG_THREADS, 0, st>>>(*a, L);
+        }
         ++g_launches;
         PLB_CHECK_LAUNCH();
     }
@@ -408,7 +645,12 @@ int edge_launch(const plb_edge_args* a, cudaStream_t st) {
         ++g_launches;
         PLB_CHECK_LAUNCH();
     }
-    edge_main_kernel<<<nb, EG_THREADS, 0, st>>>(*a, L);
+    if (L.vec_main) {
+        const int warps = L.v_first[PLB_MAX_SCALES];
+        edge_main_vec_kernel<<<(warps + EG_THREADS / 32 - 1) / (EG_THREADS / 32), EG_THREADS, 0, st>>>(*a, L);
+    } else {
+        edge_main_kernel<<<nb, EG_THREADS, 0, st>>>(*a, L);
+    }
     ++g_launches;
     PLB_CHECK_LAUNCH();
     edge_gsum_kernel<<<(a->normalize && a->want_grad) ? a->n_scales * a->B : 1, EG_THREADS, 0, st>>>(*a, L);
