@@ -310,13 +310,10 @@ def step_fn(criterion, g, cfg, leaves=None):
         for fr in disp:
             for d in fr:
                 d.grad = None
-    if cfg["variant"] == "live":
+    if cfg["variant"] in ("live", "live_edge"):
+        # live_edge: the criterion is Losses(smoothness="edge") - the edge-aware term inside the same fused call
         loss = criterion.forward(g["tgt"], g["ref_imgs"], disp, poses, g["intrinsics"], None)
         total = loss[0] + loss[1]
-    elif cfg["variant"] == "live_edge":
-        from plb200 import ops
-        mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp, poses, g["intrinsics"], do_smooth=False, deterministic=True)
-        total = mam + criterion.edge_aware_smooth_loss(disp[0], g["tgt"])
     elif cfg["variant"] in ("min", "minclip"):
         from plb200 import ops, _lib
         mam, _ = ops.fused_losses(g["tgt"], g["ref_imgs"], disp[:1], poses, g["intrinsics"], do_smooth=False,
@@ -342,7 +339,7 @@ def run_ours(args, cfg):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local if world > 1 else 0)
     torch.cuda.set_device(dev)
-    criterion = Losses()
+    criterion = Losses(smoothness="edge", deterministic=True) if cfg["variant"] == "live_edge" else Losses()
     from plb200 import ops as _ops
     n_sets = args.sets
     cpu_sets = make_sets(cfg, n_sets, 1234 + 1000 * rank, dev)
@@ -357,7 +354,7 @@ def run_ours(args, cfg):
     def capture():
         """One CUDA graph per input set, captured from the public-API calls of a step (the launch geometry - the
         persistent grid's size - is part of a graph, so a different sm_limit means a new capture)."""
-        if use_graph and cfg["variant"] == "live":
+        if use_graph and cfg["variant"] in ("live", "live_edge"):
             # the public graphed step (Losses.capture(), plb200/graphed.py): static buffers per input set, replayed
             # without copy-in; it owns its backward call, so no guarded relaunch is part of the graph
             n0 = _lib.launch_count()
@@ -495,7 +492,7 @@ def run_ours(args, cfg):
         ems, hms = time_eager(criterion, gpu_sets, cfg, dev, max(20, min(args.steps, 100)))
         eager_step = {"value": px_per_step / 1e6 / (ems / 1e3), "unit": UNIT, "ms_per_step": ems, "host_ms_per_step": hms,
                       "note": "same step issued eagerly through Losses.forward / backward (no CUDA graph), device-resident inputs"}
-        if cfg["variant"] == "live":
+        if cfg["variant"] in ("live", "live_edge"):
             cms, chms = time_captured(criterion, gpu_sets, dev, max(20, min(args.steps, 100)))
             eager_step["captured"] = {"value": px_per_step / 1e6 / (cms / 1e3), "unit": UNIT, "ms_per_step": cms,
                                       "host_ms_per_step": chms,
@@ -578,7 +575,7 @@ def run_ours(args, cfg):
                                       "batch-sharded x%d, no data-path collective" % world,
                        "l2": "inputs rotate over %d distinct sets (%.0f MB per GPU) > 126 MB L2" % (n_sets, pool_mb),
                        "step": ("CUDA-graph replay of Losses.capture() (forward + backward over static buffers; the step owns its "
-                                "backward call, so the graph holds no guarded relaunch)" if cfg["variant"] == "live" else
+                                "backward call, so the graph holds no guarded relaunch)" if cfg["variant"] in ("live", "live_edge") else
                                 "CUDA-graph replay of the public-API forward + backward") if use_graph else "eager public API"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],

@@ -178,6 +178,7 @@ typedef struct plb_edge_args {
     const float* upstream;              /* device scalar or NULL (=1)                               */
     void* workspace;                    /* plb_edge_smooth_workspace_bytes() bytes                  */
     size_t workspace_bytes;
+    const float* skip_if_unit[2];       /* as in plb_photo_args: the fused step relaunches behind this guard */
 } plb_edge_args;
 
 size_t plb_edge_smooth_workspace_bytes(const plb_edge_args* args);

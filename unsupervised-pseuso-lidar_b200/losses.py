@@ -32,7 +32,8 @@ class Losses:
     """`losses.py:56-271`.  Constructor takes no arguments in the reference
     (trainer.py:79); the keyword options only select implementation variants."""
 
-    def __init__(self, rotation_mode="axisangle", fused_backward=True, disp_head=None, deterministic=None):
+    def __init__(self, rotation_mode="axisangle", fused_backward=True, disp_head=None, deterministic=None,
+                 smoothness="second_order"):
         self.SSIM = SSIM()
         self.clip_loss = 0.5
         self.rotation_mode = rotation_mode
@@ -44,6 +45,12 @@ class Losses:
         # deterministic=True: image gradients (when a frame requires grad) are accumulated in order-independent
         # fixed point, so EVERY output is bitwise repeatable; None follows torch.use_deterministic_algorithms()
         self.deterministic = deterministic
+        # smoothness="edge": `forward` returns [loss_mam, edge-aware smoothness of the target frame's disparity pyramid]
+        # (`edge_aware_smooth_loss`, not in the reference) - evaluated inside the same call, its gradient accumulated into
+        # the photometric term's maps; "second_order" is the reference's `smooth_loss` (losses.py:242-260)
+        if smoothness not in ("second_order", "edge"):
+            raise ValueError("smoothness must be 'second_order' or 'edge'")
+        self.smoothness = smoothness
 
     # ---- live path -------------------------------------------------------
     def forward(self, tgt_img, ref_imgs, disparity, poses, intrinsics, gt=None):
@@ -51,7 +58,8 @@ class Losses:
         pyr = [list(frame) if isinstance(frame, (list, tuple)) else [frame] for frame in disparity]
         mam, smooth = ops.fused_losses(tgt_img, list(ref_imgs), pyr, poses, intrinsics, input_is_depth=False,
                                        rotation_mode=self.rotation_mode, fused_backward=self.fused_backward,
-                                       disp_head=self.disp_head, deterministic=self.deterministic)
+                                       disp_head=self.disp_head, deterministic=self.deterministic,
+                                       edge=self.smoothness == "edge")
         return [mam, smooth]
 
     __call__ = forward

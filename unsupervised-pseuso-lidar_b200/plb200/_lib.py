@@ -106,6 +106,7 @@ class EdgeArgs(C.Structure):
         ("upstream", _fp),
         ("workspace", _fp),
         ("workspace_bytes", C.c_size_t),
+        ("skip_if_unit", _fp * 2),
     ]
 
 

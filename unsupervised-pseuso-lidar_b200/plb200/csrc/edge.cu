@@ -188,6 +188,7 @@ __device__ __forceinline__ float box_sum_any(const float* __restrict__ src, int 
 constexpr int EP_T = 32;
 __global__ void __launch_bounds__(EG_THREADS)
 edge_pool_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     __shared__ float t0[3][EP_T][EP_T + 1];
     __shared__ float t1[3][EP_T / 2][EP_T / 2 + 1];
     const int tid = threadIdx.x, b = blockIdx.z;
@@ -247,6 +248,7 @@ edge_pool_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
 // per input value and ten barriers per 12 KB tile: 74 us for the 94 MB of a 64-image batch.)
 __global__ void __launch_bounds__(EG_THREADS)
 edge_pool_fast_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.z;
     const int X0 = blockIdx.x * 64 + (warp & 1) * 32, Y0 = blockIdx.y * 64 + (warp >> 1) * 16;
     if (X0 >= a.W || Y0 >= a.H) return;
@@ -288,6 +290,7 @@ edge_pool_fast_kernel(const __grid_constant__ plb_edge_args a, const __grid_cons
 // launch 1: pooled target images of the low scales + per-block disparity sums
 __global__ void __launch_bounds__(EG_THREADS)
 edge_prep_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     __shared__ double sh[EG_THREADS / 32];
     const EdgeWork k = edge_work(a, L);
     const int n = k.h * k.w;
@@ -348,6 +351,7 @@ __device__ __forceinline__ float sgn1(float v) { return v > 0.0f ? 1.0f : (v < 0
 // normalisation's gradient, and (block 0) the loss.  Same partials, same fixed order: bitwise the same values.
 __global__ void __launch_bounds__(EG_THREADS)
 edge_mean_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     __shared__ double sh[EG_THREADS / 32];
     const int s = blockIdx.x / a.B, b = blockIdx.x - s * a.B;
     const int n = a.dh[s] * a.dw[s];
@@ -357,6 +361,7 @@ edge_mean_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
 
 __global__ void __launch_bounds__(EG_THREADS)
 edge_gsum_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     __shared__ double sh[EG_THREADS / 32];
     const double* parts = (const double*)((const char*)a.workspace + L.part_loss);
     if (blockIdx.x == 0) {
@@ -378,6 +383,7 @@ edge_gsum_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
 // launch 2: loss partials and the unnormalised gradient
 __global__ void __launch_bounds__(EG_THREADS)
 edge_main_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     __shared__ double sh[EG_THREADS / 32];
     const EdgeWork k = edge_work(a, L);
     const int n = k.h * k.w, w = k.w, h = k.h;
@@ -461,6 +467,7 @@ __device__ __forceinline__ float edge_sgn(float v) {
 
 __global__ void __launch_bounds__(EG_THREADS)
 edge_main_vec_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int u = blockIdx.x * (EG_THREADS / 32) + warp;
     if (u >= L.v_first[PLB_MAX_SCALES]) return;
@@ -573,6 +580,7 @@ edge_main_vec_kernel(const __grid_constant__ plb_edge_args a, const __grid_const
 // launch 3 (only when normalising with gradients): g = g' inv - sum(g' d) inv^2 / (h w)
 __global__ void __launch_bounds__(EG_THREADS)
 edge_final_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant__ EdgeLayout L) {
+    if (skip_launch(a.skip_if_unit)) return;
     const EdgeWork k = edge_work(a, L);
     const int n = k.h * k.w;
     if (!(a.normalize && a.want_grad && a.g_disp[k.s] != nullptr)) return;

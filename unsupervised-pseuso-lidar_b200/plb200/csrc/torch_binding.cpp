@@ -45,6 +45,7 @@ struct Cfg {
     bool deterministic = false;
     float clip_loss = 0.0f;
     int sm_limit = 0;
+    bool edge = false;               // the smoothness term is the edge-aware one (plb_edge_smooth_loss) on frame 0's disparities
 };
 
 void check(int rc, const char* what) {
@@ -90,6 +91,9 @@ struct State : torch::CustomClassHolder {
     Tensor g_poses;
     plb_photo_args a;
     plb_smooth_args s;
+    plb_edge_args e;
+    std::vector<Tensor> g_scratch;
+    Tensor ws_edge;
     cudaStream_t st = nullptr;
     Tensor ws_photo, ws_smooth;
     bool fused = false, img_grad = false, used = false, have_args = false;
@@ -166,7 +170,37 @@ void launch_loss(State& S, bool want_grad, const std::vector<std::vector<Tensor>
         a.workspace_bytes = (size_t)S.ws_photo.numel();
         check(plb_photo_loss(&a, st), "plb_photo_loss");
     }
-    if (cfg.do_smooth) {
+    if (cfg.do_smooth && cfg.edge) {
+        // edge-aware first-order smoothness of the target frame's disparity pyramid, accumulated into the same gradient
+        // maps as the photometric term
+        plb_edge_args& e = S.e;
+        e = plb_edge_args();
+        e.B = (int)B; e.H = (int)H; e.W = (int)W;
+        e.n_scales = (int)S.pyr[0].size();
+        e.tgt = S.tgt.data_ptr<float>();
+        const bool g = want_grad && g_pyr;
+        if (g && S.g_scratch.size() != S.pyr[0].size()) {
+            S.g_scratch.clear();
+            for (auto& d : S.pyr[0]) S.g_scratch.push_back(torch::empty_like(d));
+        }
+        for (int k = 0; k < e.n_scales; ++k) {
+            const Tensor& d = S.pyr[0][k];
+            e.disp[k] = d.data_ptr<float>();
+            e.dh[k] = (int)d.size(-2); e.dw[k] = (int)d.size(-1);
+            e.g_disp[k] = g ? fptr((*g_pyr)[0][k]) : nullptr;
+            e.g_scratch[k] = g ? fptr(S.g_scratch[k]) : nullptr;
+        }
+        e.accumulate = cfg.do_photo ? 1 : 0;
+        e.normalize = 1;
+        e.want_grad = want_grad ? 1 : 0;
+        e.loss = out + 1;
+        e.upstream = up1;
+        if (skip) { e.skip_if_unit[0] = up0; e.skip_if_unit[1] = up1; }
+        const size_t nbytes = plb_edge_smooth_workspace_bytes(&e);
+        S.ws_edge = workspace(2, nbytes, dev, st);
+        e.workspace = S.ws_edge.data_ptr();
+        e.workspace_bytes = (size_t)S.ws_edge.numel();
+    } else if (cfg.do_smooth) {
         plb_smooth_args& s = S.s;
         s = plb_smooth_args();
         s.B = (int)B;
@@ -191,6 +225,7 @@ void launch_loss(State& S, bool want_grad, const std::vector<std::vector<Tensor>
         s.workspace_bytes = (size_t)S.ws_smooth.numel();
         check(plb_smooth_loss(&s, st), "plb_smooth_loss");
     }
+    if (cfg.do_smooth && cfg.edge) check(plb_edge_smooth_loss(&S.e, st), "plb_edge_smooth_loss");
     S.have_args = true;
 }
 
@@ -294,7 +329,12 @@ struct FusedLoss : public torch::autograd::Function<FusedLoss> {
                 S->a.skip_if_unit[0] = up0; S->a.skip_if_unit[1] = up1;
                 check(plb_photo_loss(&S->a, st), "plb_photo_loss");
             }
-            if (cfg.do_smooth) {
+            if (cfg.do_smooth && cfg.edge) {
+                S->e.want_grad = 1;
+                S->e.loss = scratch.data_ptr<float>() + 1; S->e.upstream = up1;
+                S->e.skip_if_unit[0] = up0; S->e.skip_if_unit[1] = up1;
+                check(plb_edge_smooth_loss(&S->e, st), "plb_edge_smooth_loss");
+            } else if (cfg.do_smooth) {
                 S->s.want_grad = 1;
                 S->s.loss = scratch.data_ptr<float>() + 1; S->s.upstream = up1;
                 S->s.skip_if_unit[0] = up0; S->s.skip_if_unit[1] = up1;
@@ -323,14 +363,15 @@ struct FusedLoss : public torch::autograd::Function<FusedLoss> {
 std::vector<Tensor> fused_losses(std::vector<Tensor> inputs, int64_t n_src, std::vector<int64_t> scales, int64_t input_kind,
                                  bool do_photo, bool do_smooth, int64_t rotation_mode, bool fused_backward, double disp_a,
                                  double disp_b, double scale_decay, int64_t mode, int64_t flags, double head_alpha,
-                                 double head_beta, bool deterministic, double clip_loss, int64_t sm_limit) {
+                                 double head_beta, bool deterministic, double clip_loss, int64_t sm_limit, bool edge) {
     auto S = c10::make_intrusive<State>();
     Cfg& c = S->cfg;
     c.n_src = (int)n_src; c.scales = std::move(scales); c.input_kind = (int)input_kind;
     c.do_photo = do_photo; c.do_smooth = do_smooth; c.rotation_mode = (int)rotation_mode; c.fused_backward = fused_backward;
     c.disp_a = (float)disp_a; c.disp_b = (float)disp_b; c.scale_decay = (float)scale_decay;
     c.mode = (int)mode; c.flags = (uint32_t)flags; c.head_alpha = (float)head_alpha; c.head_beta = (float)head_beta;
-    c.deterministic = deterministic; c.clip_loss = (float)clip_loss; c.sm_limit = (int)sm_limit;
+    c.deterministic = deterministic; c.clip_loss = (float)clip_loss; c.sm_limit = (int)sm_limit; c.edge = edge;
+    TORCH_CHECK(!edge || c.input_kind == PLB_INPUT_DISP, "the edge-aware smoothness takes disparities (no depth input, no folded head)");
     // which inputs want a gradient (asked here: grad mode is switched off inside forward())
     const bool grad_on = at::GradMode::is_enabled();
     for (const Tensor& t : inputs) S->need.push_back(grad_on && t.defined() && t.requires_grad());

@@ -98,8 +98,11 @@ class LossConfig:
 
     def __init__(self, n_src, scales_per_frame, input_is_depth=False, do_photo=True, do_smooth=True,
                  rotation_mode="axisangle", fused_backward=True, disp_a=10.0, disp_b=0.01, scale_decay=2.3,
-                 mode=_lib.PHOTO_L1_MEAN, flags=0, disp_head=None, deterministic=None, clip_loss=None):
+                 mode=_lib.PHOTO_L1_MEAN, flags=0, disp_head=None, deterministic=None, clip_loss=None, edge=False):
         self.n_src = n_src
+        # edge=True: the smoothness term of the step is the edge-aware first-order one (north_star's variant; not in the
+        # reference) on the target frame's disparity pyramid - inside the same call, accumulated into the same gradient maps
+        self.edge = bool(edge)
         self.scales_per_frame = list(scales_per_frame)  # e.g. [4, 4]: frames with a depth pyramid
         self.input_is_depth = bool(input_is_depth)
         self.do_photo, self.do_smooth = do_photo, do_smooth
@@ -383,12 +386,14 @@ def fused_losses(tgt, refs, pyramids, poses, K, binding=None, **cfg_kw):
     from . import _tb
     if binding == "torch" and _tb.mod is None:
         raise RuntimeError("the torch C++ binding is not built (plb200/build.py --torch)")
+    if cfg.edge and (binding == "ctypes" or _tb.mod is None):
+        raise RuntimeError("edge=True (the edge-aware term inside the fused step) needs the torch C++ binding")
     if binding != "ctypes" and _tb.mod is not None:
         head = cfg.disp_head or (0.0, 0.0)
         out = _tb.mod.fused_losses([tgt, poses, K, *refs, *flat], cfg.n_src, cfg.scales_per_frame, cfg.input_kind,
                                    cfg.do_photo, cfg.do_smooth, cfg.rotation_mode, cfg.fused_backward, cfg.disp_a,
                                    cfg.disp_b, cfg.scale_decay, cfg.mode, cfg.flags, head[0], head[1],
-                                   cfg.deterministic, cfg.clip_loss or 0.0, _sm_limit)
+                                   cfg.deterministic, cfg.clip_loss or 0.0, _sm_limit, cfg.edge)
         return out[0], out[1]
     return FusedLossFn.apply(cfg, tgt, poses, K, *refs, *flat)
 
