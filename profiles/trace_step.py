@@ -19,7 +19,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 cfg = bench.WORKLOADS[wl]
 dev = torch.device("cuda:0")
 sets = [synth.to_device(s, dev) for s in bench.make_sets(cfg, 4, 1234, dev)]
-crit = Losses()
+crit = Losses(smoothness="edge", deterministic=True) if cfg["variant"] == "live_edge" else Losses()
 side = torch.cuda.Stream(device=dev)
 with torch.cuda.stream(side):
     for g in sets:

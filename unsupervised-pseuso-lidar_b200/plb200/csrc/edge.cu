@@ -21,6 +21,9 @@ constexpr int EG_THREADS = 256;
 constexpr int EG_PX = 4;                       // consecutive pixels per thread: the per-block work (which scale / image am
 constexpr int EG_TILE = EG_THREADS * EG_PX;    // I, image mean, block sums) is amortised over 1024 pixels
 constexpr int EV_OWN = 30 * 4;                 // edge_main_vec_kernel: columns a warp owns (lanes 1..30, four each)
+#ifndef EV_WARPS_PER_SM
+#define EV_WARPS_PER_SM 12                    // the row chunks shrink until the launch has this many warps per SM
+#endif
 
 // Launch-time constants, computed once on the host.
 struct EdgeLayout {
@@ -98,7 +101,7 @@ __host__ inline EdgeLayout edge_layout(const plb_edge_args& a) {
             }
         }
         L.v_first[PLB_MAX_SCALES] = nv;
-        if (nv >= 148 * 12) break;
+        if (nv >= 148 * EV_WARPS_PER_SM) break;
     }
     const int n_part = L.vec_main && nv > nb ? nv : nb;          // partial records: blocks (scalar) or warps (vector)
     L.part_mean = off; off += ((size_t)nb * sizeof(double) + 255) / 256 * 256;
