@@ -1055,6 +1055,96 @@ photo_lowres_merge_kernel(const __grid_constant__ PhotoLaunch p, const __grid_co
     job.g_disp[s][o] = acc * chain;
 }
 
+// The same merge with the partial rows staged in shared memory (W a multiple of 4, 16-byte aligned planes, a row group
+// that fits 16 KB).  The kernel above lets every low-resolution pixel gather its 2 F taps straight from the planes:
+// lanes F floats apart, so one load instruction touches 8 - 32 sectors and the launch is bound by L1 sector traffic
+// (69 us for 110 MB at batch 64).  Here a block owns whole rows: the slots (and contributors) of each are summed while
+// they stream in through coalesced 128-bit loads - in the order the gather used, (a0 + a1) + (b0 + b1) - into one
+// W-float row of shared memory (one pad word per 32, so the stride-F reads of the second phase hit distinct banks), and
+// the pixels then take their taps from there with the same weights in the same order: bitwise the same gradients.
+constexpr int LS_MAX_FLOATS = 4096;            // staged floats per block (16 KB + padding)
+__device__ __forceinline__ int ls_pad(int x) { return x + (x >> 5); }
+
+template <int F>
+__device__ __forceinline__ float lowres_gather_smem(const float* v, int i, int dw, int W) {
+    constexpr int HF = F / 2;
+    const int xs = i * F - HF;
+    float acc = 0.0f;
+    if (i > 0 && i < dw - 1) {
+#pragma unroll
+        for (int t = 0; t < 2 * F; ++t) {
+            const float w = t < F ? ((float)t + 0.5f) * (1.0f / (float)F) : 1.0f - ((float)(t - F) + 0.5f) * (1.0f / (float)F);
+            acc = fmaf(w, v[ls_pad(xs + t)], acc);
+        }
+    } else {
+#pragma unroll 1
+        for (int t = 0; t < 2 * F; ++t) {
+            const int x = xs + t;
+            if (x < 0 || x >= W) continue;
+            float w = t < F ? ((float)t + 0.5f) * (1.0f / (float)F) : 1.0f - ((float)(t - F) + 0.5f) * (1.0f / (float)F);
+            if (x < HF) w = (i == 0) ? 1.0f : 0.0f;
+            if (i == dw - 1 && x >= W - HF) w = 1.0f;
+            acc = fmaf(w, v[ls_pad(x)], acc);
+        }
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(LM_THREADS)
+photo_lowres_merge_smem_kernel(const __grid_constant__ PhotoLaunch p, const __grid_constant__ LowMergeLaunch u) {
+    const plb_photo_args& a = p.a;
+    if (skip_launch(a.skip_if_unit)) return;
+    __shared__ float sv[LS_MAX_FLOATS + LS_MAX_FLOATS / 32 + 8];
+    int it = 0;
+#pragma unroll
+    for (int k = 1; k < PLB_MAX_JOBS * PLB_MAX_SCALES; ++k)
+        if (k < u.n_items && (int)blockIdx.x >= u.items[k].first_block) it = k;
+    const LowMergeItem item = u.items[it];
+    const plb_photo_job& job = a.jobs[item.jb];
+    const int s = item.s, dh = job.dh[s], dw = job.dw[s], W = a.W;
+    const int rows_total = a.B * dh, lr = item.col_chunks;                 // (col_chunks holds the rows per block here)
+    const int r0 = ((int)blockIdx.x - item.first_block) * lr;
+    const int nr = min(lr, rows_total - r0);
+    const float* base = (const float*)((const char*)a.workspace + p.L.ylow) + p.L.ylow_off[item.jb][s];
+    const size_t cstride = (size_t)a.B * 2 * dh * W, slot = (size_t)dh * W;
+    const int w4 = W >> 2, wp = ls_pad(W) + 1;                             // padded row pitch in shared memory
+    // phase 1: v[r][x] = sum over slots (and contributors) of the partial planes
+    for (int k = threadIdx.x; k < nr * w4; k += LM_THREADS) {
+        const int r = k / w4, x = (k - r * w4) << 2;
+        const int bj = r0 + r, b = bj / dh, j = bj - b * dh;
+        const float* q = base + ((size_t)b * 2 * dh + j) * W + x;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(q)), a1 = __ldg(reinterpret_cast<const float4*>(q + slot));
+        float4 v = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+        if (item.n_contrib > 1) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(q + cstride)), b1 = __ldg(reinterpret_cast<const float4*>(q + cstride + slot));
+            v.x += b0.x + b1.x; v.y += b0.y + b1.y; v.z += b0.z + b1.z; v.w += b0.w + b1.w;
+        }
+        float* d = sv + r * wp + ls_pad(x);                                // x is a multiple of 4: the four words share a pad group
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    // phase 2: the low-resolution pixels of the rows
+    for (int k = threadIdx.x; k < nr * dw; k += LM_THREADS) {
+        const int r = k / dw, i = k - r * dw;
+        const float* v = sv + r * wp;
+        const float acc = item.f == 2 ? lowres_gather_smem<2>(v, i, dw, W) : item.f == 4 ? lowres_gather_smem<4>(v, i, dw, W)
+                                                                                         : lowres_gather_smem<8>(v, i, dw, W);
+        float chain = 1.0f;
+        const size_t o = (size_t)(r0 + r) * dw + i;
+        if (a.input_is_depth != PLB_INPUT_DEPTH) {
+            float d = __ldg(job.disp[s] + o), hc = 1.0f;
+            if (a.input_is_depth == PLB_INPUT_LOGIT) {
+                const float sg = 1.0f / (1.0f + expf(-d));
+                d = fmaf(a.head_alpha, sg, a.head_beta);
+                hc = a.head_alpha * sg * (1.0f - sg);
+            }
+            const float D = 1.0f / (a.disp_a * d + a.disp_b);
+            chain = -a.disp_a * D * D * hc;
+        }
+        job.g_disp[s][o] = acc * chain;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Finalize: one block per image.  For every job of the image: fixed-order sum of the block records
 // of that (job, image) pair -> d loss / d P per source (through K^-1) -> K^T . dP -> (inverse) ->
@@ -1652,6 +1742,16 @@ static int photo_lowres_merge_launch(const PhotoLaunch& p, cudaStream_t st) {
     LowMergeLaunch u;
     u.n_items = 0;
     u.total_blocks = 0;
+    // rows staged in shared memory when they are whole 128-bit packets and a row fits the stage
+    const float* ylow = (const float*)((const char*)a.workspace + p.L.ylow);
+    bool staged = (a.W & 3) == 0 && a.W <= LS_MAX_FLOATS && ((uintptr_t)ylow & 15) == 0;
+    for (int j = 0; j < a.n_jobs && staged; ++j)
+        for (int s = 0; s < a.jobs[j].n_scales; ++s)
+            if ((p.smode[j][s] & 3) == PH_SM_LOWFAST && (p.L.ylow_off[j][s] & 3)) staged = false;
+#ifdef PH_MERGE_GATHER
+    staged = false;
+#endif
+    const int lr = staged ? (LS_MAX_FLOATS / a.W > 8 ? 8 : LS_MAX_FLOATS / a.W) : 0;
     for (int j = 0; j < a.n_jobs; ++j)
         for (int s = 0; s < a.jobs[j].n_scales; ++s) {
             if ((p.smode[j][s] & 3) != PH_SM_LOWFAST) continue;
@@ -1659,12 +1759,18 @@ static int photo_lowres_merge_launch(const PhotoLaunch& p, cudaStream_t st) {
             it.jb = j; it.s = s; it.first_block = u.total_blocks;
             it.n_contrib = (p.smode[j][s] & 4) ? 2 : 1;
             it.f = a.W / a.jobs[j].dw[s];
-            it.col_chunks = (a.jobs[j].dw[s] + LM_COLS - 1) / LM_COLS;
             const long long rows = (long long)a.B * a.jobs[j].dh[s];                      // < 2^31: validate_photo
-            u.total_blocks += (int)((rows + LM_ROWS - 1) / LM_ROWS) * it.col_chunks;
+            if (staged) {
+                it.col_chunks = lr;                                                        // rows per block
+                u.total_blocks += (int)((rows + lr - 1) / lr);
+            } else {
+                it.col_chunks = (a.jobs[j].dw[s] + LM_COLS - 1) / LM_COLS;
+                u.total_blocks += (int)((rows + LM_ROWS - 1) / LM_ROWS) * it.col_chunks;
+            }
         }
     if (u.n_items == 0) return PLB_OK;
-    photo_lowres_merge_kernel<<<u.total_blocks, LM_THREADS, 0, st>>>(p, u);
+    if (staged) photo_lowres_merge_smem_kernel<<<u.total_blocks, LM_THREADS, 0, st>>>(p, u);
+    else photo_lowres_merge_kernel<<<u.total_blocks, LM_THREADS, 0, st>>>(p, u);
     ++g_launches;
     PLB_CHECK_LAUNCH();
     return PLB_OK;
