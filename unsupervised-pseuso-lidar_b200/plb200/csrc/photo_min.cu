@@ -419,21 +419,36 @@ photo_min_kernel(const __grid_constant__ PminLaunch p) {
     const bool border = tx0 == 0 || ty0 == 0 || tx0 + PM_TW + 1 >= W || ty0 + PM_TH + 1 >= H;
 
     // ---- target tile (+2, reflected) and the automask reference min_i photo(src_i, tgt) -------------
-    for (int k = tid; k < PM_N2; k += PM_THREADS) {
-        const int ly = k / PM_W2, lx = k - ly * PM_W2;
-        const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
-        const int o = gy * W + gx;
+    {
+        // the image pointers live in shared memory (pc): read them ONCE into registers and issue every load of a pixel
+        // before the first store - with the pointers re-read behind every shared-memory store (possible aliasing) the
+        // loads of a pixel ran one after the other, each at the full latency of a global load
+        const float* tg = pc.tgt;
+        const float* sp[NSMAX];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) S.T2[c][k] = f2(__ldg(pc.tgt + (o + c * plane)));
-        if (automask) {
+        for (int i = 0; i < NSMAX; ++i) sp[i] = pc.src[i < n_src ? i : 0];
+        for (int k = tid; k < PM_N2; k += PM_THREADS) {
+            const int ly = k / PM_W2, lx = k - ly * PM_W2;
+            const int gx = reflect_idx(tx0 + lx - 2, W), gy = reflect_idx(ty0 + ly - 2, H);
+            const int o = gy * W + gx;
+            float t[3], x[NSMAX][3];
 #pragma unroll
-            for (int g = 0; g < NSMAX / 2; ++g) {
-                if (2 * g >= n_src) continue;
-                const bool two = 2 * g + 1 < n_src;
+            for (int c = 0; c < 3; ++c) t[c] = __ldg(tg + (o + c * plane));
+            if (automask) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    S.X2[g][c][k] = make_float2(__ldg(pc.src[2 * g] + (o + c * plane)),
-                                                two ? __ldg(pc.src[2 * g + 1] + (o + c * plane)) : 0.0f);
+                for (int i = 0; i < NSMAX; ++i)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[i][c] = i < n_src ? __ldg(sp[i] + (o + c * plane)) : 0.0f;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) S.T2[c][k] = f2(t[c]);
+            if (automask) {
+#pragma unroll
+                for (int g = 0; g < NSMAX / 2; ++g) {
+                    if (2 * g >= n_src) continue;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) S.X2[g][c][k] = make_float2(x[2 * g][c], x[2 * g + 1][c]);
+                }
             }
         }
     }
