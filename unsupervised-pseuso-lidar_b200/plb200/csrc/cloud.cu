@@ -7,15 +7,17 @@
 // (cloud_x >= 0 & cloud_z < 1) are bit-identical to the reference's.
 //
 // Order-preserving compaction in two launches with no inter-block waiting:
-//   (1) validity of every pixel, ONE WARP per 1024-pixel tile (eight 128-bit loads per lane in flight, no shared
-//       memory, no block barrier): cloud_x and cloud_z are affine in the depth, so validity (cloud_x >= 0 &
-//       cloud_z < 1) costs two fp64 FMAs per coordinate whenever the value is further than 1e-8 from its threshold;
-//       only the rare borderline pixel runs the exact chain - the mask stays bit-identical to the reference's.  Out:
-//       the tile's count and its 1024 validity bits (32 words, one per lane);
-//   (2) every tile sums the counts of the tiles before it, reads its validity bits back (the test is not repeated),
-//       compacts (pixel, depth) of its valid pixels in shared memory and evaluates the kept points densely, one per
-//       thread, at their final row-major rank; [0::sparsity] keeps ranks divisible by `sparsity`.  Integer prefix
-//       sums: bitwise repeatable.
+//   (1) cloud_count_kernel - validity of every pixel, ONE WARP per 1024-pixel tile in a rolled loop of eight 128-pixel
+//       groups (the tile prefetched into L2 by one instruction; no shared memory, no block barrier): cloud_x and
+//       cloud_z are affine in the depth, so validity (cloud_x >= 0 & cloud_z < 1) is decided by the sign of an fp32
+//       value whenever that lies beyond a rigorous error bound of its threshold, by two fp64 FMAs per coordinate
+//       otherwise, and only the rare borderline pixel runs the exact chain - the mask stays bit-identical to the
+//       reference's.  Out: the tile's count and its 1024 validity bits (32 words, one per lane);
+//   (2) cloud_write_direct_kernel (no decimation: the default) - a warp per tile walks it 32 pixels at a time, one
+//       pixel per lane: validity bit by shuffle, output row = tile base + rank in the ballot, the exact fp64 chain in
+//       place, one 256-bit store per row; or cloud_write_kernel ([0::sparsity]) - the tile compacts (pixel, depth) of
+//       its valid pixels in shared memory and evaluates the kept ranks densely, one per thread.  Integer prefix sums:
+//       bitwise repeatable.
 #include "common.cuh"
 
 namespace plb {
