@@ -259,24 +259,32 @@ smooth_vec_kernel(const __grid_constant__ plb_smooth_args a, const __grid_consta
 #pragma unroll
         for (int c = 0; c < 4; ++c) { x1ok[c] = colin && x + c <= w - 3; xmok[c] = colin && x + c <= w - 2; }
 
+        // Loads are UNCONDITIONAL, from clamped rows (the value of a row beyond the chunk, or of a lane beyond the image,
+        // is masked when it enters the window, steps later): behind `cond ? load : 0` the compiler loads into temporaries
+        // and copies them into the queue slot at once - a move that waits for the load, one exposed DRAM latency per step.
+        const float4* rowbase = reinterpret_cast<const float4*>(a.disp[s] + img);
+        (void)prow;
         int yload = ystart;
-        auto loadrow = [&]() -> float4 {                          // RAW rows [ystart, ylast]; zeros beyond
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (yload <= ylast && colin) v = __ldg(prow);
-            prow += w4; ++yload;
-            return v;
+        auto loadrow = [&]() -> float4 {                          // RAW rows [ystart, ylast]
+            const int yy = min(yload, ylast);
+            ++yload;
+            return __ldg(rowbase + (size_t)yy * w4);
         };
-        const float4* pold = reinterpret_cast<const float4*>(gbase) + (size_t)ystart * w4;
+        // old gradients (accumulate mode): rows [y0, y1); without a gradient map / without accumulation the disparity
+        // rows stand in as a valid address and the value is dropped at its use
+        const bool use_old = gbase != nullptr && a.accumulate != 0;
+        const float4* oldbase = use_old ? reinterpret_cast<const float4*>(gbase) : rowbase;
         int yold = ystart;
         auto loadold = [&]() -> float4 {
-            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (yold >= y0 && yold < y1 && rmw) v = __ldcg(pold);
-            pold += w4; ++yold;
-            return v;
+            const int yy = min(max(yold, y0), y1 - 1);
+            ++yold;
+            return __ldcg(oldbase + (size_t)yy * w4);
         };
+        (void)rmw;
         // a row in the window: its four converted depths and the first two of the lane to the right
         auto conv = [&](const float4 raw, int y, float (&r)[6]) {
-            r[0] = raw.x; r[1] = raw.y; r[2] = raw.z; r[3] = raw.w;
+            const bool live = colin && y <= ylast;               // (the load was clamped: mask here, where the data has long arrived)
+            r[0] = live ? raw.x : 0.0f; r[1] = live ? raw.y : 0.0f; r[2] = live ? raw.z : 0.0f; r[3] = live ? raw.w : 0.0f;
             if (!(is_depth || !colin || y > ylast)) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -333,7 +341,7 @@ smooth_vec_kernel(const __grid_constant__ plb_smooth_args a, const __grid_consta
                     if (is_logit) gg *= head_chain_from_depth(r0[c], da, db, ha, hb);
                     g[c] = gg;
                 }
-                *pout = make_float4(old.x + g[0], old.y + g[1], old.z + g[2], old.w + g[3]);
+                *pout = use_old ? make_float4(old.x + g[0], old.y + g[1], old.z + g[2], old.w + g[3]) : make_float4(g[0], g[1], g[2], g[3]);
             }
             pout += w4;
             smL_m1 = sm_L3;
@@ -344,15 +352,10 @@ smooth_vec_kernel(const __grid_constant__ plb_smooth_args a, const __grid_consta
         };
         int y = ystart;
 #pragma unroll 1
-        while (y < y1) {
-#pragma unroll
-            for (int k = 0; k < 2 * NQ; ++k) {                    // 6 = lcm of the rotations: no register moves
-                if (y < y1) {                                     // warp-uniform
-                    step(y, q[k % NQ], oq[k % NQ]);
-                    q[k % NQ] = loadrow(); oq[k % NQ] = loadold();
-                    ++y;
-                }
-            }
+        while (true) {                                            // three steps per trip: the queue rotates without moves
+            step(y, q[0], oq[0]); if (++y >= y1) break; q[0] = loadrow(); oq[0] = loadold();
+            step(y, q[1], oq[1]); if (++y >= y1) break; q[1] = loadrow(); oq[1] = loadold();
+            step(y, q[2], oq[2]); if (++y >= y1) break; q[2] = loadrow(); oq[2] = loadold();
         }
         total = (double)(sum1 * c1) + (double)(summ * c2) + (double)(sum3 * c3);
     }
