@@ -456,7 +456,7 @@ edge_main_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
 // Vector form of launch 2 (every width a multiple of 4, 16-byte aligned maps - the KITTI pyramids).  The kernel above
 // evaluates each edge weight twice (once from either end: 24 image loads and four expf per pixel, 288 instructions per
 // pixel, issue-bound).  Here a warp walks DOWN a strip of 120 columns (lanes 1..30 own four adjacent columns each,
-// lanes 0 / 31 are the halo), rows y, y + 1, y + 2 in three register sets that rotate without moves: every lane
+// lanes 0 / 31 are the halo), rows y .. y + 3 in four register sets that rotate without moves: every lane
 // evaluates the x- and y-difference anchored on each of its pixels ONCE - |dd| e into the forward sum, sgn(dd) e kept
 // for the gradient of the pixel itself and (by one shuffle / one row of registers) of its +x / +y neighbour.  One
 // 128-bit load of the disparity and three of the image per four pixels, one 128-bit store; per-warp partials in
@@ -560,14 +560,17 @@ edge_main_vec_kernel(const __grid_constant__ plb_edge_args a, const __grid_const
         for (int c = 0; c < 4; ++c) ty_up[c] = ty[c];
     };
 
-    EdgeRow A, Bq, C;
-    load(A, ystart); load(Bq, ystart + 1); load(C, ystart + 2);
+    // four register sets: a row is loaded two full steps before its first use (with three, one step - ~1000 cycles -
+    // was less than a DRAM round trip under load: the first use of every row held 30 % of the stall samples)
+    EdgeRow A, Bq, C, Dq;
+    load(A, ystart); load(Bq, ystart + 1); load(C, ystart + 2); load(Dq, ystart + 3);
     int y = ystart;
 #pragma unroll 1
     while (true) {
-        step(y, A, Bq); if (++y >= y1) break; load(A, y + 2);
-        step(y, Bq, C); if (++y >= y1) break; load(Bq, y + 2);
-        step(y, C, A); if (++y >= y1) break; load(C, y + 2);
+        step(y, A, Bq); if (++y >= y1) break; load(A, y + 3);
+        step(y, Bq, C); if (++y >= y1) break; load(Bq, y + 3);
+        step(y, C, Dq); if (++y >= y1) break; load(C, y + 3);
+        step(y, Dq, A); if (++y >= y1) break; load(Dq, y + 3);
     }
     // the warp's partials, lanes in a fixed (butterfly) order
     double l = (double)lsum, q = (double)gd;
