@@ -16,6 +16,7 @@ $NCU -k regex:lowres_merge\|smooth -s 4 -c 2 -o $O/r2_aux_c2 python profiles/pro
 $NCU -k regex:photo_min -s 2 -c 1 -o $O/r2_photo_min_c2min python profiles/prof_photo.py c2min 4 > $O/r2_ncu_d.log 2>&1
 $NCU -k regex:cloud_ -s 4 -c 2 -o $O/r2_cloud python profiles/prof_cloud.py > $O/r2_ncu_e.log 2>&1
 $NCU -k regex:velo_ -s 4 -c 2 -o $O/r2_velo python profiles/prof_velo.py > $O/r2_ncu_f.log 2>&1
+$NCU -k regex:edge_ -s 12 -c 6 -o $O/r2_edge python profiles/prof_edge.py > $O/r2_ncu_g.log 2>&1
 python profiles/cloud_kbench.py velo > $O/r2_cloud_kbench.txt 2>&1
 python profiles/kbench.py headline headline64 c1 c2 c3 c5 c2min > $O/r2_kbench.txt 2>&1
 for w in c3 c5 c5e; do python bench.py --workload $w --no-cpu --no-cloud > $O/r2_bench_$w.json 2>> $O/r2_bench_default.err; done

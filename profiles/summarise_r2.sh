@@ -11,7 +11,7 @@ grep -v "^/\|_warn_once" $O/r2_timeline_headline.txt > $R/timeline_headline.txt
 cp $O/r2_kbench.txt $R/kbench.txt
 cp $O/r2_cloud_kbench.txt $R/cloud_kbench.txt
 for w in c3 c5 c5e; do cp $O/r2_bench_$w.json $R/bench_$w.json; done
-for n in r2_photo_l1_c2 r2_photo_l1_headline r2_aux_c2 r2_photo_min_c2min r2_cloud r2_velo; do
+for n in r2_photo_l1_c2 r2_photo_l1_headline r2_aux_c2 r2_photo_min_c2min r2_cloud r2_velo r2_edge; do
   python profiles/ncu_summary.py $O/$n.ncu-rep > $R/$n.summary.txt
 done
 python profiles/ncu_hot.py $O/r2_photo_l1_c2.ncu-rep > $R/r2_photo_l1_c2.opcodes.txt
