@@ -18,8 +18,8 @@
 namespace plb {
 
 constexpr int EG_THREADS = 256;
-constexpr int EG_PX = 4;                       // consecutive pixels per thread: the per-block work (which scale / image am
-constexpr int EG_TILE = EG_THREADS * EG_PX;    // I, image mean, block sums) is amortised over 1024 pixels
+constexpr int EG_PX = 16;                      // pixels per thread: the per-block work (which scale / image am I, block sums)
+constexpr int EG_TILE = EG_THREADS * EG_PX;    // is amortised over 4096 pixels (at 1024 the sum / fix-up launches were issue-bound on it)
 constexpr int EV_OWN = 30 * 4;                 // edge_main_vec_kernel: columns a warp owns (lanes 1..30, four each)
 #ifndef EV_WARPS_PER_SM
 #define EV_WARPS_PER_SM 12                    // the row chunks shrink until the launch has this many warps per SM
@@ -304,16 +304,20 @@ edge_prep_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
     const float inv = 1.0f / (float)(k.f * k.f);
     if ((k.f == 1 || L.tile_pooled[k.s]) && (n & 3) == 0 && ((size_t)a.disp[k.s] & 15) == 0) {
         // nothing to pool here: the block only sums its 1024 disparities - one 128-bit load per thread
-        const int o = (k.o0 - (int)threadIdx.x) + 4 * (int)threadIdx.x;
-        if (o < n) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(disp + o));
-            dsum = (v.x + v.y) + (v.z + v.w);
+        const int o0 = (k.o0 - (int)threadIdx.x) + 4 * (int)threadIdx.x;
+        float4 v[EG_PX / 4];
+#pragma unroll
+        for (int j = 0; j < EG_PX / 4; ++j) {
+            const int o = o0 + j * (4 * EG_THREADS);
+            v[j] = o < n ? __ldg(reinterpret_cast<const float4*>(disp + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int j = 0; j < EG_PX / 4; ++j) dsum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
         const double tot = block_sum((double)dsum, sh);
         if (threadIdx.x == 0) ((double*)((char*)a.workspace + L.part_mean))[blockIdx.x] = tot;
         return;
     }
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < EG_PX; ++j) {
         const int o = k.o0 + j * EG_THREADS;
         if (o < n) {
@@ -404,7 +408,7 @@ edge_main_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant_
                          fabsf(__ldg(img + 2 * n + p) - __ldg(img + 2 * n + q));
         return expf(-gi * (1.0f / 3.0f));
     };
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < EG_PX; ++j) {
         const int o = k.o0 + j * EG_THREADS;
         if (o < n) {
@@ -594,18 +598,22 @@ edge_final_kernel(const __grid_constant__ plb_edge_args a, const __grid_constant
     const float s_c = __ldg((const float*)((const char*)a.workspace + L.img_c) + k.s * a.B + k.b);
     if ((n & 3) == 0 && (((size_t)a.g_scratch[k.s] | (size_t)a.g_disp[k.s]) & 15) == 0) {
         // four consecutive pixels per thread: 128-bit loads and stores
-        const int o = (k.o0 - (int)threadIdx.x) + 4 * (int)threadIdx.x;
-        if (o < n) {
-            const size_t go = (size_t)k.b * n + o;
-            const float4 v = __ldcs(reinterpret_cast<const float4*>(a.g_scratch[k.s] + go));
-            float4 g = make_float4(v.x * s_inv - s_c, v.y * s_inv - s_c, v.z * s_inv - s_c, v.w * s_inv - s_c);
-            float4* out = reinterpret_cast<float4*>(a.g_disp[k.s] + go);
-            if (a.accumulate) { const float4 w = *out; g.x += w.x; g.y += w.y; g.z += w.z; g.w += w.w; }
-            *out = g;
+        const int o0 = (k.o0 - (int)threadIdx.x) + 4 * (int)threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < EG_PX / 4; ++j) {
+            const int o = o0 + j * (4 * EG_THREADS);
+            if (o < n) {
+                const size_t go = (size_t)k.b * n + o;
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(a.g_scratch[k.s] + go));
+                float4 g = make_float4(v.x * s_inv - s_c, v.y * s_inv - s_c, v.z * s_inv - s_c, v.w * s_inv - s_c);
+                float4* out = reinterpret_cast<float4*>(a.g_disp[k.s] + go);
+                if (a.accumulate) { const float4 w = *out; g.x += w.x; g.y += w.y; g.z += w.z; g.w += w.w; }
+                *out = g;
+            }
         }
         return;
     }
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < EG_PX; ++j) {
         const int o = k.o0 + j * EG_THREADS;
         if (o < n) {
