@@ -37,6 +37,7 @@ class CapturedLossStep:
             "disparity": [[clone(d).requires_grad_(True) for d in fr] for fr in pyr],
             "poses": clone(poses).requires_grad_(True), "intrinsics": clone(intrinsics),
         }
+        self._one = torch.ones((), dtype=torch.float32, device=dev)
         self._stream = torch.cuda.Stream(device=dev)
         self._stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self._stream):
@@ -60,7 +61,7 @@ class CapturedLossStep:
         with ops.unit_upstream():
             loss = self.criterion.forward(i["tgt"], i["ref_imgs"], i["disparity"], i["poses"], i["intrinsics"], None)
             total = loss[0] + loss[1]
-            total.backward()
+            total.backward(self._one)                   # a static upstream 1: no fill kernel inside the captured step
         self.total = total.detach()
         return [l.detach() for l in loss]
 
