@@ -352,28 +352,35 @@ class FusedLossFn(torch.autograd.Function):
 
 def _check_loss_shapes(tgt, refs, pyramids, poses, K):
     """The kernels see pointers, not extents: every shape the reference's torch ops would have rejected (or broadcast)
-    is rejected here, before a launch can read or write past a buffer."""
-    if tgt.dim() != 4 or tgt.shape[1] != 3:
-        raise ValueError("tgt must be [B,3,H,W], got %s" % (tuple(tgt.shape),))
-    B, _, H, W = tgt.shape
-    if not 1 <= len(refs) <= _lib.MAX_SRC:
-        raise ValueError("1..%d reference images, got %d" % (_lib.MAX_SRC, len(refs)))
+    is rejected here, before a launch can read or write past a buffer.  (~6 us per call: plain size comparisons.)"""
+    ts = tgt.shape
+    if len(ts) != 4 or ts[1] != 3:
+        raise ValueError("tgt must be [B,3,H,W], got %s" % (tuple(ts),))
+    B = ts[0]
+    n_ref = len(refs)
+    if not 1 <= n_ref <= _lib.MAX_SRC:
+        raise ValueError("1..%d reference images, got %d" % (_lib.MAX_SRC, n_ref))
     for r in refs:
-        if tuple(r.shape) != tuple(tgt.shape):
-            raise ValueError("every reference image must have the target's shape %s, got %s" % (tuple(tgt.shape), tuple(r.shape)))
-    if not 1 <= len(pyramids) <= 1 + len(refs):
-        raise ValueError("1..%d disparity pyramids (target frame first), got %d" % (1 + len(refs), len(pyramids)))
+        if r.shape != ts:
+            raise ValueError("every reference image must have the target's shape %s, got %s" % (tuple(ts), tuple(r.shape)))
+    n_pyr = len(pyramids)
+    if not 1 <= n_pyr <= 1 + n_ref:
+        raise ValueError("1..%d disparity pyramids (target frame first), got %d" % (1 + n_ref, n_pyr))
     for p in pyramids:
         if not 1 <= len(p) <= _lib.MAX_SCALES:
             raise ValueError("1..%d scales per pyramid, got %d" % (_lib.MAX_SCALES, len(p)))
         for d in p:
-            if d.dim() < 3 or d.shape[0] != B or d.numel() != B * d.shape[-2] * d.shape[-1] or d.numel() == 0:
-                raise ValueError("a disparity map must be [%d,1,h,w], got %s" % (B, tuple(d.shape)))
-    n_pose = max(len(refs), len(pyramids) - 1)
-    if poses.dim() != 3 or poses.shape[0] != B or poses.shape[1] < n_pose or poses.shape[2] != 6:
-        raise ValueError("poses must be [%d,>=%d,6], got %s" % (B, n_pose, tuple(poses.shape)))
-    if tuple(K.shape) != (B, 3, 3):
-        raise ValueError("intrinsics must be [%d,3,3], got %s" % (B, tuple(K.shape)))
+            ds = d.shape
+            nd = len(ds)
+            if nd < 3 or ds[0] != B or ds[-1] < 1 or ds[-2] < 1 or (nd == 4 and ds[1] != 1) or nd > 4:
+                raise ValueError("a disparity map must be [%d,1,h,w], got %s" % (B, tuple(ds)))
+    ps = poses.shape
+    n_pose = n_ref if n_ref > n_pyr - 1 else n_pyr - 1
+    if len(ps) != 3 or ps[0] != B or ps[1] < n_pose or ps[2] != 6:
+        raise ValueError("poses must be [%d,>=%d,6], got %s" % (B, n_pose, tuple(ps)))
+    ks = K.shape
+    if len(ks) != 3 or ks[0] != B or ks[1] != 3 or ks[2] != 3:
+        raise ValueError("intrinsics must be [%d,3,3], got %s" % (B, tuple(ks)))
 
 
 def fused_losses(tgt, refs, pyramids, poses, K, binding=None, **cfg_kw):
